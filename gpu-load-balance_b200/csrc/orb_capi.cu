@@ -1,0 +1,839 @@
+// orb_capi.cu — context, per-level orchestration and the extern "C" surface of liborb_b200.so
+// (declared in include/orb_b200.h).  The level loop of orbit.cpp:102-275 runs here with no host
+// round trip per bisection iteration: count -> (NCCL allreduce) -> device-side decision, with the
+// host only polling a mapped status word a bounded number of passes behind the GPU.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+#include "orb_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t rc_ = (call);                                                                          \
+        if (rc_ != cudaSuccess)                                                                            \
+            return fail(ORB_ERR_CUDA, "%s error %d in %s(%d)\n%s", #call, (int)rc_, __FILE__, __LINE__,    \
+                        cudaGetErrorString(rc_));                                                          \
+    } while (0)
+
+// ---- NCCL, resolved at run time so a single-GPU user needs no NCCL at all ----
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && GetErrorString;
+    }
+} g_nccl;
+
+#define NK(call)                                                                                     \
+    do {                                                                                             \
+        ncclResult_t rc_ = (call);                                                                   \
+        if (rc_ != ncclSuccess)                                                                      \
+            return fail(ORB_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(rc_));          \
+    } while (0)
+
+constexpr int kMaxLevels = 40;
+constexpr int kPassSlots = 40;   // >= 32 passes + slack, per level
+
+}  // namespace
+
+struct orb_ctx {
+    int device = 0;
+    int nSM = 148;
+    uint64_t nLocal = 0;
+    uint32_t d = 0;           // leaf cells
+    uint32_t nHeap = 0;       // 2d-1
+    uint32_t maxLevelCells = 0;
+    cudaStream_t stream = nullptr;
+
+    float *x[2] = {nullptr, nullptr}, *y[2] = {nullptr, nullptr}, *z[2] = {nullptr, nullptr};
+    int cur = 0;
+    bool haveParticles = false;
+
+    orb_cell *d_heap = nullptr;       // [nHeap]
+    orb_cell *d_cells = nullptr;      // [maxLevelCells] staging for service-granular calls
+    uint32_t *d_range = nullptr;      // [nHeap*2]
+    uint32_t *d_total = nullptr;      // [nHeap]
+    orb::LevelState lv{};
+    uint32_t *d_cnt_g_buf = nullptr;  // separate allreduce target (multi-rank only)
+    float *d_final_cut = nullptr;     // [maxLevelCells]
+    uint32_t *d_tile_first = nullptr; // [nMapTiles]
+    uint64_t *d_tile_state = nullptr; // [nPartTiles]
+    uint32_t *d_tickets = nullptr;    // [kMaxLevels]
+    uint32_t *d_nactive = nullptr;    // [kMaxLevels*kPassSlots]
+    uint32_t *d_done = nullptr;       // [kMaxLevels*kPassSlots]
+    uint32_t *d_misc = nullptr;       // [0]=n_unfound
+    unsigned long long *d_active_particles = nullptr;
+    int32_t *d_level_iters = nullptr; // [kMaxLevels]
+    int *d_err = nullptr;
+    uint32_t *d_bb = nullptr;         // [maxLevelCells*2*8] encoded boxes
+    float *d_bb6 = nullptr;           // [maxLevelCells*2*6]
+
+    volatile uint32_t *h_status = nullptr;   // pinned+mapped [kMaxLevels*kPassSlots]
+    uint32_t *h_status_dev = nullptr;        // device alias of h_status
+    uint32_t *h_scratch = nullptr;           // pinned scratch for small read-backs
+    size_t h_scratch_bytes = 0;
+
+    uint32_t epoch = 0;
+    int trialDepth = 3;
+    int runAhead = 2;
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evCount, evPart;
+    size_t evCountUsed = 0, evPartUsed = 0;
+
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    bool ownComm = false;
+    int rank = 0, nRanks = 1;
+
+    // launch accounting
+    uint64_t nCountLaunch = 0, nUpdateLaunch = 0, nPartLaunch = 0, nOtherLaunch = 0;
+};
+
+namespace {
+
+inline uint32_t ceil_div(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
+
+int ensure_scratch(orb_ctx *c, size_t bytes) {
+    if (c->h_scratch_bytes >= bytes) return ORB_OK;
+    if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    c->h_scratch = nullptr;
+    c->h_scratch_bytes = 0;
+    CK(cudaMallocHost((void **)&c->h_scratch, bytes));
+    c->h_scratch_bytes = bytes;
+    return ORB_OK;
+}
+
+int check_device_err(orb_ctx *c) {
+    int e = 0;
+    CK(cudaMemcpyAsync(&e, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (e != 0) {
+        CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+        if (e == ORB_ERR_RANGE) return fail(ORB_ERR_RANGE, "cells of the level do not tile [0,n_local) in id order");
+        return fail(e, "invalid cell (cutAxis outside 0..2)");
+    }
+    return ORB_OK;
+}
+
+// ---- level preparation: SoA state + tile map (ServiceCopyCells' role, copyCells.cu:29-61) ----
+int level_prepare(orb_ctx *c, const orb_cell *d_cells, uint32_t nCells, int nc, uint32_t *n_active0) {
+    using namespace orb;
+    if (nCells == 0 || nCells > c->maxLevelCells) return fail(ORB_ERR_ARG, "n_cells %u out of range (max %u)", nCells, c->maxLevelCells);
+    const uint32_t blocks = ceil_div(nCells, 256);
+    k_level_setup<<<blocks, 256, 0, c->stream>>>(d_cells, nCells, c->d_range, c->d_total, c->lv, (uint32_t)c->nLocal, nc, c->d_err);
+    c->nOtherLaunch++;
+    if (n_active0) {
+        // any non-zero value opens the gate of the first pass
+        static const uint32_t one = 1u;
+        CK(cudaMemcpyAsync(n_active0, &one, 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    const uint32_t nMap = ceil_div(c->nLocal, kMapTile);
+    if (nMap) {
+        k_tile_map<<<ceil_div(nMap, 256), 256, 0, c->stream>>>(c->lv.bnd, nCells, nMap, c->d_tile_first);
+        c->nOtherLaunch++;
+    }
+    CK(cudaGetLastError());
+    return ORB_OK;
+}
+
+int launch_count(orb_ctx *c, uint32_t nCells, int nc, const uint32_t *gate) {
+    using namespace orb;
+    const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
+    if (!nTiles) return ORB_OK;
+    const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * 8u);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profile) {
+        if (c->evCountUsed == c->evCount.size()) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            c->evCount.emplace_back(a, b);
+        }
+        e0 = c->evCount[c->evCountUsed].first;
+        e1 = c->evCount[c->evCountUsed].second;
+        c->evCountUsed++;
+        CK(cudaEventRecord(e0, c->stream));
+    }
+    switch (nc) {
+    case 1: k_count<1><<<grid, kThreads, 0, c->stream>>>(c->x[c->cur], c->y[c->cur], c->z[c->cur], c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate); break;
+    case 3: k_count<3><<<grid, kThreads, 0, c->stream>>>(c->x[c->cur], c->y[c->cur], c->z[c->cur], c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate); break;
+    case 7: k_count<7><<<grid, kThreads, 0, c->stream>>>(c->x[c->cur], c->y[c->cur], c->z[c->cur], c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate); break;
+    default: return fail(ORB_ERR_ARG, "unsupported trial count %d", nc);
+    }
+    if (c->profile) CK(cudaEventRecord(e1, c->stream));
+    c->nCountLaunch++;
+    CK(cudaGetLastError());
+    return ORB_OK;
+}
+
+// sum the per-cell counters over ranks (Combine: countLeft.cpp:44-53), in-stream
+int allreduce_counts(orb_ctx *c, uint32_t nCells, int nc) {
+    if (c->nRanks <= 1) return ORB_OK;
+    const size_t n = (size_t)nCells * orb::kCS;
+    (void)nc;
+    NK(g_nccl.AllReduce(c->lv.cnt_l, c->lv.cnt_g, n, ncclUint32, ncclSum, c->comm, c->stream));
+    return ORB_OK;
+}
+
+int launch_update(orb_ctx *c, uint32_t nCells, int M, int passSlot, orb::PassCtl ctl) {
+    using namespace orb;
+    const uint32_t blocks = ceil_div(nCells, kThreads);
+    switch (M) {
+    case 1: k_update<1><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl); break;
+    case 2: k_update<2><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl); break;
+    case 3: k_update<3><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl); break;
+    default: return fail(ORB_ERR_ARG, "unsupported trial depth %d", M);
+    }
+    c->nUpdateLaunch++;
+    CK(cudaGetLastError());
+    return ORB_OK;
+}
+
+inline void cpu_relax() {
+#if defined(__x86_64__)
+    _mm_pause();
+#endif
+}
+
+// Bisection loop of one level (orbit.cpp:146-232).  `slotBase` selects this level's private region of
+// the pass-control arrays (zeroed when the build / call starts).  Returns passes launched.
+int run_bisection(orb_ctx *c, uint32_t nCells, int M, int slotBase, int levelIdx, int *passesOut) {
+    using namespace orb;
+    const int nc = (1 << M) - 1;
+    const int maxPasses = (kMaxIter + M - 1) / M;
+    PassCtl ctl;
+    ctl.n_active = c->d_nactive + slotBase;
+    ctl.done = c->d_done + slotBase;
+    ctl.h_status = (volatile uint32_t *)(c->h_status_dev + slotBase);
+    ctl.active_particles = c->d_active_particles;
+    ctl.level_iters = c->d_level_iters + levelIdx;
+    volatile uint32_t *hs = c->h_status + slotBase;
+    int launched = 0;
+    for (;;) {
+        int rc = launch_count(c, nCells, nc, ctl.n_active + launched);
+        if (rc) return rc;
+        rc = allreduce_counts(c, nCells, nc);
+        if (rc) return rc;
+        rc = launch_update(c, nCells, M, launched, ctl);
+        if (rc) return rc;
+        launched++;
+        if (launched >= maxPasses) break;
+        // Decide deterministically (identically on every rank): look at the status of pass
+        // launched-1-runAhead; stop once a pass reported "no active cells".
+        const int k = launched - 1 - c->runAhead;
+        if (k >= 0) {
+            uint32_t s;
+            while ((s = hs[k]) == 0u) cpu_relax();
+            if (s == 1u) break;
+        }
+    }
+    if (passesOut) *passesOut = launched;
+    return ORB_OK;
+}
+
+// after the loop: cells that hit the iteration cap need one extra count at their final cut
+int finalize_unfound(orb_ctx *c, uint32_t nCells, uint32_t *nUnfoundOut) {
+    using namespace orb;
+    CK(cudaMemsetAsync(c->d_misc, 0, 4, c->stream));
+    k_finalize_prepare<<<ceil_div(nCells, 256), 256, 0, c->stream>>>(c->lv, nCells, c->d_misc);
+    c->nOtherLaunch++;
+    uint32_t n = 0;
+    CK(cudaMemcpyAsync(&n, c->d_misc, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (nUnfoundOut) *nUnfoundOut = n;
+    // every rank sees the same n (found flags derive from global counts), so the collective below matches
+    if (n) {
+        int rc = launch_count(c, nCells, 1, nullptr);
+        if (rc) return rc;
+        rc = allreduce_counts(c, nCells, 1);
+        if (rc) return rc;
+        k_finalize_apply<<<ceil_div(nCells, 256), 256, 0, c->stream>>>(c->lv, nCells);
+        c->nOtherLaunch++;
+    }
+    CK(cudaGetLastError());
+    return ORB_OK;
+}
+
+int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket) {
+    using namespace orb;
+    const uint32_t nTiles = ceil_div(c->nLocal, kPartTile);
+    if (!nTiles) return ORB_OK;
+    c->epoch++;
+    if (c->epoch >= (1u << 30)) {   // epoch field is 30 bits: start over with a clean state array
+        CK(cudaMemsetAsync(c->d_tile_state, 0, (size_t)nTiles * 8, c->stream));
+        c->epoch = 1;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profile) {
+        if (c->evPartUsed == c->evPart.size()) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            c->evPart.emplace_back(a, b);
+        }
+        e0 = c->evPart[c->evPartUsed].first;
+        e1 = c->evPart[c->evPartUsed].second;
+        c->evPartUsed++;
+        CK(cudaEventRecord(e0, c->stream));
+    }
+    const int o = c->cur ^ 1;
+    k_partition<<<nTiles, kThreads, 0, c->stream>>>(c->x[c->cur], c->y[c->cur], c->z[c->cur], c->x[o], c->y[o], c->z[o], c->lv,
+                                                    c->d_final_cut, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles,
+                                                    c->d_tile_state, c->epoch, ticket);
+    if (c->profile) CK(cudaEventRecord(e1, c->stream));
+    c->nPartLaunch++;
+    CK(cudaGetLastError());
+    c->cur = o;
+    return ORB_OK;
+}
+
+int reset_pass_ctl(orb_ctx *c) {
+    CK(cudaMemsetAsync(c->d_nactive, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots, c->stream));
+    CK(cudaMemsetAsync(c->d_done, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots, c->stream));
+    CK(cudaMemsetAsync(c->d_tickets, 0, sizeof(uint32_t) * kMaxLevels, c->stream));
+    CK(cudaMemsetAsync(c->d_level_iters, 0, sizeof(int32_t) * kMaxLevels, c->stream));
+    CK(cudaMemsetAsync(c->d_active_particles, 0, sizeof(unsigned long long), c->stream));
+    // the previous call's speculative passes may still be writing status words: drain first
+    CK(cudaStreamSynchronize(c->stream));
+    memset((void *)c->h_status, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots);
+    return ORB_OK;
+}
+
+int upload_cells(orb_ctx *c, const orb_cell *cells, uint32_t nCells) {
+    if (!cells || nCells == 0 || nCells > c->maxLevelCells) return fail(ORB_ERR_ARG, "bad cell array (n=%u, max %u)", nCells, c->maxLevelCells);
+    for (uint32_t i = 0; i < nCells; ++i)
+        if (cells[i].id < 0 || (uint32_t)cells[i].id >= c->nHeap) return fail(ORB_ERR_ARG, "cell id %d outside heap of %u", cells[i].id, c->nHeap);
+    CK(cudaMemcpyAsync(c->d_cells, cells, (size_t)nCells * sizeof(orb_cell), cudaMemcpyHostToDevice, c->stream));
+    return ORB_OK;
+}
+
+float sum_events(std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &ev, size_t used) {
+    float tot = 0.f;
+    for (size_t i = 0; i < used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev[i].first, ev[i].second) == cudaSuccess) tot += ms;
+    }
+    return tot;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+const char *orb_last_error(void) { return g_err; }
+int orb_version(void) { return 100; }
+
+int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cells) {
+    if (!out) return fail(ORB_ERR_ARG, "null ctx pointer");
+    *out = nullptr;
+    if (n_leaf_cells < 1 || (n_leaf_cells & (n_leaf_cells - 1))) return fail(ORB_ERR_ARG, "n_leaf_cells must be a power of two (orbit.cpp:42)");
+    if (n_local >= (1ull << 32) - orb::kCountTile) return fail(ORB_ERR_ARG, "n_local must fit 32-bit particle indices");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(ORB_ERR_CUDA, "no CUDA device %d (found %d); there is no CPU fallback", device, ndev);
+    CK(cudaSetDevice(device));
+    orb_ctx *c = new orb_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->nSM = prop.multiProcessorCount;
+    c->nLocal = n_local;
+    c->d = n_leaf_cells;
+    c->nHeap = 2 * n_leaf_cells - 1;
+    c->maxLevelCells = std::max<uint32_t>(1u, n_leaf_cells);   // deepest level we may be handed (children of the last split level)
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t nPad = (size_t)n_local + orb::kCountTile;   // tail tiles may be read with vector loads only when fully inside; pad anyway
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaMalloc(&c->x[b], nPad * 4));
+        CK(cudaMalloc(&c->y[b], nPad * 4));
+        CK(cudaMalloc(&c->z[b], nPad * 4));
+    }
+    const size_t L = c->maxLevelCells;
+    CK(cudaMalloc(&c->d_heap, (size_t)c->nHeap * sizeof(orb_cell)));
+    CK(cudaMalloc(&c->d_cells, L * sizeof(orb_cell)));
+    CK(cudaMalloc(&c->d_range, (size_t)c->nHeap * 8));
+    CK(cudaMalloc(&c->d_total, (size_t)c->nHeap * 4));
+    CK(cudaMemset(c->d_range, 0, (size_t)c->nHeap * 8));
+    CK(cudaMemset(c->d_total, 0, (size_t)c->nHeap * 4));
+    CK(cudaMalloc(&c->lv.bnd, (L + 1) * 4));
+    CK(cudaMalloc(&c->lv.axis, L * 4));
+    CK(cudaMalloc(&c->lv.mL, L * 4));
+    CK(cudaMalloc(&c->lv.mR, L * 4));
+    CK(cudaMalloc(&c->lv.total, L * 4));
+    CK(cudaMalloc(&c->lv.nleaf, L * 4));
+    CK(cudaMalloc(&c->lv.active, L * 4));
+    CK(cudaMalloc(&c->lv.found, L * 4));
+    CK(cudaMalloc(&c->lv.iter, L * 4));
+    CK(cudaMalloc(&c->lv.nleft_g, L * 4));
+    CK(cudaMalloc(&c->lv.nleft_l, L * 4));
+    CK(cudaMalloc(&c->lv.cuts, L * orb::kCS * 4));
+    CK(cudaMalloc(&c->lv.cnt_l, L * orb::kCS * 4));
+    c->lv.cnt_g = c->lv.cnt_l;
+    CK(cudaMalloc(&c->d_final_cut, L * 4));
+    const size_t nMap = ceil_div(n_local, orb::kMapTile) + 1;
+    CK(cudaMalloc(&c->d_tile_first, nMap * 4));
+    CK(cudaMalloc(&c->d_tile_state, nMap * 8));
+    CK(cudaMemset(c->d_tile_state, 0, nMap * 8));
+    CK(cudaMalloc(&c->d_tickets, sizeof(uint32_t) * kMaxLevels));
+    CK(cudaMalloc(&c->d_nactive, sizeof(uint32_t) * kMaxLevels * kPassSlots));
+    CK(cudaMalloc(&c->d_done, sizeof(uint32_t) * kMaxLevels * kPassSlots));
+    CK(cudaMalloc(&c->d_misc, 64));
+    CK(cudaMalloc(&c->d_active_particles, 8));
+    CK(cudaMalloc(&c->d_level_iters, sizeof(int32_t) * kMaxLevels));
+    CK(cudaMalloc(&c->d_err, sizeof(int)));
+    CK(cudaMemset(c->d_err, 0, sizeof(int)));
+    CK(cudaMalloc(&c->d_bb, L * 2 * 8 * 4));
+    CK(cudaMalloc(&c->d_bb6, L * 2 * 6 * 4));
+    CK(cudaHostAlloc((void **)&c->h_status, sizeof(uint32_t) * kMaxLevels * kPassSlots, cudaHostAllocMapped));
+    memset((void *)c->h_status, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots);
+    CK(cudaHostGetDevicePointer((void **)&c->h_status_dev, (void *)c->h_status, 0));
+    const char *p = getenv("ORB_PROFILE");
+    c->profile = p && atoi(p) != 0;
+    const char *td = getenv("ORB_TRIAL_DEPTH");
+    if (td && atoi(td) >= 1 && atoi(td) <= 3) c->trialDepth = atoi(td);
+    const char *ra = getenv("ORB_RUN_AHEAD");
+    if (ra && atoi(ra) >= 0 && atoi(ra) <= 8) c->runAhead = atoi(ra);
+    CK(cudaDeviceSynchronize());
+    *out = c;
+    return ORB_OK;
+}
+
+int orb_destroy(orb_ctx *c) {
+    if (!c) return ORB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && c->ownComm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (int b = 0; b < 2; ++b) { cudaFree(c->x[b]); cudaFree(c->y[b]); cudaFree(c->z[b]); }
+    cudaFree(c->d_heap); cudaFree(c->d_cells); cudaFree(c->d_range); cudaFree(c->d_total);
+    cudaFree(c->lv.bnd); cudaFree(c->lv.axis); cudaFree(c->lv.mL); cudaFree(c->lv.mR); cudaFree(c->lv.total);
+    cudaFree(c->lv.nleaf); cudaFree(c->lv.active); cudaFree(c->lv.found); cudaFree(c->lv.iter);
+    cudaFree(c->lv.nleft_g); cudaFree(c->lv.nleft_l); cudaFree(c->lv.cuts); cudaFree(c->lv.cnt_l);
+    if (c->d_cnt_g_buf) cudaFree(c->d_cnt_g_buf);
+    cudaFree(c->d_final_cut); cudaFree(c->d_tile_first); cudaFree(c->d_tile_state); cudaFree(c->d_tickets);
+    cudaFree(c->d_nactive); cudaFree(c->d_done); cudaFree(c->d_misc); cudaFree(c->d_active_particles);
+    cudaFree(c->d_level_iters); cudaFree(c->d_err); cudaFree(c->d_bb); cudaFree(c->d_bb6);
+    cudaFreeHost((void *)c->h_status);
+    if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    for (auto &e : c->evCount) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto &e : c->evPart) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return ORB_OK;
+}
+
+int orb_set_trial_depth(orb_ctx *c, int m) {
+    if (!c) return fail(ORB_ERR_ARG, "null ctx");
+    if (m == 0) m = 3;
+    if (m < 1 || m > 3) return fail(ORB_ERR_ARG, "trial depth must be 1..3");
+    c->trialDepth = m;
+    return ORB_OK;
+}
+
+int orb_set_profile(orb_ctx *c, int on) {
+    if (!c) return fail(ORB_ERR_ARG, "null ctx");
+    c->profile = on != 0;
+    return ORB_OK;
+}
+
+// ---------------------------------------------------------------- multi-GPU
+int orb_comm_unique_id(void *id128) {
+    if (!id128) return fail(ORB_ERR_ARG, "null id buffer");
+    if (!g_nccl.load()) return fail(ORB_ERR_NCCL, "libnccl.so.2 not found: %s", dlerror());
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return ORB_OK;
+}
+
+static int setup_multi(orb_ctx *c) {
+    if (c->nRanks > 1 && !c->d_cnt_g_buf) {
+        CK(cudaMalloc(&c->d_cnt_g_buf, (size_t)c->maxLevelCells * orb::kCS * 4));
+        c->lv.cnt_g = c->d_cnt_g_buf;
+    }
+    return ORB_OK;
+}
+
+int orb_comm_init(orb_ctx *c, const void *id128, int rank, int n_ranks) {
+    if (!c || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ORB_ERR_ARG, "bad communicator arguments");
+    if (!g_nccl.load()) return fail(ORB_ERR_NCCL, "libnccl.so.2 not found: %s", dlerror());
+    CK(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NK(g_nccl.CommInitRank(&c->comm, n_ranks, id, rank));
+    c->ownComm = true;
+    c->rank = rank;
+    c->nRanks = n_ranks;
+    return setup_multi(c);
+}
+
+int orb_comm_attach(orb_ctx *c, void *nccl_comm, int rank, int n_ranks) {
+    if (!c || !nccl_comm || n_ranks < 1) return fail(ORB_ERR_ARG, "bad communicator arguments");
+    if (!g_nccl.load()) return fail(ORB_ERR_NCCL, "libnccl.so.2 not found: %s", dlerror());
+    CK(cudaSetDevice(c->device));
+    c->comm = (ncclComm_t)nccl_comm;
+    c->ownComm = false;
+    c->rank = rank;
+    c->nRanks = n_ranks;
+    return setup_multi(c);
+}
+
+// ---------------------------------------------------------------- particles
+static int set_root_range(orb_ctx *c) {
+    uint32_t r[2] = {0u, (uint32_t)c->nLocal};
+    CK(cudaMemcpyAsync(c->d_range, r, 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->haveParticles = true;
+    return ORB_OK;
+}
+
+int orb_upload_xyz(orb_ctx *c, const float *x, const float *y, const float *z) {
+    if (!c || !x || !y || !z) return fail(ORB_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    c->cur = 0;
+    CK(cudaMemcpyAsync(c->x[0], x, c->nLocal * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->y[0], y, c->nLocal * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->z[0], z, c->nLocal * 4, cudaMemcpyHostToDevice, c->stream));
+    return set_root_range(c);
+}
+
+int orb_load_device_xyz(orb_ctx *c, const float *dx, const float *dy, const float *dz) {
+    if (!c || !dx || !dy || !dz) return fail(ORB_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    c->cur = 0;
+    CK(cudaMemcpyAsync(c->x[0], dx, c->nLocal * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->y[0], dy, c->nLocal * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->z[0], dz, c->nLocal * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return set_root_range(c);
+}
+
+int orb_download_xyz(orb_ctx *c, float *x, float *y, float *z) {
+    if (!c || !x || !y || !z) return fail(ORB_ERR_ARG, "null argument");
+    if (!c->haveParticles) return fail(ORB_ERR_STATE, "no particles uploaded");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(x, c->x[c->cur], c->nLocal * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(y, c->y[c->cur], c->nLocal * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(z, c->z[c->cur], c->nLocal * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ORB_OK;
+}
+
+int orb_device_xyz(orb_ctx *c, const float **dx, const float **dy, const float **dz) {
+    if (!c) return fail(ORB_ERR_ARG, "null ctx");
+    if (dx) *dx = c->x[c->cur];
+    if (dy) *dy = c->y[c->cur];
+    if (dz) *dz = c->z[c->cur];
+    return ORB_OK;
+}
+
+int orb_get_ranges(orb_ctx *c, uint32_t first_id, uint32_t n, uint32_t *out) {
+    if (!c || !out || (uint64_t)first_id + n > c->nHeap) return fail(ORB_ERR_ARG, "range read outside heap");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->d_range + 2 * (size_t)first_id, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ORB_OK;
+}
+
+// ---------------------------------------------------------------- service-granular calls
+int orb_count(orb_ctx *c, const orb_cell *cells, uint32_t n_cells, uint32_t *out) {
+    if (!c || !out) return fail(ORB_ERR_ARG, "null argument");
+    if (!c->haveParticles) return fail(ORB_ERR_STATE, "no particles uploaded");
+    CK(cudaSetDevice(c->device));
+    int rc = upload_cells(c, cells, n_cells);
+    if (rc) return rc;
+    // local sizes come straight from the range map (count.cpp:16); sum over ranks like Combine (count.cpp:21-30)
+    rc = ensure_scratch(c, (size_t)c->nHeap * 8);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->h_scratch, c->d_range, (size_t)c->nHeap * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < n_cells; ++i) out[i] = c->h_scratch[2 * cells[i].id + 1] - c->h_scratch[2 * cells[i].id];
+    if (c->nRanks > 1) {
+        CK(cudaMemcpyAsync(c->lv.cnt_l, out, (size_t)n_cells * 4, cudaMemcpyHostToDevice, c->stream));
+        NK(g_nccl.AllReduce(c->lv.cnt_l, c->lv.cnt_g, n_cells, ncclUint32, ncclSum, c->comm, c->stream));
+        CK(cudaMemcpyAsync(out, c->lv.cnt_g, (size_t)n_cells * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    // remember global totals per id for the fused paths
+    std::vector<uint32_t> tot(c->nHeap, 0u);
+    CK(cudaMemcpyAsync(tot.data(), c->d_total, (size_t)c->nHeap * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < n_cells; ++i) tot[cells[i].id] = out[i];
+    CK(cudaMemcpyAsync(c->d_total, tot.data(), (size_t)c->nHeap * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ORB_OK;
+}
+
+int orb_count_left(orb_ctx *c, const orb_cell *cells, uint32_t n_cells, uint32_t *out) {
+    if (!c || !out) return fail(ORB_ERR_ARG, "null argument");
+    if (!c->haveParticles) return fail(ORB_ERR_STATE, "no particles uploaded");
+    CK(cudaSetDevice(c->device));
+    int rc = upload_cells(c, cells, n_cells);
+    if (rc) return rc;
+    rc = level_prepare(c, c->d_cells, n_cells, 1, nullptr);   // cuts[c] = getCut(c) (cell.h:74-76)
+    if (rc) return rc;
+    rc = launch_count(c, n_cells, 1, nullptr);
+    if (rc) return rc;
+    rc = allreduce_counts(c, n_cells, 1);
+    if (rc) return rc;
+    rc = ensure_scratch(c, (size_t)n_cells * orb::kCS * 4);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->h_scratch, c->lv.cnt_g, (size_t)n_cells * orb::kCS * 4, cudaMemcpyDeviceToHost, c->stream));
+    rc = check_device_err(c);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n_cells; ++i)
+        if (!cells[i].foundCut) out[i] = c->h_scratch[(size_t)i * orb::kCS];   // found cells keep their old entry (countLeft.cpp:19-21)
+    return ORB_OK;
+}
+
+int orb_partition(orb_ctx *c, const orb_cell *cells, uint32_t n_cells) {
+    if (!c) return fail(ORB_ERR_ARG, "null ctx");
+    if (!c->haveParticles) return fail(ORB_ERR_STATE, "no particles uploaded");
+    CK(cudaSetDevice(c->device));
+    int rc = upload_cells(c, cells, n_cells);
+    if (rc) return rc;
+    // count at the final cut of EVERY cell (found or not) to get the split offsets, then scatter
+    std::vector<orb_cell> tmp(cells, cells + n_cells);
+    for (auto &t : tmp) t.foundCut = 0;
+    CK(cudaMemcpyAsync(c->d_cells, tmp.data(), (size_t)n_cells * sizeof(orb_cell), cudaMemcpyHostToDevice, c->stream));
+    rc = level_prepare(c, c->d_cells, n_cells, 1, nullptr);
+    if (rc) return rc;
+    rc = launch_count(c, n_cells, 1, nullptr);
+    if (rc) return rc;
+    rc = allreduce_counts(c, n_cells, 1);
+    if (rc) return rc;
+    orb::k_finalize_apply<<<ceil_div(n_cells, 256), 256, 0, c->stream>>>(c->lv, n_cells);
+    orb::k_ranges_from_level<<<ceil_div(n_cells, 256), 256, 0, c->stream>>>(c->d_cells, n_cells, c->lv, c->d_range, c->d_final_cut);
+    c->nOtherLaunch += 2;
+    CK(cudaMemsetAsync(c->d_tickets, 0, 4, c->stream));
+    rc = launch_partition(c, n_cells, c->d_tickets);
+    if (rc) return rc;
+    return check_device_err(c);
+}
+
+static int bbox_level(orb_ctx *c, const uint32_t *bnd_unused, uint32_t nCells, float *d_out6) {
+    using namespace orb;
+    (void)bnd_unused;
+    k_bbox_init<<<ceil_div((uint64_t)nCells * 8, 256), 256, 0, c->stream>>>(c->d_bb, nCells);
+    const uint32_t nTiles = ceil_div(c->nLocal, kMapTile);
+    if (nTiles) {
+        const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * 8u);
+        k_bbox<<<grid, kThreads, 0, c->stream>>>(c->x[c->cur], c->y[c->cur], c->z[c->cur], c->lv.bnd, c->d_tile_first, nCells,
+                                                 (uint32_t)c->nLocal, nTiles, c->d_bb);
+    }
+    c->nOtherLaunch += 2;
+    if (c->nRanks > 1) {
+        // encoded uint32 boxes: unsigned min / max over ranks (one call each over the interleaved rows would mix
+        // mins and maxes, so reduce twice and let the decode pick the right half)
+        uint32_t *tmp = c->d_bb + (size_t)c->maxLevelCells * 8;   // second half of d_bb (allocated 2x)
+        NK(g_nccl.AllReduce(c->d_bb, tmp, (size_t)nCells * 8, ncclUint32, ncclMax, c->comm, c->stream));
+        NK(g_nccl.AllReduce(c->d_bb, c->d_bb, (size_t)nCells * 8, ncclUint32, ncclMin, c->comm, c->stream));
+        // merge: mins from the Min result (in place), maxes from the Max result
+        CK(cudaMemcpy2DAsync(c->d_bb + 3, 32, tmp + 3, 32, 12, nCells, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    k_bbox_decode<<<ceil_div((uint64_t)nCells * 6, 256), 256, 0, c->stream>>>(c->d_bb, nCells, d_out6);
+    c->nOtherLaunch++;
+    CK(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orb_bbox(orb_ctx *c, const orb_cell *cells, uint32_t n_cells, float *out6) {
+    if (!c || !out6) return fail(ORB_ERR_ARG, "null argument");
+    if (!c->haveParticles) return fail(ORB_ERR_STATE, "no particles uploaded");
+    CK(cudaSetDevice(c->device));
+    if (n_cells > c->maxLevelCells) return fail(ORB_ERR_ARG, "too many cells");
+    int rc = upload_cells(c, cells, n_cells);
+    if (rc) return rc;
+    rc = level_prepare(c, c->d_cells, n_cells, 1, nullptr);
+    if (rc) return rc;
+    rc = bbox_level(c, nullptr, n_cells, c->d_bb6);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out6, c->d_bb6, (size_t)n_cells * 24, cudaMemcpyDeviceToHost, c->stream));
+    return check_device_err(c);
+}
+
+// ---------------------------------------------------------------- fused level
+int orb_find_cuts(orb_ctx *c, orb_cell *cells, uint32_t n_cells, int32_t *iters, int32_t *passes) {
+    if (!c) return fail(ORB_ERR_ARG, "null ctx");
+    if (!c->haveParticles) return fail(ORB_ERR_STATE, "no particles uploaded");
+    CK(cudaSetDevice(c->device));
+    int rc = upload_cells(c, cells, n_cells);
+    if (rc) return rc;
+    rc = reset_pass_ctl(c);
+    if (rc) return rc;
+    const int M = c->trialDepth;
+    rc = level_prepare(c, c->d_cells, n_cells, (1 << M) - 1, c->d_nactive);
+    if (rc) return rc;
+    int np = 0;
+    rc = run_bisection(c, n_cells, M, 0, 0, &np);
+    if (rc) return rc;
+    orb::k_writeback_cells<<<ceil_div(n_cells, 256), 256, 0, c->stream>>>(c->d_cells, c->lv, n_cells);
+    c->nOtherLaunch++;
+    CK(cudaMemcpyAsync(cells, c->d_cells, (size_t)n_cells * sizeof(orb_cell), cudaMemcpyDeviceToHost, c->stream));
+    int32_t it = 0;
+    CK(cudaMemcpyAsync(&it, c->d_level_iters, 4, cudaMemcpyDeviceToHost, c->stream));
+    rc = check_device_err(c);
+    if (rc) return rc;
+    if (iters) *iters = it;
+    if (passes) *passes = np;
+    return ORB_OK;
+}
+
+// ---------------------------------------------------------------- whole build (orbit.cpp:74-275)
+int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *stats) {
+    using namespace orb;
+    if (!c) return fail(ORB_ERR_ARG, "null ctx");
+    if (!c->haveParticles) return fail(ORB_ERR_STATE, "no particles uploaded");
+    CK(cudaSetDevice(c->device));
+    const bool tight = (flags & ORB_TIGHT_BOX) != 0;
+    const int nLevelsRef = (int)std::ceil(std::log2((double)c->d));            // Cell::getNLevels (cell.h:65-67)
+    const int lEnd = (flags & ORB_FULL_LEVELS) ? nLevelsRef + 1 : nLevelsRef;  // orbit.cpp:102
+    if (lEnd - 1 > kMaxLevels) return fail(ORB_ERR_ARG, "too many levels");
+    int rc = reset_pass_ctl(c);
+    if (rc) return rc;
+    c->evCountUsed = c->evPartUsed = 0;
+    const uint64_t l0 = c->nCountLaunch, l1 = c->nUpdateLaunch, l2 = c->nPartLaunch, l3 = c->nOtherLaunch;
+
+    cudaEvent_t evA, evB;
+    CK(cudaEventCreate(&evA));
+    CK(cudaEventCreate(&evB));
+    CK(cudaEventRecord(evA, c->stream));
+
+    // root cell: orbit.cpp:45-46,74-76
+    orb_cell root;
+    memset(&root, 0, sizeof(root));
+    root.id = 0; root.nLeafCells = (int)c->d; root.prevCutAxis = -1; root.cutAxis = 0; root.foundCut = 0;
+    for (int k = 0; k < 3; ++k) { root.lower[k] = -0.5f; root.upper[k] = 0.5f; }
+    root.cutMarginLeft = root.lower[0]; root.cutMarginRight = root.upper[0];
+    CK(cudaMemsetAsync(c->d_heap, 0, (size_t)c->nHeap * sizeof(orb_cell), c->stream));
+    CK(cudaMemcpyAsync(c->d_heap, &root, sizeof(root), cudaMemcpyHostToDevice, c->stream));
+    {   // global particle count of the root (ServiceCount at level 1, count.cpp:16,28)
+        uint32_t n = (uint32_t)c->nLocal;
+        CK(cudaMemcpyAsync(c->d_total, &n, 4, cudaMemcpyHostToDevice, c->stream));
+        if (c->nRanks > 1) NK(g_nccl.AllReduce(c->d_total, c->d_total, 1, ncclUint32, ncclSum, c->comm, c->stream));
+        uint32_t r[2] = {0u, n};
+        CK(cudaMemcpyAsync(c->d_range, r, 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (tight) {   // extension: root box = particle bounding box
+        rc = level_prepare(c, c->d_heap, 1, 1, nullptr);
+        if (rc) return rc;
+        rc = bbox_level(c, nullptr, 1, c->d_bb6);
+        if (rc) return rc;
+        k_apply_bbox<<<1, 32, 0, c->stream>>>(c->d_heap, 1, c->d_bb6, c->d_total);
+        c->nOtherLaunch++;
+    }
+
+    const int M = c->trialDepth;
+    std::vector<int> passes;
+    std::vector<uint32_t> unfound;
+    int nDone = 0;
+    for (int l = 1; l < lEnd; ++l) {
+        const uint32_t first = (1u << (l - 1)) - 1u;   // a = 2^(l-1)-1 (orbit.cpp:104); nCells = 2^(l-1) for d = 2^y
+        const uint32_t nCells = 1u << (l - 1);
+        const int slot = (l - 1) * kPassSlots;
+        rc = level_prepare(c, c->d_heap + first, nCells, (1 << M) - 1, c->d_nactive + slot);
+        if (rc) return rc;
+        int np = 0;
+        rc = run_bisection(c, nCells, M, slot, l - 1, &np);
+        if (rc) return rc;
+        passes.push_back(np);
+        uint32_t nu = 0;
+        // only a level that used every pass can have unfound cells
+        if (np >= (kMaxIter + M - 1) / M) {
+            rc = finalize_unfound(c, nCells, &nu);
+            if (rc) return rc;
+        }
+        unfound.push_back(nu);
+        k_split<<<ceil_div(nCells, 256), 256, 0, c->stream>>>(c->d_heap, first, nCells, c->lv, c->d_range, c->d_total, c->d_final_cut);
+        c->nOtherLaunch++;
+        rc = launch_partition(c, nCells, c->d_tickets + (l - 1));
+        if (rc) return rc;
+        if (tight) {   // children boxes from their particles; needs the children's ranges as a level
+            const uint32_t cf = (1u << l) - 1u, cn = 1u << l;
+            if (cn <= c->maxLevelCells) {
+                rc = level_prepare(c, c->d_heap + cf, cn, 1, nullptr);
+                if (rc) return rc;
+                rc = bbox_level(c, nullptr, cn, c->d_bb6);
+                if (rc) return rc;
+                k_apply_bbox<<<ceil_div(cn, 256), 256, 0, c->stream>>>(c->d_heap + cf, cn, c->d_bb6, c->d_total);
+                c->nOtherLaunch++;
+            }
+        }
+        nDone = l;
+    }
+    CK(cudaEventRecord(evB, c->stream));
+    if (heap_out) CK(cudaMemcpyAsync(heap_out, c->d_heap, (size_t)c->nHeap * sizeof(orb_cell), cudaMemcpyDeviceToHost, c->stream));
+    int32_t iters[kMaxLevels];
+    unsigned long long ap = 0;
+    CK(cudaMemcpyAsync(iters, c->d_level_iters, sizeof(iters), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&ap, c->d_active_particles, 8, cudaMemcpyDeviceToHost, c->stream));
+    rc = check_device_err(c);
+    if (rc) return rc;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->n_levels = nDone;
+        for (int l = 0; l < nDone && l < 64; ++l) {
+            stats->iters[l] = iters[l];
+            stats->passes[l] = passes[l];
+            stats->not_found[l] = (int32_t)unfound[l];
+        }
+        stats->active_passes = ap;
+        stats->count_launches = c->nCountLaunch - l0;
+        stats->update_launches = c->nUpdateLaunch - l1;
+        stats->partition_launches = c->nPartLaunch - l2;
+        stats->other_launches = c->nOtherLaunch - l3;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evA, evB);
+        stats->ms_total = ms;
+        if (c->profile) {
+            stats->ms_count = sum_events(c->evCount, c->evCountUsed);
+            stats->ms_partition = sum_events(c->evPart, c->evPartUsed);
+        }
+    }
+    cudaEventDestroy(evA);
+    cudaEventDestroy(evB);
+    return ORB_OK;
+}
+
+}  // extern "C"
