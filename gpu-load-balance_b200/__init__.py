@@ -56,6 +56,7 @@ class BuildStats(C.Structure):
         ("passes", C.c_int32 * 64),
         ("not_found", C.c_int32 * 64),
         ("active_passes", C.c_uint64),
+        ("iter_particle_passes", C.c_uint64),
         ("count_launches", C.c_uint64),
         ("update_launches", C.c_uint64),
         ("partition_launches", C.c_uint64),
@@ -73,6 +74,7 @@ class BuildStats(C.Structure):
             "passes": list(self.passes[:n]),
             "not_found": list(self.not_found[:n]),
             "active_passes": int(self.active_passes),
+            "iter_particle_passes": int(self.iter_particle_passes),
             "count_launches": int(self.count_launches),
             "update_launches": int(self.update_launches),
             "partition_launches": int(self.partition_launches),

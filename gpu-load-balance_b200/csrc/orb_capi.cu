@@ -333,7 +333,7 @@ int reset_pass_ctl(orb_ctx *c) {
     CK(cudaMemsetAsync(c->d_done, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots, c->stream));
     CK(cudaMemsetAsync(c->d_tickets, 0, sizeof(uint32_t) * kMaxLevels, c->stream));
     CK(cudaMemsetAsync(c->d_level_iters, 0, sizeof(int32_t) * kMaxLevels, c->stream));
-    CK(cudaMemsetAsync(c->d_active_particles, 0, sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->d_active_particles, 0, 2 * sizeof(unsigned long long), c->stream));
     // the previous call's speculative passes may still be writing status words: drain first
     CK(cudaStreamSynchronize(c->stream));
     memset((void *)c->h_status, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots);
@@ -420,7 +420,7 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaMalloc(&c->d_nactive, sizeof(uint32_t) * kMaxLevels * kPassSlots));
     CK(cudaMalloc(&c->d_done, sizeof(uint32_t) * kMaxLevels * kPassSlots));
     CK(cudaMalloc(&c->d_misc, 64));
-    CK(cudaMalloc(&c->d_active_particles, 8));
+    CK(cudaMalloc(&c->d_active_particles, 16));
     CK(cudaMalloc(&c->d_level_iters, sizeof(int32_t) * kMaxLevels));
     CK(cudaMalloc(&c->d_err, sizeof(int)));
     CK(cudaMemset(c->d_err, 0, sizeof(int)));
@@ -730,15 +730,14 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
     const int nLevelsRef = (int)std::ceil(std::log2((double)c->d));            // Cell::getNLevels (cell.h:65-67)
     const int lEnd = (flags & ORB_FULL_LEVELS) ? nLevelsRef + 1 : nLevelsRef;  // orbit.cpp:102
     if (lEnd - 1 > kMaxLevels) return fail(ORB_ERR_ARG, "too many levels");
+    cudaEvent_t evA, evB;
+    CK(cudaEventCreate(&evA));
+    CK(cudaEventCreate(&evB));
+    CK(cudaEventRecord(evA, c->stream));   // the build's clock starts before any of its bookkeeping
     int rc = reset_pass_ctl(c);
     if (rc) return rc;
     c->evCountUsed = c->evPartUsed = 0;
     const uint64_t l0 = c->nCountLaunch, l1 = c->nUpdateLaunch, l2 = c->nPartLaunch, l3 = c->nOtherLaunch;
-
-    cudaEvent_t evA, evB;
-    CK(cudaEventCreate(&evA));
-    CK(cudaEventCreate(&evB));
-    CK(cudaEventRecord(evA, c->stream));
 
     // root cell: orbit.cpp:45-46,74-76
     orb_cell root;
@@ -805,9 +804,9 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
     CK(cudaEventRecord(evB, c->stream));
     if (heap_out) CK(cudaMemcpyAsync(heap_out, c->d_heap, (size_t)c->nHeap * sizeof(orb_cell), cudaMemcpyDeviceToHost, c->stream));
     int32_t iters[kMaxLevels];
-    unsigned long long ap = 0;
+    unsigned long long ap[2] = {0, 0};
     CK(cudaMemcpyAsync(iters, c->d_level_iters, sizeof(iters), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(&ap, c->d_active_particles, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(ap, c->d_active_particles, 16, cudaMemcpyDeviceToHost, c->stream));
     rc = check_device_err(c);
     if (rc) return rc;
     if (stats) {
@@ -818,7 +817,8 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             stats->passes[l] = passes[l];
             stats->not_found[l] = (int32_t)unfound[l];
         }
-        stats->active_passes = ap;
+        stats->active_passes = ap[0];
+        stats->iter_particle_passes = ap[1];
         stats->count_launches = c->nCountLaunch - l0;
         stats->update_launches = c->nUpdateLaunch - l1;
         stats->partition_launches = c->nPartLaunch - l2;

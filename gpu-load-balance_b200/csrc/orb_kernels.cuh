@@ -276,7 +276,8 @@ struct PassCtl {
     uint32_t *n_active;        // device: [maxPasses+2] active cells after pass p (index p+1); [0] = before first pass
     uint32_t *done;            // device: [maxPasses+2] block tickets
     volatile uint32_t *h_status;   // pinned host: [maxPasses+2] n_active+1 after pass p (0 = not yet known)
-    unsigned long long *active_particles;   // device: sum of local particles in cells active during counted passes
+    unsigned long long *active_particles;   // device: [0] local particles streamed (cells active in a pass, per HBM pass)
+                                            //         [1] the same weighted by bisection iterations consumed (reference-equivalent)
     int32_t *level_iters;      // device: max iterations over cells (the reference's j)
 };
 
@@ -285,17 +286,18 @@ __global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCe
     constexpr int NC = (1 << M) - 1;
     const uint32_t gate = ctl.n_active[pass];
     __shared__ uint32_t s_n;
-    __shared__ unsigned long long s_p;
+    __shared__ unsigned long long s_p, s_q;
     __shared__ int s_it;
-    if (threadIdx.x == 0) { s_n = 0; s_p = 0ull; s_it = 0; }
+    if (threadIdx.x == 0) { s_n = 0; s_p = 0ull; s_q = 0ull; s_it = 0; }
     __syncthreads();
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t still = 0;
-    unsigned long long npart = 0;
+    unsigned long long npart = 0, nipart = 0;
     int it = 0;
     if (gate != 0u && c < nCells && lv.active[c]) {
         float L = lv.mL[c], R = lv.mR[c];
         it = lv.iter[c];
+        const int it0 = it;
         const uint32_t total = lv.total[c];
         const int nleaf = lv.nleaf[c];
         const float ratio = (float)(ceil(nleaf / 2.0) / nleaf);          // orbit.cpp:204
@@ -319,6 +321,7 @@ __global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCe
             if (it >= kMaxIter) break;                                                // orbit.cpp:149
         }
         lv.mL[c] = L; lv.mR[c] = R; lv.iter[c] = it;
+        nipart = npart * (unsigned long long)(it - it0);
         if (fnd) { lv.found[c] = 1u; lv.active[c] = 0u; }
         else if (it >= kMaxIter) { lv.active[c] = 0u; }
         else {
@@ -339,16 +342,21 @@ __global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCe
     // block -> grid reduction of (cells still active, particles streamed this pass, max iterations)
     uint32_t wn = __reduce_add_sync(0xffffffffu, still);
     int wit = __reduce_max_sync(0xffffffffu, it);
-    for (int o = 16; o; o >>= 1) npart += __shfl_xor_sync(0xffffffffu, npart, o);
+    for (int o = 16; o; o >>= 1) {
+        npart += __shfl_xor_sync(0xffffffffu, npart, o);
+        nipart += __shfl_xor_sync(0xffffffffu, nipart, o);
+    }
     if ((threadIdx.x & 31) == 0) {
         if (wn) atomicAdd(&s_n, wn);
         if (npart) atomicAdd(&s_p, npart);
+        if (nipart) atomicAdd(&s_q, nipart);
         if (wit) atomicMax(&s_it, wit);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_n) atomicAdd(&ctl.n_active[pass + 1], s_n);
         if (s_p) atomicAdd(ctl.active_particles, s_p);
+        if (s_q) atomicAdd(ctl.active_particles + 1, s_q);
         if (s_it) atomicMax(ctl.level_iters, s_it);
         __threadfence();
         uint32_t ticket = atomicAdd(&ctl.done[pass], 1u);

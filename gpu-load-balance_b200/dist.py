@@ -1,0 +1,43 @@
+"""Host-side plumbing for the one-process-per-GPU launch (torchrun): which slice of the single
+particle stream a rank owns, how the NCCL unique id reaches every rank, and device-timed max-over-ranks.
+torch.distributed is plumbing only; the data-path collective (per-cell count allreduce) is NCCL inside
+liborb_b200.so.  Works with the gloo backend on CPU (tests/test_dist_gloo.py) and nccl on GPUs."""
+from __future__ import annotations
+
+import os
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def shard_slice(rank: int, world: int, n_local: int):
+    """Rank r owns particles [r*n_local, (r+1)*n_local) of the single generator stream — the reference's
+    static per-thread shards (orbit.cpp:83: N/Threads particles per thread, never migrated)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank outside world")
+    return rank * n_local, (rank + 1) * n_local
+
+
+def broadcast_bytes(payload: bytes | None, nbytes: int, src: int = 0, device="cpu") -> bytes:
+    """Send `nbytes` raw bytes from rank `src` to every rank (used for the 128-byte NCCL unique id)."""
+    import torch
+    import torch.distributed as dist
+
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    if dist.get_rank() == src:
+        assert payload is not None and len(payload) == nbytes
+        buf.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(buf, src)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def reduce_scalar(value: float, op: str = "max", device="cpu") -> float:
+    """max / sum of a scalar over ranks (timings: max; work counters: sum)."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+    return float(t.item())

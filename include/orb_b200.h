@@ -57,7 +57,9 @@ typedef struct orb_build_stats {
     int32_t iters[64];           /* bisection iterations per level (the reference's j, orbit.cpp:149) */
     int32_t passes[64];          /* HBM count passes per level (each evaluates up to 2^m-1 trial cuts) */
     int32_t not_found[64];       /* cells that hit the 32-iteration cap */
-    uint64_t active_passes;      /* sum over passes of local particles in active cells ("particle-passes") */
+    uint64_t active_passes;      /* sum over HBM count passes of local particles in active cells (4 B each streamed) */
+    uint64_t iter_particle_passes; /* the same weighted by bisection iterations: the reference-equivalent
+                                      "particle-passes" (what orbit.cpp's loop would have streamed) */
     uint64_t count_launches;     /* kernel launches by category (this rank) */
     uint64_t update_launches;
     uint64_t partition_launches;

@@ -33,6 +33,8 @@ bool g_dumpParticles = false;
 int g_nParticles = 0;
 std::chrono::steady_clock::time_point g_tInitDone, g_tLast;
 bool g_haveInit = false;
+std::vector<unsigned> g_levelCounts;          // last ServiceCount output (global particles per cell)
+unsigned long long g_particlePasses = 0;      // sum over count-left calls of particles in unfound cells
 
 inline uint64_t mix64(uint64_t v) {   // splitmix64 finaliser
     v ^= v >> 30; v *= 0xbf58476d1ce4e5b9ULL;
@@ -83,9 +85,16 @@ void tap(mdl::mdlClass *mdl, int sid, int nIn, void *pIn, void *pOut, int /*nOut
         }
         return;
     }
-    if (!g_trace) return;
     uint32_t nCells = (uint32_t)(nIn / sizeof(Cell));
     const Cell *cells = static_cast<const Cell *>(pIn);
+    // cheap bookkeeping for the CPU-baseline throughput figure (no trace file needed)
+    if (sid == PST_COUNT) {
+        g_levelCounts.assign(static_cast<unsigned *>(pOut), static_cast<unsigned *>(pOut) + nCells);
+    } else if (sid == PST_COUNTLEFT || sid == PST_COUNTLEFTGPU || sid == PST_COUNTLEFTAXISGPU) {
+        for (uint32_t c = 0; c < nCells && c < g_levelCounts.size(); ++c)
+            if (!cells[c].foundCut) g_particlePasses += g_levelCounts[c];
+    }
+    if (!g_trace) return;
     switch (sid) {
     case PST_COUNT:
     case PST_COUNTLEFT:
@@ -148,6 +157,7 @@ struct Installer {
             // (the reference starts its own clocks after Init too, orbit.cpp:85-87)
             long long us = std::chrono::duration_cast<std::chrono::microseconds>(g_tLast - g_tInitDone).count();
             std::fprintf(stderr, "RefBuildWall-us, %lld\n", us);
+            std::fprintf(stderr, "RefParticlePasses, %llu\n", g_particlePasses);
         }
     }
 } g_installer;
