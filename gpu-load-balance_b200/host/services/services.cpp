@@ -1,0 +1,157 @@
+// services.cpp — Service()/Combine() bodies: thin calls into the C ABI (include/orb_b200.h).
+#include "services.h"
+
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+static_assert(std::is_trivial<ServiceInit::input>() && std::is_trivial<ServiceCount::input>() &&
+                  std::is_trivial<ServiceBBox::output>() && std::is_trivial<ServiceBuild::input>() &&
+                  std::is_trivial<ServiceDump::input>(),
+              "service wire types travel by memcpy");
+static_assert(sizeof(Cell) == sizeof(orb_cell), "Cell and orb_cell are the same 52-byte record");
+
+namespace {
+inline const orb_cell *asOrb(const void *cells) { return static_cast<const orb_cell *>(cells); }
+inline orb_cell *asOrb(void *cells) { return static_cast<orb_cell *>(cells); }
+
+// one NCCL id per launch, made by whichever rank thread arrives first
+std::once_flag g_idOnce;
+unsigned char g_ncclId[128];
+}  // namespace
+
+// ------------------------------------------------------------------ Init (init.cu:27-144)
+int ServiceInit::Service(PST pst, void *vin, int, void *, int) {
+    LocalData *lcl = pst->lcl;
+    const input in = *static_cast<input *>(vin);
+    lcl->rank = mdlSelf(pst->mdl);
+    lcl->nRanks = mdlThreads(pst->mdl);
+    lcl->nParticles = in.nParticles;
+    lcl->nLeafCells = in.d;
+    lcl->firstParticle = (unsigned long long)lcl->rank * (unsigned long long)in.nParticles;
+    lcl->x.resize(in.nParticles);
+    lcl->y.resize(in.nParticles);
+    lcl->z.resize(in.nParticles);
+    // deterministic slice of the single xorshf96 stream (the reference's generator state is a racy
+    // file-scope static, init.cu:11, so its multi-thread runs are not reproducible; this is)
+    const char *dist = std::getenv("ORB_DIST");
+    if (dist && std::string(dist) == "gaussian") orb_generate_clustered(0, lcl->firstParticle, in.nParticles, lcl->x.data(), lcl->y.data(), lcl->z.data());
+    else if (dist && std::string(dist) == "plummer") orb_generate_clustered(1, lcl->firstParticle, in.nParticles, lcl->x.data(), lcl->y.data(), lcl->z.data());
+    else orb_generate_uniform(lcl->firstParticle, in.nParticles, lcl->x.data(), lcl->y.data(), lcl->z.data());
+    ORB_CHECK(orb_create(&lcl->ctx, lcl->rank, (uint64_t)in.nParticles, (uint32_t)in.d));
+    if (lcl->nRanks > 1) {
+        std::call_once(g_idOnce, [] { ORB_CHECK(orb_comm_unique_id(g_ncclId)); });
+        ORB_CHECK(orb_comm_init(lcl->ctx, g_ncclId, lcl->rank, lcl->nRanks));
+    }
+    return 0;
+}
+int ServiceInit::Combine(void *, void *, int, int, int) { return 0; }
+
+// ------------------------------------------------------------------ CopyParticles (copyParticles.cu:29-57)
+int ServiceCopyParticles::Service(PST pst, void *, int, void *, int) {
+    LocalData *lcl = pst->lcl;
+    ORB_CHECK(orb_upload_xyz(lcl->ctx, lcl->x.data(), lcl->y.data(), lcl->z.data()));
+    return 0;
+}
+int ServiceCopyParticles::Combine(void *, void *, int, int, int) { return 0; }
+
+// ------------------------------------------------------------------ CopyCells (copyCells.cu:10-64): nothing to stage
+int ServiceCopyCells::Service(PST, void *, int, void *, int) { return 0; }
+int ServiceCopyCells::Combine(void *, void *, int, int, int) { return 0; }
+
+// ------------------------------------------------------------------ Count (count.cpp:8-30)
+int ServiceCount::Service(PST pst, void *vin, int nIn, void *vout, int) {
+    const unsigned nCells = nIn / sizeof(input);
+    ORB_CHECK(orb_count(pst->lcl->ctx, asOrb(vin), nCells, static_cast<output *>(vout)));
+    return nCells * sizeof(output);
+}
+int ServiceCount::Combine(void *, void *, int nIn, int, int) { return (nIn / sizeof(input)) * sizeof(output); }
+
+// ------------------------------------------------------------------ CountLeft on the GPU (countLeftGPU.cu:80-162, countLeftGPUAxis.cu:188-259)
+int ServiceCountLeftGPU::Service(PST pst, void *vin, int nIn, void *vout, int) {
+    const unsigned nCells = nIn / sizeof(input);
+    ORB_CHECK(orb_count_left(pst->lcl->ctx, asOrb(vin), nCells, static_cast<output *>(vout)));
+    return nCells * sizeof(output);
+}
+int ServiceCountLeftGPU::Combine(void *, void *, int nIn, int, int) { return (nIn / sizeof(input)) * sizeof(output); }
+
+int ServiceCountLeftGPUAxis::Service(PST pst, void *vin, int nIn, void *vout, int) {
+    const unsigned nCells = nIn / sizeof(input);
+    ORB_CHECK(orb_count_left(pst->lcl->ctx, asOrb(vin), nCells, static_cast<output *>(vout)));
+    return nCells * sizeof(output);
+}
+int ServiceCountLeftGPUAxis::Combine(void *, void *, int nIn, int, int) { return (nIn / sizeof(input)) * sizeof(output); }
+
+// ------------------------------------------------------------------ Partition on the GPU (partitionGPU.cu:283-527)
+int ServicePartitionGPU::Service(PST pst, void *vin, int nIn, void *, int) {
+    ORB_CHECK(orb_partition(pst->lcl->ctx, asOrb(vin), nIn / sizeof(input)));
+    return 0;
+}
+int ServicePartitionGPU::Combine(void *, void *, int, int, int) { return 0; }
+
+// ------------------------------------------------------------------ Finalize (finalize.cu:15-45)
+int ServiceFinalize::Service(PST pst, void *, int, void *, int) {
+    LocalData *lcl = pst->lcl;
+    if (lcl->ctx) {
+        // leave the partitioned particles in host memory, where the reference's CPU partition leaves them
+        ORB_CHECK(orb_download_xyz(lcl->ctx, lcl->x.data(), lcl->y.data(), lcl->z.data()));
+        ORB_CHECK(orb_destroy(lcl->ctx));
+        lcl->ctx = nullptr;
+    }
+    return 0;
+}
+int ServiceFinalize::Combine(void *, void *, int, int, int) { return 0; }
+
+// ------------------------------------------------------------------ BBox (new)
+int ServiceBBox::Service(PST pst, void *vin, int nIn, void *vout, int) {
+    const unsigned nCells = nIn / sizeof(input);
+    ORB_CHECK(orb_bbox(pst->lcl->ctx, asOrb(vin), nCells, static_cast<float *>(vout)));
+    return nCells * sizeof(output);
+}
+int ServiceBBox::Combine(void *, void *, int nIn, int, int) { return (nIn / sizeof(input)) * sizeof(output); }
+
+// ------------------------------------------------------------------ FindCuts (new)
+int ServiceFindCuts::Service(PST pst, void *vin, int nIn, void *vout, int) {
+    const unsigned nCells = nIn / sizeof(input);
+    std::memcpy(vout, vin, (size_t)nCells * sizeof(Cell));
+    ORB_CHECK(orb_find_cuts(pst->lcl->ctx, asOrb(vout), nCells, nullptr, nullptr));
+    return nCells * sizeof(output);
+}
+int ServiceFindCuts::Combine(void *, void *, int nIn, int, int) { return (nIn / sizeof(input)) * sizeof(output); }
+
+// ------------------------------------------------------------------ Build (new)
+int ServiceBuild::Service(PST pst, void *vin, int, void *vout, int) {
+    const input in = *static_cast<input *>(vin);
+    LocalData *lcl = pst->lcl;
+    // every rank computes the identical heap (replicated tree); only rank 0 copies it out
+    orb_cell *heap = (lcl->rank == 0) ? reinterpret_cast<orb_cell *>(in.heapOut) : nullptr;
+    ORB_CHECK(orb_build(lcl->ctx, in.flags, heap, static_cast<output *>(vout)));
+    return sizeof(output);
+}
+int ServiceBuild::Combine(void *, void *, int, int, int) { return sizeof(output); }
+
+// ------------------------------------------------------------------ Dump (new; parity harness)
+// file "<path>.<rank>": u32 nHeap, u32 nParticles, ranges[nHeap][2], x[n], y[n], z[n] (device order)
+int ServiceDump::Service(PST pst, void *vin, int, void *, int) {
+    LocalData *lcl = pst->lcl;
+    const input *in = static_cast<input *>(vin);
+    const unsigned nHeap = 2u * (unsigned)lcl->nLeafCells - 1u, n = (unsigned)lcl->nParticles;
+    std::vector<uint32_t> rng((size_t)nHeap * 2);
+    std::vector<float> x(n), y(n), z(n);
+    ORB_CHECK(orb_get_ranges(lcl->ctx, 0, nHeap, rng.data()));
+    ORB_CHECK(orb_download_xyz(lcl->ctx, x.data(), y.data(), z.data()));
+    const std::string path = std::string(in->path) + "." + std::to_string(lcl->rank);
+    FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) { std::perror(path.c_str()); std::exit(1); }
+    std::fwrite(&nHeap, 4, 1, f);
+    std::fwrite(&n, 4, 1, f);
+    std::fwrite(rng.data(), 4, rng.size(), f);
+    std::fwrite(x.data(), 4, n, f);
+    std::fwrite(y.data(), 4, n, f);
+    std::fwrite(z.data(), 4, n, f);
+    std::fclose(f);
+    return 0;
+}
+int ServiceDump::Combine(void *, void *, int, int, int) { return 0; }

@@ -1,0 +1,81 @@
+"""GPU tests of the C++ host driver `orbit <x> <y> <o>` (same CLI/stdout as the reference): every mode
+must leave exactly the oracle's tree, ranges and particle order; multi-rank runs (thread per GPU + NCCL)
+must give the same cells as one rank."""
+import os
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+ORBIT = ROOT / "gpu-load-balance_b200" / "host" / "orbit"
+
+
+def run_orbit(x, y, o, tmp_path, threads=1, env_extra=None):
+    subprocess.run(["make", "-C", str(ORBIT.parent)], check=True, capture_output=True)
+    env = dict(os.environ, ORB_MDL_THREADS=str(threads), ORB_DUMP=str(tmp_path / "dump"))
+    env.update(env_extra or {})
+    r = subprocess.run([str(ORBIT), str(x), str(y), str(o)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def read_dump(tmp_path, oracle, rank=0):
+    heap = np.fromfile(tmp_path / "dump.heap", dtype=oracle.CELL_DTYPE)
+    raw = (tmp_path / f"dump.{rank}").read_bytes()
+    n_heap, n = np.frombuffer(raw, "<u4", 2)
+    off = 8
+    rng = np.frombuffer(raw, "<u4", n_heap * 2, off).reshape(n_heap, 2); off += n_heap * 8
+    x = np.frombuffer(raw, "<f4", n, off); off += 4 * n
+    y = np.frombuffer(raw, "<f4", n, off); off += 4 * n
+    z = np.frombuffer(raw, "<f4", n, off)
+    return heap, rng, x, y, z
+
+
+@pytest.mark.parametrize("o", [0, 1, 2])
+@pytest.mark.parametrize("x,y", [(16, 6), (18, 9)])
+def test_orbit_modes_match_oracle(oracle, tmp_path, x, y, o):
+    out = run_orbit(x, y, o, tmp_path)
+    # the three reference stdout lines (orbit.cpp:284-286)
+    assert re.search(rf"^CountCopy-{x}-{y}, \d+ $", out, re.M)
+    assert re.search(rf"^Partition-{x}-{y}, \d+ $", out, re.M)
+    assert re.search(rf"^MakeAxis-{x}-{y}, 0 $", out, re.M)
+    heap, rng, gx, gy, gz = read_dump(tmp_path, oracle)
+    xs, ys, zs = oracle.generate_uniform(1 << x)
+    ref = oracle.build(xs, ys, zs, 1 << y, ties=oracle.TIES_CANONICAL)
+    assert heap.tobytes() == ref["heap"].tobytes()
+    assert np.array_equal(rng, ref["ranges"][0])
+    assert np.array_equal(gx.view(np.uint32), ref["x"].view(np.uint32))
+    assert np.array_equal(gy.view(np.uint32), ref["y"].view(np.uint32))
+    assert np.array_equal(gz.view(np.uint32), ref["z"].view(np.uint32))
+
+
+def test_orbit_full_levels_env(oracle, tmp_path):
+    run_orbit(15, 5, 0, tmp_path, env_extra={"ORB_FULL_LEVELS": "1"})
+    heap, rng, *_ = read_dump(tmp_path, oracle)
+    xs, ys, zs = oracle.generate_uniform(1 << 15)
+    ref = oracle.build(xs, ys, zs, 1 << 5, ties=oracle.TIES_CANONICAL, full_levels=True)
+    assert heap.tobytes() == ref["heap"].tobytes()
+    assert np.array_equal(rng, ref["ranges"][0])
+
+
+@pytest.mark.parametrize("o", [0, 1, 2])
+def test_orbit_two_ranks_match_sharded_oracle(oracle, tmp_path, o):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    x, y, R = 17, 7, 2
+    run_orbit(x, y, o, tmp_path, threads=R)
+    xs, ys, zs = oracle.generate_uniform(1 << x)
+    ref = oracle.build(xs, ys, zs, 1 << y, ties=oracle.TIES_CANONICAL, n_shards=R)
+    heap = np.fromfile(tmp_path / "dump.heap", dtype=oracle.CELL_DTYPE)
+    assert heap.tobytes() == ref["heap"].tobytes()
+    per = (1 << x) // R
+    for r in range(R):
+        _, rng, gx, gy, gz = read_dump(tmp_path, oracle, r)
+        assert np.array_equal(rng, ref["ranges"][r])
+        assert np.array_equal(gx.view(np.uint32), ref["x"][r * per:(r + 1) * per].view(np.uint32))
