@@ -98,7 +98,7 @@ struct orb_ctx {
     uint32_t *d_cnt_g_buf = nullptr;  // separate allreduce target (multi-rank only)
     float *d_final_cut = nullptr;     // [maxLevelCells]
     uint32_t *d_tile_first = nullptr; // [nMapTiles]
-    uint64_t *d_tile_state = nullptr; // [nPartTiles]
+    uint32_t *d_blk_left = nullptr, *d_blk_restart = nullptr;   // [resident blocks] partition phase-1 records
     uint32_t *d_tickets = nullptr;    // [kMaxLevels]
     uint32_t *d_nactive = nullptr;    // [kMaxLevels*kPassSlots]
     uint32_t *d_done = nullptr;       // [kMaxLevels*kPassSlots]
@@ -114,7 +114,7 @@ struct orb_ctx {
     uint32_t *h_scratch = nullptr;           // pinned scratch for small read-backs
     size_t h_scratch_bytes = 0;
 
-    uint32_t epoch = 0;
+    int occPartStream = 1, occPartCells = 1;   // resident blocks per SM of the partition kernels
     int trialDepth = 3;
     int runAhead = 2;
     bool profile = false;
@@ -177,11 +177,32 @@ int level_prepare(orb_ctx *c, const orb_cell *d_cells, uint32_t nCells, int nc, 
     return ORB_OK;
 }
 
+// Count pass over all active cells of the level.  Kernel choice by average local cell size:
+//   >= 16 tiles   : k_count_stream (persistent, tile streaming, one atomic per block per (cell,cut))
+//   >= 1024       : k_count_cells, one block per cell
+//   otherwise     : k_count_cells, one warp per cell
+template <int NC>
+int launch_count_nc(orb_ctx *c, uint32_t nCells, const uint32_t *gate) {
+    using namespace orb;
+    const uint64_t avg = c->nLocal / nCells;
+    const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
+    if (avg >= 16ull * kCountTile) {
+        const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
+        const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * 4u);
+        k_count_stream<NC><<<grid, kThreads, 0, c->stream>>>(x, y, z, c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate);
+    } else if (avg >= 1024) {
+        const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * 4u);
+        k_count_cells<NC, 256><<<grid, kThreads, 0, c->stream>>>(x, y, z, c->lv, nCells, gate);
+    } else {
+        const uint32_t grid = std::min<uint32_t>(ceil_div(nCells, kWarps), (uint32_t)c->nSM * 4u);
+        k_count_cells<NC, 32><<<grid, kThreads, 0, c->stream>>>(x, y, z, c->lv, nCells, gate);
+    }
+    return ORB_OK;
+}
+
 int launch_count(orb_ctx *c, uint32_t nCells, int nc, const uint32_t *gate) {
     using namespace orb;
-    const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
-    if (!nTiles) return ORB_OK;
-    const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * 8u);
+    if (!c->nLocal) return ORB_OK;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->profile) {
         if (c->evCountUsed == c->evCount.size()) {
@@ -196,9 +217,9 @@ int launch_count(orb_ctx *c, uint32_t nCells, int nc, const uint32_t *gate) {
         CK(cudaEventRecord(e0, c->stream));
     }
     switch (nc) {
-    case 1: k_count<1><<<grid, kThreads, 0, c->stream>>>(c->x[c->cur], c->y[c->cur], c->z[c->cur], c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate); break;
-    case 3: k_count<3><<<grid, kThreads, 0, c->stream>>>(c->x[c->cur], c->y[c->cur], c->z[c->cur], c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate); break;
-    case 7: k_count<7><<<grid, kThreads, 0, c->stream>>>(c->x[c->cur], c->y[c->cur], c->z[c->cur], c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate); break;
+    case 1: launch_count_nc<1>(c, nCells, gate); break;
+    case 3: launch_count_nc<3>(c, nCells, gate); break;
+    case 7: launch_count_nc<7>(c, nCells, gate); break;
     default: return fail(ORB_ERR_ARG, "unsupported trial count %d", nc);
     }
     if (c->profile) CK(cudaEventRecord(e1, c->stream));
@@ -295,15 +316,14 @@ int finalize_unfound(orb_ctx *c, uint32_t nCells, uint32_t *nUnfoundOut) {
     return ORB_OK;
 }
 
+// Stable split of every cell of the level (canonical tie mode).  Kernel choice by average local cell size:
+// cells of at most 16 tiles (and enough of them to fill the GPU) -> one block per cell with a running carry;
+// otherwise persistent tile streaming with decoupled look-back (cooperative launch: all blocks co-resident).
 int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket) {
     using namespace orb;
+    (void)ticket;
     const uint32_t nTiles = ceil_div(c->nLocal, kPartTile);
     if (!nTiles) return ORB_OK;
-    c->epoch++;
-    if (c->epoch >= (1u << 30)) {   // epoch field is 30 bits: start over with a clean state array
-        CK(cudaMemsetAsync(c->d_tile_state, 0, (size_t)nTiles * 8, c->stream));
-        c->epoch = 1;
-    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->profile) {
         if (c->evPartUsed == c->evPart.size()) {
@@ -318,9 +338,21 @@ int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket) {
         CK(cudaEventRecord(e0, c->stream));
     }
     const int o = c->cur ^ 1;
-    k_partition<<<nTiles, kThreads, 0, c->stream>>>(c->x[c->cur], c->y[c->cur], c->z[c->cur], c->x[o], c->y[o], c->z[o], c->lv,
-                                                    c->d_final_cut, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles,
-                                                    c->d_tile_state, c->epoch, ticket);
+    const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
+    float *x2 = c->x[o], *y2 = c->y[o], *z2 = c->z[o];
+    const uint64_t avg = c->nLocal / nCells;
+    const size_t smem = sizeof(PartSmem);
+    if (avg <= 16ull * kPartTile && nCells >= 2u * (uint32_t)c->nSM) {
+        const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)c->occPartCells);
+        k_partition_cells<<<grid, kThreads, smem, c->stream>>>(x, y, z, x2, y2, z2, c->lv, c->d_final_cut, nCells, (uint32_t)c->nLocal);
+    } else {
+        const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)c->occPartStream);
+        uint32_t nLocal32 = (uint32_t)c->nLocal, nT = nTiles, nC = nCells;
+        void *args[] = {(void *)&x, (void *)&y, (void *)&z, (void *)&x2, (void *)&y2, (void *)&z2, (void *)&c->lv,
+                        (void *)&c->d_final_cut, (void *)&c->d_tile_first, (void *)&nC, (void *)&nLocal32, (void *)&nT,
+                        (void *)&c->d_blk_left, (void *)&c->d_blk_restart};
+        CK(cudaLaunchCooperativeKernel((const void *)k_partition_coop, dim3(grid), dim3(kThreads), args, smem, c->stream));
+    }
     if (c->profile) CK(cudaEventRecord(e1, c->stream));
     c->nPartLaunch++;
     CK(cudaGetLastError());
@@ -414,8 +446,8 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaMalloc(&c->d_final_cut, L * 4));
     const size_t nMap = ceil_div(n_local, orb::kMapTile) + 1;
     CK(cudaMalloc(&c->d_tile_first, nMap * 4));
-    CK(cudaMalloc(&c->d_tile_state, nMap * 8));
-    CK(cudaMemset(c->d_tile_state, 0, nMap * 8));
+    CK(cudaMalloc(&c->d_blk_left, sizeof(uint32_t) * 64 * (size_t)c->nSM));
+    CK(cudaMalloc(&c->d_blk_restart, sizeof(uint32_t) * 64 * (size_t)c->nSM));
     CK(cudaMalloc(&c->d_tickets, sizeof(uint32_t) * kMaxLevels));
     CK(cudaMalloc(&c->d_nactive, sizeof(uint32_t) * kMaxLevels * kPassSlots));
     CK(cudaMalloc(&c->d_done, sizeof(uint32_t) * kMaxLevels * kPassSlots));
@@ -429,6 +461,11 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaHostAlloc((void **)&c->h_status, sizeof(uint32_t) * kMaxLevels * kPassSlots, cudaHostAllocMapped));
     memset((void *)c->h_status, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots);
     CK(cudaHostGetDevicePointer((void **)&c->h_status_dev, (void *)c->h_status, 0));
+    CK(cudaFuncSetAttribute(orb::k_partition_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(orb::PartSmem)));
+    CK(cudaFuncSetAttribute(orb::k_partition_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(orb::PartSmem)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occPartStream, orb::k_partition_coop, orb::kThreads, sizeof(orb::PartSmem)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occPartCells, orb::k_partition_cells, orb::kThreads, sizeof(orb::PartSmem)));
+    if (c->occPartStream < 1 || c->occPartCells < 1) return fail(ORB_ERR_CUDA, "partition kernels do not fit on this device");
     const char *p = getenv("ORB_PROFILE");
     c->profile = p && atoi(p) != 0;
     const char *td = getenv("ORB_TRIAL_DEPTH");
@@ -451,7 +488,7 @@ int orb_destroy(orb_ctx *c) {
     cudaFree(c->lv.nleaf); cudaFree(c->lv.active); cudaFree(c->lv.found); cudaFree(c->lv.iter);
     cudaFree(c->lv.nleft_g); cudaFree(c->lv.nleft_l); cudaFree(c->lv.cuts); cudaFree(c->lv.cnt_l);
     if (c->d_cnt_g_buf) cudaFree(c->d_cnt_g_buf);
-    cudaFree(c->d_final_cut); cudaFree(c->d_tile_first); cudaFree(c->d_tile_state); cudaFree(c->d_tickets);
+    cudaFree(c->d_final_cut); cudaFree(c->d_tile_first); cudaFree(c->d_blk_left); cudaFree(c->d_blk_restart); cudaFree(c->d_tickets);
     cudaFree(c->d_nactive); cudaFree(c->d_done); cudaFree(c->d_misc); cudaFree(c->d_active_particles);
     cudaFree(c->d_level_iters); cudaFree(c->d_err); cudaFree(c->d_bb); cudaFree(c->d_bb6);
     cudaFreeHost((void *)c->h_status);

@@ -19,6 +19,7 @@
 //   k_bbox         per-cell min/max of x,y,z (north-star extension).  12 B / particle
 //   k_level_setup, k_tile_map, k_split, k_finalize_*  O(nCells) bookkeeping.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/orb_b200.h"
@@ -128,143 +129,405 @@ __global__ void k_tile_map(const uint32_t *__restrict__ bnd, uint32_t nCells, ui
 // =====================================================================================
 // Count-left: replaces reduce3/reduce (countLeftGPUAxis.cu:133-186, countLeftGPU.cu:21-78)
 // with the CPU comparison `x < cut` (countLeft.cpp:35).
+//
+// Two kernels, chosen per level by the average cell size (see launch_count in orb_capi.cu):
+//   k_count_stream  cells much larger than a tile: persistent blocks stream 16 KB tiles, counters persist in
+//                   registers across tiles of one cell, warp REDUX -> shared -> ONE global atomic per block per
+//                   (cell, cut);
+//   k_count_cells   small cells: one block or one warp owns a cell and stores its counts (no atomics).
+//
+// NC = 7 (three bisection steps per pass): the seven cuts form a sorted binary tree, so each particle
+// is binned with a 3-compare descent (3 FSETP + 4 FSEL) and the bin is added to two packed 4x8-bit
+// accumulators; 12 instructions per particle instead of 7 compare+add pairs.  Bins are turned into the
+// per-cut cumulative counts `#{x < cut_k}` at flush time.  Sorted order of the heap-ordered cuts:
+// c3 <= c1 <= c4 <= c0 <= c5 <= c2 <= c6 (float midpoints are monotone, so the order is non-strict but
+// never violated; equal cuts only leave bins empty).
 // =====================================================================================
+// heap node -> number of sorted bins at or below it (cumulative index): node k gets bins [0 .. kSortedRank[k]]
+__device__ __constant__ int kSortedRank7[7] = {3, 1, 5, 0, 2, 4, 6};
+
 template <int NC>
-__device__ __forceinline__ void count4(const float4 v, const float (&cv)[NC], unsigned (&cnt)[NC]) {
+__device__ __forceinline__ void count_vals(const float (&v)[4], const bool (&in)[4], const float (&cv)[NC], unsigned (&cnt)[NC],
+                                           unsigned &lo, unsigned &hi) {
+    if constexpr (NC == 7) {
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        cnt[k] += (v.x < cv[k]);
-        cnt[k] += (v.y < cv[k]);
-        cnt[k] += (v.z < cv[k]);
-        cnt[k] += (v.w < cv[k]);
+        for (int j = 0; j < 4; ++j) {
+            const float x = v[j];
+            const bool p0 = x < cv[0];
+            const float a = p0 ? cv[1] : cv[2];
+            const bool p1 = x < a;
+            const float t = p1 ? cv[3] : cv[4];
+            const float u = p1 ? cv[5] : cv[6];
+            const float b = p0 ? t : u;
+            const bool p2 = x < b;
+            // sorted bin s = 4*!p0 + 2*!p1 + !p2 ; packed increment 1 << (8*(s&3)) into lo (s<4) or hi
+            const unsigned w0 = p2 ? 0x1u : 0x100u;
+            const unsigned w1 = p2 ? 0x10000u : 0x1000000u;
+            unsigned inc = p1 ? w0 : w1;
+            if (!in[j]) inc = 0u;
+            lo += p0 ? inc : 0u;
+            hi += p0 ? 0u : inc;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NC; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cnt[k] += (in[j] && v[j] < cv[k]);
     }
 }
 
 template <int NC>
-__global__ void __launch_bounds__(kThreads, 4) k_count(const float *__restrict__ x, const float *__restrict__ y,
-                                                    const float *__restrict__ z, LevelState lv,
-                                                    const uint32_t *__restrict__ tile_first, uint32_t nCells,
-                                                    uint32_t nLocal, uint32_t nTiles,
-                                                    const uint32_t *__restrict__ gate) {
-    if (gate && *gate == 0u) return;   // speculative pass after convergence: nothing to do
-    __shared__ uint32_t s_acc[NC];
-    __shared__ uint32_t s_cell[kCountCellsSmem * NC];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < NC) s_acc[tid] = 0u;
-    __syncthreads();
+__device__ __forceinline__ void count_f4(const float4 q, const float (&cv)[NC], unsigned (&cnt)[NC], unsigned &lo, unsigned &hi) {
+    const float v[4] = {q.x, q.y, q.z, q.w};
+    const bool in[4] = {true, true, true, true};
+    count_vals<NC>(v, in, cv, cnt, lo, hi);
+}
 
-    unsigned cnt[NC];
+// NC==7: fold the packed 8-bit bins into the eight 32-bit bin counters (call at least every 255 particles per thread)
+__device__ __forceinline__ void unpack_bins(unsigned &lo, unsigned &hi, unsigned (&bin)[8]) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        bin[s] += (lo >> (8 * s)) & 0xffu;
+        bin[4 + s] += (hi >> (8 * s)) & 0xffu;
+    }
+    lo = 0u;
+    hi = 0u;
+}
+
+// ---- shared pieces of the count kernels -------------------------------------------------------------
+// per-thread accumulators: NC < 7 -> one counter per cut; NC == 7 -> eight sorted bins (+ packed lo/hi)
+template <int NC>
+struct Acc {
+    static constexpr int NB = (NC == 7) ? 8 : NC;
+    unsigned a[NB];
+    unsigned lo, hi;
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int k = 0; k < NB; ++k) a[k] = 0u;
+        lo = hi = 0u;
+    }
+    __device__ __forceinline__ void add_f4(const float4 q, const float (&cv)[NC]) {
+        const float v[4] = {q.x, q.y, q.z, q.w};
+        const bool in[4] = {true, true, true, true};
+        unsigned dummy[NC];
+        if constexpr (NC == 7) count_vals<NC>(v, in, cv, dummy, lo, hi);
+        else count_vals<NC>(v, in, cv, a, lo, hi);
+    }
+    __device__ __forceinline__ void add_masked(const float (&v)[4], const bool (&in)[4], const float (&cv)[NC]) {
+        unsigned dummy[NC];
+        if constexpr (NC == 7) count_vals<NC>(v, in, cv, dummy, lo, hi);
+        else count_vals<NC>(v, in, cv, a, lo, hi);
+    }
+    // NC == 7: call at least every 255 particles per thread
+    __device__ __forceinline__ void fold() {
+        if constexpr (NC == 7) unpack_bins(lo, hi, a);
+    }
+};
+
+// cumulative count `#{x < cut_k}` for heap node k from the eight sorted bins
+__device__ __forceinline__ unsigned cum_from_bins(const unsigned *bins, int k) {
+    unsigned v = 0u;
+    const int r = kSortedRank7[k];
+    for (int i = 0; i <= r; ++i) v += bins[i];
+    return v;
+}
+
+// Fragmented tile [t0,t1): several cells.  Per-warp 128-particle segments, shared per-cell accumulators,
+// one global atomic per (cell, cut) per tile.  Block-uniform call (contains barriers).
+template <int NC>
+__device__ __forceinline__ void count_fragmented_tile(const float *__restrict__ x, const float *__restrict__ y,
+                                                      const float *__restrict__ z, const LevelState &lv, uint32_t nCells,
+                                                      uint32_t cT, uint32_t t0, uint32_t t1, uint32_t *s_cell) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kCountCellsSmem * NC; i += kThreads) s_cell[i] = 0u;
+    __syncthreads();
+    for (uint32_t seg = t0 + warp * 128u; seg < t1; seg += kWarps * 128u) {
+        const uint32_t segEnd = min(seg + 128u, t1);
+        uint32_t cc = cT;
+        while (lv.bnd[cc + 1] <= seg) ++cc;
+        const uint32_t e0 = seg + lane * 4u;
+        while (cc < nCells) {
+            const uint32_t b = lv.bnd[cc], e = lv.bnd[cc + 1];
+            if (b >= segEnd) break;
+            const uint32_t lo_e = max(b, seg), hi_e = min(e, segEnd);
+            if (hi_e > lo_e && lv.active[cc]) {
+                const float *cl = pick_col(lv.axis[cc], x, y, z);
+                float v[4];
+                bool in[4];
+                if (e0 >= lo_e && e0 + 4u <= hi_e) {
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(cl + e0));
+                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                    in[0] = in[1] = in[2] = in[3] = true;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t ee = e0 + j;
+                        in[j] = (ee >= lo_e && ee < hi_e);
+                        v[j] = in[j] ? __ldg(cl + ee) : 0.f;
+                    }
+                }
+                float ccv[NC];
+#pragma unroll
+                for (int k = 0; k < NC; ++k) ccv[k] = lv.cuts[cc * kCS + k];
+                unsigned n[NC];
+#pragma unroll
+                for (int k = 0; k < NC; ++k) n[k] = 0u;
+                if constexpr (NC == 7) {
+                    // <=128 particles per warp segment: packed 8-bit bins survive the warp sum
+                    unsigned plo = 0u, phi = 0u;
+                    count_vals<NC>(v, in, ccv, n, plo, phi);
+                    plo = __reduce_add_sync(0xffffffffu, plo);
+                    phi = __reduce_add_sync(0xffffffffu, phi);
+                    unsigned run = 0u, cum[8];
+#pragma unroll
+                    for (int sIdx = 0; sIdx < 4; ++sIdx) { run += (plo >> (8 * sIdx)) & 0xffu; cum[sIdx] = run; }
+#pragma unroll
+                    for (int sIdx = 0; sIdx < 4; ++sIdx) { run += (phi >> (8 * sIdx)) & 0xffu; cum[4 + sIdx] = run; }
+                    n[0] = cum[3]; n[1] = cum[1]; n[2] = cum[5]; n[3] = cum[0]; n[4] = cum[2]; n[5] = cum[4]; n[6] = cum[6];
+                } else {
+                    unsigned dlo = 0u, dhi = 0u;
+                    count_vals<NC>(v, in, ccv, n, dlo, dhi);
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) n[k] = __reduce_add_sync(0xffffffffu, n[k]);
+                }
+                if (lane == 0) {
+                    const uint32_t j = cc - cT;
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        if (!n[k]) continue;
+                        if (j < (uint32_t)kCountCellsSmem) atomicAdd(&s_cell[j * NC + k], n[k]);
+                        else atomicAdd(&lv.cnt_l[cc * kCS + k], n[k]);
+                    }
+                }
+            }
+            if (e > segEnd) break;
+            ++cc;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < kCountCellsSmem * NC; i += kThreads) {
+        const unsigned v = s_cell[i];
+        if (v) atomicAdd(&lv.cnt_l[(cT + i / NC) * kCS + (i % NC)], v);
+    }
+    __syncthreads();
+}
+
+// ---- regime A: cells much larger than a tile.  Persistent blocks, tile u = blockIdx + i*grid. ------------
+// Phase 1: every thread classifies one of the block's tiles (cell, stream / skip / fragmented) - two
+// memory latencies for the whole block instead of a dependent chain per tile.  Phase 2: the streamable
+// tiles run through a register double buffer (the next tile's four 128-bit loads are issued before the
+// current tile is counted); counters persist across tiles of one cell.
+constexpr int kMaxUnits = 256;   // tiles classified per round (one per thread)
+template <int NC>
+__global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__restrict__ x, const float *__restrict__ y,
+                                                              const float *__restrict__ z, LevelState lv,
+                                                              const uint32_t *__restrict__ tile_first, uint32_t nCells,
+                                                              uint32_t nLocal, uint32_t nTiles,
+                                                              const uint32_t *__restrict__ gate) {
+    if (gate && *gate == 0u) return;   // speculative pass after convergence: nothing to do
+    constexpr int NB = Acc<NC>::NB;
+    __shared__ uint32_t s_acc[NB];
+    __shared__ uint32_t s_cell[kCountCellsSmem * NC];
+    __shared__ uint32_t s_uTile[kMaxUnits], s_uCell[kMaxUnits];   // compacted streamable tiles
+    __shared__ int s_uAx[kMaxUnits];
+    __shared__ uint32_t s_fTile[kMaxUnits], s_fCell[kMaxUnits];   // fragmented tiles
+    __shared__ uint32_t s_wS[kWarps], s_wF[kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < NB) s_acc[tid] = 0u;
+
+    Acc<NC> acc;
+    acc.clear();
     float cv[NC];
 #pragma unroll
-    for (int k = 0; k < NC; ++k) { cnt[k] = 0u; cv[k] = 0.f; }
+    for (int k = 0; k < NC; ++k) cv[k] = 0.f;
     int cur = -1;
-    const float *col = x;
 
-    // one global atomic per block per (cell, cut): warp REDUX -> shared -> global
-    auto flush = [&]() {
+    auto flush = [&]() {   // block-uniform
         if (cur < 0) return;
+        acc.fold();
 #pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            unsigned v = __reduce_add_sync(0xffffffffu, cnt[k]);
+        for (int k = 0; k < NB; ++k) {
+            const unsigned v = __reduce_add_sync(0xffffffffu, acc.a[k]);
             if (lane == 0 && v) atomicAdd(&s_acc[k], v);
-            cnt[k] = 0u;
+            acc.a[k] = 0u;
         }
         __syncthreads();
         if (tid < NC) {
-            unsigned v = s_acc[tid];
+            unsigned v;
+            if constexpr (NC == 7) v = cum_from_bins(s_acc, tid);
+            else v = s_acc[tid];
             if (v) atomicAdd(&lv.cnt_l[(uint32_t)cur * kCS + tid], v);
-            s_acc[tid] = 0u;
         }
+        __syncthreads();
+        if (tid < NB) s_acc[tid] = 0u;
         __syncthreads();
     };
 
-    for (uint32_t t = blockIdx.x; t < nTiles; t += gridDim.x) {
-        const uint32_t t0 = t * (uint32_t)kCountTile;
-        const uint32_t t1 = min(t0 + (uint32_t)kCountTile, nLocal);
-        const uint32_t c = tile_first[t * (kCountTile / kMapTile)];
-        const uint32_t cb = lv.bnd[c], ce = lv.bnd[c + 1];
-        if (cb <= t0 && ce >= t1) {
-            // ---- tile inside one cell (block-uniform branch) ----
-            if (!lv.active[c]) continue;
-            if ((int)c != cur) {
-                flush();
-                cur = (int)c;
+    for (uint32_t base = blockIdx.x; base < nTiles; base += gridDim.x * (uint32_t)kMaxUnits) {
+        // ---- phase 1: classify up to 256 tiles of this block ----
+        const uint32_t t = base + (uint32_t)tid * gridDim.x;
+        int kind = 0;   // 0 none/skip, 1 stream, 2 fragmented
+        uint32_t c = 0;
+        int ax = 0;
+        if (t < nTiles) {
+            const uint32_t t0 = t * (uint32_t)kCountTile, t1 = min(t0 + (uint32_t)kCountTile, nLocal);
+            c = tile_first[t * (kCountTile / kMapTile)];
+            const uint32_t cb = lv.bnd[c], ce = lv.bnd[c + 1];
+            ax = lv.axis[c];
+            if (cb <= t0 && ce >= t1 && (t1 - t0) == (uint32_t)kCountTile) kind = lv.active[c] ? 1 : 0;
+            else kind = 2;
+        }
+        const unsigned mS = __ballot_sync(0xffffffffu, kind == 1), mF = __ballot_sync(0xffffffffu, kind == 2);
+        if (lane == 0) { s_wS[warp] = __popc(mS); s_wF[warp] = __popc(mF); }
+        __syncthreads();
+        uint32_t offS = 0, offF = 0, nS = 0, nF = 0;
 #pragma unroll
-                for (int k = 0; k < NC; ++k) cv[k] = lv.cuts[c * kCS + k];
-                col = pick_col(lv.axis[c], x, y, z);
+        for (int w = 0; w < kWarps; ++w) {
+            if (w < warp) { offS += s_wS[w]; offF += s_wF[w]; }
+            nS += s_wS[w]; nF += s_wF[w];
+        }
+        const unsigned ltMask = (1u << lane) - 1u;
+        if (kind == 1) { const uint32_t r = offS + __popc(mS & ltMask); s_uTile[r] = t; s_uCell[r] = c; s_uAx[r] = ax; }
+        if (kind == 2) { const uint32_t r = offF + __popc(mF & ltMask); s_fTile[r] = t; s_fCell[r] = c; }
+        __syncthreads();
+
+        // ---- phase 2a: streamable tiles, software-pipelined ----
+        if (nS) {
+            float4 q0, q1, q2, q3;
+            uint32_t cNext = s_uCell[0];
+            {
+                const float4 *p = reinterpret_cast<const float4 *>(pick_col(s_uAx[0], x, y, z) + s_uTile[0] * (uint32_t)kCountTile) + tid;
+                q0 = __ldg(p); q1 = __ldg(p + kThreads); q2 = __ldg(p + 2 * kThreads); q3 = __ldg(p + 3 * kThreads);
             }
-            if (t1 - t0 == (uint32_t)kCountTile) {
-                const float4 *p = reinterpret_cast<const float4 *>(col + t0) + tid;
-                float4 v0 = __ldg(p), v1 = __ldg(p + kThreads), v2 = __ldg(p + 2 * kThreads), v3 = __ldg(p + 3 * kThreads);
-                count4<NC>(v0, cv, cnt);
-                count4<NC>(v1, cv, cnt);
-                count4<NC>(v2, cv, cnt);
-                count4<NC>(v3, cv, cnt);
-            } else {
-                for (uint32_t e = t0 + tid; e < t1; e += kThreads) {
-                    float v = __ldg(col + e);
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) cnt[k] += (v < cv[k]);
+            for (uint32_t k = 0; k < nS; ++k) {
+                const uint32_t cK = cNext;
+                float4 n0 = q0, n1 = q1, n2 = q2, n3 = q3;
+                if (k + 1 < nS) {   // issue the next tile's loads before counting this one
+                    cNext = s_uCell[k + 1];
+                    const float4 *p = reinterpret_cast<const float4 *>(pick_col(s_uAx[k + 1], x, y, z) + s_uTile[k + 1] * (uint32_t)kCountTile) + tid;
+                    n0 = __ldg(p); n1 = __ldg(p + kThreads); n2 = __ldg(p + 2 * kThreads); n3 = __ldg(p + 3 * kThreads);
                 }
+                if ((int)cK != cur) {
+                    flush();
+                    cur = (int)cK;
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) cv[j] = lv.cuts[cK * kCS + j];
+                }
+                acc.add_f4(q0, cv); acc.add_f4(q1, cv); acc.add_f4(q2, cv); acc.add_f4(q3, cv);
+                if ((k & 7u) == 7u) acc.fold();   // 16 particles per tile per thread: fold before 255
+                q0 = n0; q1 = n1; q2 = n2; q3 = n3;
             }
-        } else {
-            // ---- fragmented tile: several cells; per-warp 128-element chunks ----
+            acc.fold();
+        }
+        // ---- phase 2b: fragmented tiles (cell boundaries, array tail) ----
+        if (nF) {
             flush();
             cur = -1;
-            for (int i = tid; i < kCountCellsSmem * NC; i += kThreads) s_cell[i] = 0u;
-            __syncthreads();
-            for (uint32_t chunk = t0 + warp * 128u; chunk < t1; chunk += kWarps * 128u) {
-                const uint32_t cend = min(chunk + 128u, t1);
-                uint32_t cc = c;
-                while (lv.bnd[cc + 1] <= chunk) ++cc;
-                const uint32_t e0 = chunk + lane * 4u;
-                while (cc < nCells) {
-                    const uint32_t b = lv.bnd[cc], e = lv.bnd[cc + 1];
-                    if (b >= cend) break;
-                    const uint32_t lo = max(b, chunk), hi = min(e, cend);
-                    if (hi > lo && lv.active[cc]) {
-                        const float *cl = pick_col(lv.axis[cc], x, y, z);
-                        float v[4];
-                        bool in[4];
-                        if (e0 >= lo && e0 + 4u <= hi) {
-                            float4 q = __ldg(reinterpret_cast<const float4 *>(cl + e0));
-                            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-                            in[0] = in[1] = in[2] = in[3] = true;
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint32_t ee = e0 + j;
-                                in[j] = (ee >= lo && ee < hi);
-                                v[j] = in[j] ? __ldg(cl + ee) : 0.f;
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < NC; ++k) {
-                            float ck = lv.cuts[cc * kCS + k];
-                            unsigned n = 0;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) n += (in[j] && v[j] < ck);
-                            n = __reduce_add_sync(0xffffffffu, n);
-                            if (lane == 0 && n) {
-                                uint32_t j = cc - c;
-                                if (j < (uint32_t)kCountCellsSmem) atomicAdd(&s_cell[j * NC + k], n);
-                                else atomicAdd(&lv.cnt_l[cc * kCS + k], n);
-                            }
-                        }
-                    }
-                    if (e > cend) break;
-                    ++cc;
-                }
+            for (uint32_t k = 0; k < nF; ++k) {
+                const uint32_t tt = s_fTile[k];
+                const uint32_t t0 = tt * (uint32_t)kCountTile, t1 = min(t0 + (uint32_t)kCountTile, nLocal);
+                count_fragmented_tile<NC>(x, y, z, lv, nCells, s_fCell[k], t0, t1, s_cell);
             }
-            __syncthreads();
-            for (int i = tid; i < kCountCellsSmem * NC; i += kThreads) {
-                unsigned v = s_cell[i];
-                if (v) atomicAdd(&lv.cnt_l[(c + i / NC) * kCS + (i % NC)], v);
-            }
-            __syncthreads();
         }
+        __syncthreads();
     }
     flush();
+}
+
+// ---- regime B: cells of at most a few tiles.  One group of G threads per cell (G = 256: block, G = 32: warp);
+// the group owns the cell, so the result is a plain store (no atomics) and inactive cells cost one load. ----
+template <int NC, int G>
+__global__ void __launch_bounds__(kThreads, 4) k_count_cells(const float *__restrict__ x, const float *__restrict__ y,
+                                                             const float *__restrict__ z, LevelState lv, uint32_t nCells,
+                                                             const uint32_t *__restrict__ gate) {
+    if (gate && *gate == 0u) return;
+    constexpr int NB = Acc<NC>::NB;
+    constexpr int GPB = kThreads / G;                 // groups per block
+    __shared__ uint32_t s_acc[GPB][kWarps][NB];       // only used when G == 256
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gtid = tid % G;                         // thread index inside the group
+    const uint32_t group = blockIdx.x * GPB + tid / G, nGroups = gridDim.x * GPB;
+
+    for (uint32_t c = group; c < nCells; c += nGroups) {
+        const uint32_t b = lv.bnd[c], e = lv.bnd[c + 1];
+        const uint32_t act = lv.active[c];
+        const int ax = lv.axis[c];
+        float cv[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) cv[k] = lv.cuts[c * kCS + k];
+        if (!act) continue;                            // group-uniform
+        Acc<NC> acc;
+        acc.clear();
+        if (e > b) {
+            const float *col = pick_col(ax, x, y, z);
+            const uint32_t a0 = min((b + 3u) & ~3u, e);    // first 16-byte aligned particle
+            const uint32_t a1 = max(a0, e & ~3u);          // end of the aligned body
+            // head [b,a0) and tail [a1,e): at most 3 + 3 particles
+            if (gtid < 8) {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                bool in[4] = {false, false, false, false};
+                const uint32_t ee = (gtid < 4) ? b + gtid : a1 + (gtid - 4);
+                const bool ok = (gtid < 4) ? (ee < a0) : (ee < e);
+                in[0] = ok;
+                v[0] = ok ? __ldg(col + ee) : 0.f;
+                acc.add_masked(v, in, cv);
+            }
+            // body: G threads stride over float4; 4 loads in flight per thread
+            const float4 *p = reinterpret_cast<const float4 *>(col + a0);
+            const uint32_t n4 = (a1 - a0) >> 2;
+            uint32_t i = gtid;
+            int sinceFold = 1;
+            for (; i + 3u * G < n4; i += 4u * G) {
+                const float4 q0 = __ldg(p + i), q1 = __ldg(p + i + G), q2 = __ldg(p + i + 2 * G), q3 = __ldg(p + i + 3 * G);
+                acc.add_f4(q0, cv); acc.add_f4(q1, cv); acc.add_f4(q2, cv); acc.add_f4(q3, cv);
+                sinceFold += 16;
+                if (sinceFold > 224) { acc.fold(); sinceFold = 0; }
+            }
+            for (; i < n4; i += G) {
+                acc.add_f4(__ldg(p + i), cv);
+                sinceFold += 4;
+                if (sinceFold > 224) { acc.fold(); sinceFold = 0; }
+            }
+        }
+        acc.fold();
+        // reduce over the group and store
+        unsigned r[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) r[k] = __reduce_add_sync(0xffffffffu, acc.a[k]);
+        if constexpr (G == 32) {
+            if (lane < NC) {
+                unsigned v;
+                if constexpr (NC == 7) v = cum_from_bins(r, lane);
+                else { v = 0u;
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) if (k == lane) v = r[k]; }
+                lv.cnt_l[c * kCS + lane] = v;
+            }
+        } else {
+            __syncthreads();   // previous cell's readers are done with s_acc
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < NB; ++k) s_acc[0][warp][k] = r[k];
+            }
+            __syncthreads();
+            if (tid < NC) {
+                unsigned bins[NB];
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+                    unsigned v = 0u;
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) v += s_acc[0][w][k];
+                    bins[k] = v;
+                }
+                unsigned v;
+                if constexpr (NC == 7) v = cum_from_bins(bins, tid);
+                else { v = 0u;
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) if (k == tid) v = bins[k]; }
+                lv.cnt_l[c * kCS + tid] = v;
+            }
+        }
+    }
 }
 
 // =====================================================================================
@@ -475,222 +738,434 @@ __global__ void k_ranges_from_level(const orb_cell *__restrict__ cells, uint32_t
 // contain a cell boundary publish an inclusive prefix at once, so look-back chains restart at every
 // cell boundary.
 // =====================================================================================
-constexpr uint64_t kStAgg = 1ull, kStPrefix = 2ull;
-__device__ __forceinline__ uint64_t pack_state(uint32_t epoch, uint64_t st, uint32_t v) {
-    return ((uint64_t)epoch << 34) | (st << 32) | (uint64_t)v;
+// ---- asynchronous tile loads (LDGSTS): global -> shared without staging in registers ----
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// dynamic shared memory of the partition kernels
+struct PartSmem {
+    float raw[2][3][kPartTile];       // double-buffered x,y,z tile (48 KB)
+    uint32_t sd[kPartTile];           // destination index of the particle staged at slot p
+    uint16_t sperm[kPartTile];        // tile offset of the particle that goes to slot p (inverse permutation)
+    uint32_t cbeg[kPartCells], cend[kPartCells], nleft[kPartCells], B[kPartCells], Bend[kPartCells];
+    float cut[kPartCells];
+    int axis[kPartCells];
+    uint32_t warpTot[kWarps];
+    uint32_t lbsum[kWarps];
+};
+
+// issue the asynchronous copy of tile [T, T+kPartTile) of x,y,z into buffer `bsel` (6 x 16 B per thread)
+__device__ __forceinline__ void part_prefetch(PartSmem &sm, int bsel, const float *__restrict__ x, const float *__restrict__ y,
+                                              const float *__restrict__ z, uint32_t T) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t o = (uint32_t)(h * kThreads + tid) * 4u;
+        cp_async16(&sm.raw[bsel][0][o], x + T + o);
+        cp_async16(&sm.raw[bsel][1][o], y + T + o);
+        cp_async16(&sm.raw[bsel][2][o], z + T + o);
+    }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) k_partition(const float *__restrict__ x, const float *__restrict__ y,
-                                                        const float *__restrict__ z, float *__restrict__ x2,
-                                                        float *__restrict__ y2, float *__restrict__ z2,
-                                                        LevelState lv, const float *__restrict__ final_cut,
-                                                        const uint32_t *__restrict__ tile_first, uint32_t nCells,
-                                                        uint32_t nLocal, uint32_t nTiles, uint64_t *tile_state,
-                                                        uint32_t epoch, uint32_t *ticket) {
-    __shared__ float sx[kPartTile], sy[kPartTile], sz[kPartTile];
-    __shared__ uint32_t sd[kPartTile];
-    __shared__ uint32_t s_cbeg[kPartCells], s_cend[kPartCells], s_nleft[kPartCells], s_B[kPartCells], s_Bend[kPartCells];
-    __shared__ float s_cut[kPartCells];
-    __shared__ int s_axis[kPartCells];
-    __shared__ uint32_t s_warp[kWarps];
-    __shared__ uint32_t s_tile, s_carry;
-
+// Table-driven tile body: particles of tile [T, T+kPartTile) that lie in [s0,s1) are split per cell, stable.
+// The cell table (ncell entries, first entry = cell containing s0) is in shared memory; `carryIn` = left particles
+// of the first cell that precede s0.  Returns the number of left particles of the segment that reaches s1.
+__device__ __forceinline__ uint32_t part_tile_body(PartSmem &sm, int bsel, uint32_t T, uint32_t s0, uint32_t s1, int ncell,
+                                                   uint32_t carryIn, float *__restrict__ x2, float *__restrict__ y2,
+                                                   float *__restrict__ z2) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t t = s_tile;
-    if (t >= nTiles) return;
-    const uint32_t t0 = t * (uint32_t)kPartTile, t1 = min(t0 + (uint32_t)kPartTile, nLocal);
-    const uint32_t c0 = tile_first[t];
-    const bool needCarry = lv.bnd[c0] < t0;
-
-    uint32_t s0 = t0, cfirst = c0;
-    bool firstSub = true;
-    while (s0 < t1) {
-        // ---- cell table of this sub-range: cells cfirst+i that begin before t1 ----
-        uint32_t cidx = cfirst + tid;
-        bool valid = false;
-        uint32_t cb = 0, ce = 0;
-        if (cidx < nCells) {
-            cb = lv.bnd[cidx];
-            valid = (tid == 0) || (cb < t1);
-            if (valid) ce = lv.bnd[cidx + 1];
-        }
-        const int ncell = __syncthreads_count(valid);   // cells are consecutive, so valid is a prefix of the threads
-        uint32_t s1 = t1;
-        if (valid) {
-            s_cbeg[tid] = cb; s_cend[tid] = ce;
-            s_nleft[tid] = lv.nleft_l[cidx];
-            s_cut[tid] = final_cut[cidx];
-            s_axis[tid] = lv.axis[cidx];
-        }
-        __syncthreads();
-        if (ncell == kPartCells) s1 = min(s_cend[kPartCells - 1], t1);   // table full: finish the rest in another sub-range
-        const bool lastSub = (s1 == t1);
-
-        // ---- load 8 particles per thread: two float4 groups, warp-striped ----
-        float vx[8], vy[8], vz[8];
-        bool ok[8], fl[8];
-        uint32_t jj[8];
+    // ---- cell of each of my 8 particles (two groups of 4 consecutive), left flag ----
+    bool ok[8], fl[8];
+    uint32_t jj[8];
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            const uint32_t o = warp * 256u + g * 128u + lane * 4u;   // offset in tile
-            const uint32_t e = t0 + o;
-            if (e >= s0 && e + 4u <= s1) {
-                float4 a = __ldg(reinterpret_cast<const float4 *>(x + e));
-                float4 b = __ldg(reinterpret_cast<const float4 *>(y + e));
-                float4 cq = __ldg(reinterpret_cast<const float4 *>(z + e));
-                vx[4 * g] = a.x; vx[4 * g + 1] = a.y; vx[4 * g + 2] = a.z; vx[4 * g + 3] = a.w;
-                vy[4 * g] = b.x; vy[4 * g + 1] = b.y; vy[4 * g + 2] = b.z; vy[4 * g + 3] = b.w;
-                vz[4 * g] = cq.x; vz[4 * g + 1] = cq.y; vz[4 * g + 2] = cq.z; vz[4 * g + 3] = cq.w;
+    for (int g = 0; g < 2; ++g) {
+        const uint32_t o = warp * 256u + g * 128u + lane * 4u;
+        const uint32_t e = T + o;
+        if (ncell == 1) {
+            const float4 q = *reinterpret_cast<const float4 *>(&sm.raw[bsel][sm.axis[0]][o]);
+            const float v[4] = {q.x, q.y, q.z, q.w};
+            const float cutv = sm.cut[0];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ok[4 * g + k] = true;
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t ee = e + k;
-                    const bool in = (ee >= s0 && ee < s1);
-                    ok[4 * g + k] = in;
-                    vx[4 * g + k] = in ? __ldg(x + ee) : 0.f;
-                    vy[4 * g + k] = in ? __ldg(y + ee) : 0.f;
-                    vz[4 * g + k] = in ? __ldg(z + ee) : 0.f;
-                }
+            for (int k = 0; k < 4; ++k) {
+                jj[4 * g + k] = 0u;
+                ok[4 * g + k] = (e + k) >= s0 && (e + k) < s1;
+                fl[4 * g + k] = ok[4 * g + k] && (v[k] < cutv);
             }
-        }
-        // ---- cell of each particle, left flag ----
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            const uint32_t e = t0 + warp * 256u + g * 128u + lane * 4u;
+        } else {
             uint32_t j = 0;
-            if (ncell > 1) {   // largest j with s_cbeg[j] <= e (j >= 1 entries are sorted begins inside the tile)
+            {   // largest j with cbeg[j] <= e
                 uint32_t lo = 0, hi = (uint32_t)ncell - 1;
                 while (lo < hi) {
-                    uint32_t m = (lo + hi + 1) >> 1;
-                    if (s_cbeg[m] <= e) lo = m; else hi = m - 1;
+                    const uint32_t m = (lo + hi + 1) >> 1;
+                    if (sm.cbeg[m] <= e) lo = m; else hi = m - 1;
                 }
                 j = lo;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t ee = e + k;
-                while (j + 1 < (uint32_t)ncell && s_cbeg[j + 1] <= ee) ++j;
+                while (j + 1 < (uint32_t)ncell && sm.cbeg[j + 1] <= ee) ++j;
                 jj[4 * g + k] = j;
-                const int a = s_axis[j];
-                const float v = a == 0 ? vx[4 * g + k] : (a == 1 ? vy[4 * g + k] : vz[4 * g + k]);
-                fl[4 * g + k] = ok[4 * g + k] && (v < s_cut[j]);
+                ok[4 * g + k] = ee >= s0 && ee < s1;
+                const float v = sm.raw[bsel][sm.axis[j]][o + k];
+                fl[4 * g + k] = ok[4 * g + k] && (v < sm.cut[j]);
             }
         }
-        // ---- block exclusive scan of the left flags (order: warp region, group, lane, k) ----
-        uint32_t c0n = (uint32_t)fl[0] + fl[1] + fl[2] + fl[3];
-        uint32_t c1n = (uint32_t)fl[4] + fl[5] + fl[6] + fl[7];
-        uint32_t i0 = c0n, i1 = c1n;
+    }
+    // ---- block exclusive scan of the left flags (order: warp region, group, lane, k) ----
+    const uint32_t c0n = (uint32_t)fl[0] + fl[1] + fl[2] + fl[3];
+    const uint32_t c1n = (uint32_t)fl[4] + fl[5] + fl[6] + fl[7];
+    uint32_t i0 = c0n, i1 = c1n;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t a = __shfl_up_sync(0xffffffffu, i0, o);
-            uint32_t b = __shfl_up_sync(0xffffffffu, i1, o);
-            if (lane >= o) { i0 += a; i1 += b; }
-        }
-        const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
-        if (lane == 0) s_warp[warp] = tot0 + tot1;
-        __syncthreads();
-        uint32_t woff = 0, total = 0;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, i0, o);
+        const uint32_t b = __shfl_up_sync(0xffffffffu, i1, o);
+        if (lane >= o) { i0 += a; i1 += b; }
+    }
+    const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+    if (lane == 0) sm.warpTot[warp] = tot0 + tot1;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const uint32_t v = s_warp[w];
-            if (w < warp) woff += v;
-            total += v;
-        }
-        uint32_t LE[8];
-        {
-            uint32_t r0 = woff + (i0 - c0n), r1 = woff + tot0 + (i1 - c1n);
+    for (int w = 0; w < kWarps; ++w) {
+        const uint32_t v = sm.warpTot[w];
+        if (w < warp) woff += v;
+        total += v;
+    }
+    uint32_t LE[8];
+    {
+        uint32_t r0 = woff + (i0 - c0n), r1 = woff + tot0 + (i1 - c1n);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { LE[k] = r0; r0 += fl[k]; LE[4 + k] = r1; r1 += fl[4 + k]; }
-        }
-        // ---- first / last particle of every segment record the running left count ----
+        for (int k = 0; k < 4; ++k) { LE[k] = r0; r0 += fl[k]; LE[4 + k] = r1; r1 += fl[4 + k]; }
+    }
+    // ---- first / last particle of every segment record the running left count ----
 #pragma unroll
-        for (int g = 0; g < 2; ++g)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int q = 4 * g + k;
-                if (!ok[q]) continue;
-                const uint32_t ee = t0 + warp * 256u + g * 128u + lane * 4u + k;
-                const uint32_t j = jj[q];
-                if (ee == max(s_cbeg[j], s0)) s_B[j] = LE[q];
-                if (ee + 1u == min(s_cend[j], s1)) s_Bend[j] = LE[q] + fl[q];
-            }
-        __syncthreads();
+    for (int q = 0; q < 8; ++q) {
+        if (!ok[q]) continue;
+        const uint32_t ee = T + warp * 256u + (q >> 2) * 128u + lane * 4u + (q & 3);
+        const uint32_t j = jj[q];
+        if (ee == max(sm.cbeg[j], s0)) sm.B[j] = LE[q];
+        if (ee + 1u == min(sm.cend[j], s1)) sm.Bend[j] = LE[q] + fl[q];
+    }
+    __syncthreads();
 
-        // ---- publish this tile's state, fetch the carry-in ----
-        if (firstSub && tid == 0) s_carry = 0u;
-        if (lastSub && tid == 0) {
-            const uint32_t lastSeg = total - s_B[ncell - 1];   // left particles of the segment that reaches t1
-            const bool restart = !(firstSub && ncell == 1 && needCarry);
-            ((volatile uint64_t *)tile_state)[t] = pack_state(epoch, restart ? kStPrefix : kStAgg, lastSeg);
+    const uint32_t lastSeg = total - sm.B[ncell - 1];   // left particles of the segment that reaches s1
+
+    // ---- slot p of every particle (per segment: lefts, then rights) and its destination without carry ----
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (!ok[q]) continue;
+        const uint32_t o = warp * 256u + (q >> 2) * 128u + lane * 4u + (q & 3);
+        const uint32_t ee = T + o;
+        const uint32_t j = jj[q];
+        const uint32_t cbj = sm.cbeg[j];
+        const uint32_t segStart = max(cbj, s0);
+        const uint32_t lb = LE[q] - sm.B[j];                 // lefts of this cell before me, inside [s0,s1)
+        uint32_t p, d;
+        if (fl[q]) {
+            p = (segStart - T) + lb;
+            d = cbj + lb;
+        } else {
+            const uint32_t nLt = sm.Bend[j] - sm.B[j];
+            const uint32_t rb = (ee - segStart) - lb;        // rights of this cell before me, inside [s0,s1)
+            p = (segStart - T) + nLt + rb;
+            d = cbj + sm.nleft[j] + ((ee - cbj) - lb);
         }
-        if (firstSub && needCarry && warp == 0) {
-            uint32_t carry = 0;
-            int pos = (int)t - 1;
+        sm.sperm[p] = (uint16_t)o;
+        sm.sd[p] = d;
+    }
+    __syncthreads();
+
+    const uint32_t carry0 = carryIn;
+    // ---- coalesced runs out to the ping-pong columns; the first cell's destinations shift by the carry ----
+    const uint32_t seg0len = min(sm.cend[0], s1) - s0;
+    const uint32_t nLt0 = seg0len ? (sm.Bend[0] - sm.B[0]) : 0u;
+    const uint32_t pBase = s0 - T;
+    for (uint32_t p = pBase + tid; p < (s1 - T); p += kThreads) {
+        uint32_t d = sm.sd[p];
+        const uint32_t rel = p - pBase;
+        if (rel < seg0len) d = (rel < nLt0) ? d + carry0 : d - carry0;
+        const uint32_t o = sm.sperm[p];
+        x2[d] = sm.raw[bsel][0][o];
+        y2[d] = sm.raw[bsel][1][o];
+        z2[d] = sm.raw[bsel][2][o];
+    }
+    __syncthreads();
+    return lastSeg;
+}
+
+// build the cell table of a sub-range starting at s0 with first cell `cfirst`; returns ncell, sets s1
+__device__ __forceinline__ int part_build_table(PartSmem &sm, const LevelState &lv, const float *__restrict__ final_cut,
+                                                uint32_t nCells, uint32_t cfirst, uint32_t tEnd, uint32_t &s1) {
+    const int tid = threadIdx.x;
+    const uint32_t cidx = cfirst + tid;
+    bool valid = false;
+    uint32_t cb = 0, ce = 0;
+    if (cidx < nCells) {
+        cb = lv.bnd[cidx];
+        valid = (tid == 0) || (cb < tEnd);
+        if (valid) ce = lv.bnd[cidx + 1];
+    }
+    const int ncell = __syncthreads_count(valid);   // cells are consecutive, so valid is a prefix of the threads
+    if (valid) {
+        sm.cbeg[tid] = cb; sm.cend[tid] = ce;
+        sm.nleft[tid] = lv.nleft_l[cidx];
+        sm.cut[tid] = final_cut[cidx];
+        sm.axis[tid] = lv.axis[cidx];
+    }
+    __syncthreads();
+    s1 = tEnd;
+    if (ncell == kPartCells) s1 = min(sm.cend[kPartCells - 1], tEnd);   // table full: rest in another sub-range
+    return ncell;
+}
+
+// Lean body for a tile [T, tEnd) that lies inside ONE cell (the common case when cells are larger than a
+// tile): all cell parameters are block-uniform registers, destinations are affine in the slot index, so only
+// the inverse permutation goes through shared memory.  Returns the number of left particles in the tile.
+__device__ __forceinline__ uint32_t part_tile_single(PartSmem &sm, int bsel, uint32_t oLo, uint32_t oHi, int axis, float cutv,
+                                                     uint32_t baseL, uint32_t baseR, float *__restrict__ x2,
+                                                     float *__restrict__ y2, float *__restrict__ z2) {
+    // valid particles are the tile offsets [oLo, oHi)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nValid = oHi - oLo;
+    bool fl[8];
+    uint32_t o8[2];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const uint32_t o = warp * 256u + g * 128u + lane * 4u;
+        o8[g] = o;
+        const float4 q = *reinterpret_cast<const float4 *>(&sm.raw[bsel][axis][o]);
+        fl[4 * g + 0] = (o + 0u >= oLo) && (o + 0u < oHi) && (q.x < cutv);
+        fl[4 * g + 1] = (o + 1u >= oLo) && (o + 1u < oHi) && (q.y < cutv);
+        fl[4 * g + 2] = (o + 2u >= oLo) && (o + 2u < oHi) && (q.z < cutv);
+        fl[4 * g + 3] = (o + 3u >= oLo) && (o + 3u < oHi) && (q.w < cutv);
+    }
+    const uint32_t c0n = (uint32_t)fl[0] + fl[1] + fl[2] + fl[3];
+    const uint32_t c1n = (uint32_t)fl[4] + fl[5] + fl[6] + fl[7];
+    uint32_t i0 = c0n, i1 = c1n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, i0, o);
+        const uint32_t b = __shfl_up_sync(0xffffffffu, i1, o);
+        if (lane >= o) { i0 += a; i1 += b; }
+    }
+    const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+    if (lane == 0) sm.warpTot[warp] = tot0 + tot1;
+    __syncthreads();
+    uint32_t woff = 0, nLt = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        const uint32_t v = sm.warpTot[w];
+        if (w < warp) woff += v;
+        nLt += v;
+    }
+    // slot of each particle: lefts keep their order in [0,nLt), rights in [nLt,nValid)
+    {
+        uint32_t r0 = woff + (i0 - c0n), r1 = woff + tot0 + (i1 - c1n);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t oa = o8[0] + k, ob = o8[1] + k;
+            if (oa >= oLo && oa < oHi) sm.sperm[fl[k] ? r0 : (nLt + (oa - oLo) - r0)] = (uint16_t)oa;
+            r0 += fl[k];
+            if (ob >= oLo && ob < oHi) sm.sperm[fl[4 + k] ? r1 : (nLt + (ob - oLo) - r1)] = (uint16_t)ob;
+            r1 += fl[4 + k];
+        }
+    }
+    __syncthreads();
+    for (uint32_t p = tid; p < nValid; p += kThreads) {
+        const uint32_t o = sm.sperm[p];
+        const uint32_t d = (p < nLt) ? (baseL + p) : (baseR + (p - nLt));
+        x2[d] = sm.raw[bsel][0][o];
+        y2[d] = sm.raw[bsel][1][o];
+        z2[d] = sm.raw[bsel][2][o];
+    }
+    __syncthreads();
+    return nLt;
+}
+
+// Regime A: cells larger than a tile.  Reduce-then-scan in ONE cooperative launch.  Block b owns the contiguous
+// tiles [tb0,tb1).  Phase 1 counts the left particles of the block's trailing segment (the cell that continues into
+// the next block) - reads at most the cut-axis column of the block's range.  After one grid-wide barrier every block
+// derives the carry-in of its first cell from the (at most gridDim) per-block records and then streams its tiles in
+// order with the carry in a register: no tile ever waits on another block.
+// (The first implementation was a single-pass decoupled look-back; ncu showed 35-42% of the stall samples on the
+//  look-back wait and ~170 instructions per particle, see profiles/r01_partition_lookback_notes.txt.)
+__global__ void __launch_bounds__(kThreads, 3) k_partition_coop(const float *__restrict__ x, const float *__restrict__ y,
+                                                               const float *__restrict__ z, float *__restrict__ x2,
+                                                               float *__restrict__ y2, float *__restrict__ z2,
+                                                               LevelState lv, const float *__restrict__ final_cut,
+                                                               const uint32_t *__restrict__ tile_first, uint32_t nCells,
+                                                               uint32_t nLocal, uint32_t nTiles, uint32_t *blkLeft,
+                                                               uint32_t *blkRestart) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PartSmem &sm = *reinterpret_cast<PartSmem *>(smem_raw);
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tilesPerBlock = (nTiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t tb0 = min(blockIdx.x * tilesPerBlock, nTiles), tb1 = min(tb0 + tilesPerBlock, nTiles);
+    const uint32_t chunkStart = tb0 * (uint32_t)kPartTile, chunkEnd = min(tb1 * (uint32_t)kPartTile, nLocal);
+
+    // start the first tile's copy right away; it lands while phase 1 runs
+    if (tb0 < tb1) part_prefetch(sm, 0, x, y, z, chunkStart);
+    cp_async_commit();
+
+    // ---------------- phase 1: left particles of the trailing segment ----------------
+    {
+        uint32_t cnt = 0, restart = 0;
+        if (tb0 < tb1) {
+            uint32_t c = tile_first[tb1 - 1];
+            while (lv.bnd[c + 1] < chunkEnd) ++c;            // cell that contains particle chunkEnd-1
+            const uint32_t cb = lv.bnd[c];
+            restart = cb >= chunkStart ? 1u : 0u;
+            const uint32_t b = max(cb, chunkStart), e = chunkEnd;
+            const float *col = pick_col(lv.axis[c], x, y, z);
+            const float cutv = final_cut[c];
+            const uint32_t a0 = min((b + 3u) & ~3u, e), a1 = max(a0, e & ~3u);
+            if (tid < 8) {
+                const uint32_t ee = (tid < 4) ? b + tid : a1 + (tid - 4);
+                const bool ok = (tid < 4) ? (ee < a0) : (ee < e);
+                if (ok) cnt += (__ldg(col + ee) < cutv);
+            }
+            const float4 *p = reinterpret_cast<const float4 *>(col + a0);
+            const uint32_t n4 = (a1 - a0) >> 2;
+            uint32_t i = tid;
+            for (; i + 3u * kThreads < n4; i += 4u * kThreads) {
+                const float4 q0 = __ldg(p + i), q1 = __ldg(p + i + kThreads), q2 = __ldg(p + i + 2 * kThreads), q3 = __ldg(p + i + 3 * kThreads);
+                cnt += (q0.x < cutv) + (q0.y < cutv) + (q0.z < cutv) + (q0.w < cutv);
+                cnt += (q1.x < cutv) + (q1.y < cutv) + (q1.z < cutv) + (q1.w < cutv);
+                cnt += (q2.x < cutv) + (q2.y < cutv) + (q2.z < cutv) + (q2.w < cutv);
+                cnt += (q3.x < cutv) + (q3.y < cutv) + (q3.z < cutv) + (q3.w < cutv);
+            }
+            for (; i < n4; i += kThreads) {
+                const float4 q = __ldg(p + i);
+                cnt += (q.x < cutv) + (q.y < cutv) + (q.z < cutv) + (q.w < cutv);
+            }
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) sm.warpTot[warp] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) tot += sm.warpTot[w];
+            blkLeft[blockIdx.x] = tot;
+            blkRestart[blockIdx.x] = restart;
+        }
+    }
+    grid.sync();
+    if (tb0 >= tb1) return;
+
+    // ---------------- phase 2: carry-in of the first cell, then stream the tiles ----------------
+    uint32_t c = tile_first[tb0];
+    uint32_t cb = lv.bnd[c], ce = lv.bnd[c + 1];
+    uint32_t carry = 0;
+    if (cb < chunkStart) {
+        if (warp == 0) {   // walk the predecessors back to the block in which this cell began
+            uint32_t acc = 0;
+            int pos = (int)blockIdx.x - 1;
             for (;;) {
                 const int idx = pos - lane;
-                uint64_t st = pack_state(epoch, kStPrefix, 0u);
-                if (idx >= 0) st = ((volatile uint64_t *)tile_state)[idx];
-                const bool okst = ((uint32_t)(st >> 34) == epoch) && (((st >> 32) & 3ull) != 0ull);
-                const bool isP = okst && (((st >> 32) & 3ull) == kStPrefix);
-                const unsigned inval = __ballot_sync(0xffffffffu, !okst);
-                const unsigned pref = __ballot_sync(0xffffffffu, isP);
-                const int fp = pref ? (__ffs(pref) - 1) : 32;
-                const unsigned need = (fp >= 31) ? 0xffffffffu : ((2u << fp) - 1u);
-                if (inval & need) continue;   // a predecessor has not published yet: poll again
-                const uint32_t contrib = (lane <= fp) ? (uint32_t)(st & 0xffffffffull) : 0u;
-                carry += __reduce_add_sync(0xffffffffu, contrib);
+                const uint32_t v = idx >= 0 ? blkLeft[idx] : 0u;
+                const uint32_t r = idx >= 0 ? blkRestart[idx] : 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, r != 0u);
+                const int fp = m ? (__ffs(m) - 1) : 32;
+                acc += __reduce_add_sync(0xffffffffu, lane <= fp ? v : 0u);
                 if (fp < 32) break;
                 pos -= 32;
             }
-            if (lane == 0) {
-                s_carry = carry;
-                if (lastSub && ncell == 1)
-                    ((volatile uint64_t *)tile_state)[t] = pack_state(epoch, kStPrefix, carry + total);
-            }
+            if (lane == 0) sm.lbsum[0] = acc;
         }
         __syncthreads();
-        const uint32_t carry0 = firstSub ? s_carry : 0u;
-
-        // ---- stage in shared memory in destination order (per segment: lefts, then rights) ----
-#pragma unroll
-        for (int g = 0; g < 2; ++g)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int q = 4 * g + k;
-                if (!ok[q]) continue;
-                const uint32_t ee = t0 + warp * 256u + g * 128u + lane * 4u + k;
-                const uint32_t j = jj[q];
-                const uint32_t cbj = s_cbeg[j];
-                const uint32_t segStart = max(cbj, s0);
-                const uint32_t lb = LE[q] - s_B[j];                 // lefts of this cell before me, inside this sub-range
-                const uint32_t cj = (j == 0) ? carry0 : 0u;         // ... and in earlier tiles
-                uint32_t p, d;
-                if (fl[q]) {
-                    p = (segStart - t0) + lb;
-                    d = cbj + cj + lb;
-                } else {
-                    const uint32_t nLt = s_Bend[j] - s_B[j];
-                    const uint32_t rb = (ee - segStart) - lb;       // rights of this cell before me, inside this sub-range
-                    p = (segStart - t0) + nLt + rb;
-                    d = cbj + s_nleft[j] + ((ee - cbj) - (cj + lb));
-                }
-                sx[p] = vx[q]; sy[p] = vy[q]; sz[p] = vz[q]; sd[p] = d;
-            }
-        __syncthreads();
-        // ---- coalesced runs out to the ping-pong columns ----
-        for (uint32_t o = (s0 - t0) + tid; o < (s1 - t0); o += kThreads) {
-            const uint32_t d = sd[o];
-            x2[d] = sx[o]; y2[d] = sy[o]; z2[d] = sz[o];
-        }
-        __syncthreads();
-        s0 = s1;
-        cfirst += (uint32_t)ncell;
-        firstSub = false;
+        carry = sm.lbsum[0];
     }
+    uint32_t nleft = lv.nleft_l[c];
+    float cutv = final_cut[c];
+    int axis = lv.axis[c];
+
+    int it = 0;
+    for (uint32_t t = tb0; t < tb1; ++t, ++it) {
+        const int bsel = it & 1;
+        const uint32_t T = t * (uint32_t)kPartTile, tEnd = min(T + (uint32_t)kPartTile, nLocal);
+        if (t + 1 < tb1) {
+            part_prefetch(sm, bsel ^ 1, x, y, z, T + (uint32_t)kPartTile);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();   // tile t is in sm.raw[bsel]
+        if (ce >= tEnd) {
+            // ---- tile inside the running cell ----
+            const uint32_t baseL = cb + carry;
+            const uint32_t baseR = cb + nleft + ((T - cb) - carry);
+            carry += part_tile_single(sm, bsel, 0u, tEnd - T, axis, cutv, baseL, baseR, x2, y2, z2);
+        } else {
+            // ---- a cell boundary inside the tile: table-driven body, then re-seed the running cell ----
+            uint32_t s0 = T, cfirst = c;
+            bool firstSub = true;
+            uint32_t lastSeg = 0;
+            int ncell = 1;
+            while (s0 < tEnd) {
+                uint32_t s1;
+                ncell = part_build_table(sm, lv, final_cut, nCells, cfirst, tEnd, s1);
+                lastSeg = part_tile_body(sm, bsel, T, s0, s1, ncell, firstSub ? carry : 0u, x2, y2, z2);
+                s0 = s1;
+                cfirst += (uint32_t)ncell;
+                firstSub = false;
+            }
+            c = cfirst - 1;            // cell that reaches the end of the tile
+            cb = lv.bnd[c];
+            ce = lv.bnd[c + 1];
+            nleft = lv.nleft_l[c];
+            cutv = final_cut[c];
+            axis = lv.axis[c];
+            carry = lastSeg;           // it began inside this tile, so this is all of its lefts so far
+        }
+    }
+}
+
+// Regime B: cells of at most a few tiles.  One block per cell; the block walks the cell's tiles in order with the
+// carry in a register, so there is no inter-block dependency at all.
+__global__ void __launch_bounds__(kThreads, 3) k_partition_cells(const float *__restrict__ x, const float *__restrict__ y,
+                                                                const float *__restrict__ z, float *__restrict__ x2,
+                                                                float *__restrict__ y2, float *__restrict__ z2,
+                                                                LevelState lv, const float *__restrict__ final_cut,
+                                                                uint32_t nCells, uint32_t nLocal) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PartSmem &sm = *reinterpret_cast<PartSmem *>(smem_raw);
+    for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
+        const uint32_t b = lv.bnd[c], e = lv.bnd[c + 1];
+        if (e <= b) continue;   // block-uniform
+        const uint32_t nleft = lv.nleft_l[c];
+        const float cutv = final_cut[c];
+        const int axis = lv.axis[c];
+        const uint32_t Tfirst = (b / (uint32_t)kPartTile) * (uint32_t)kPartTile;
+        part_prefetch(sm, 0, x, y, z, Tfirst);
+        cp_async_commit();
+        uint32_t carry = 0u;
+        int it = 0;
+        for (uint32_t T = Tfirst; T < e; T += (uint32_t)kPartTile, ++it) {
+            const int bsel = it & 1;
+            if (T + (uint32_t)kPartTile < e) {
+                part_prefetch(sm, bsel ^ 1, x, y, z, T + (uint32_t)kPartTile);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+            const uint32_t s0 = max(b, T), s1 = min(e, T + (uint32_t)kPartTile);
+            const uint32_t baseL = b + carry;
+            const uint32_t baseR = b + nleft + ((s0 - b) - carry);
+            carry += part_tile_single(sm, bsel, s0 - T, s1 - T, axis, cutv, baseL, baseR, x2, y2, z2);
+        }
+    }
+    (void)nLocal;
 }
 
 // =====================================================================================

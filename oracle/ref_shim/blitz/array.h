@@ -98,7 +98,7 @@ public:
         // Storage is never released (process-lifetime buffers): keeps Array copies
         // trivially cheap, like Blitz's non-atomic reference counts, so that the
         // by-value Array in partition.cpp:10 costs what it costs with the real library.
-        data_ = static_cast<T *>(std::calloc(n > 0 ? (size_t)n : 1, sizeof(T)));
+        data_ = static_cast<T *>(std::calloc((n > 0 ? (size_t)n : 1) + 16, sizeof(T)));   // +16: absorbs the reference's one-element overrun in MakeAxis (makeAxis.cpp:23-28)
     }
     // Pre-existing memory. The reference hands over cudaMallocHost memory with
     // deleteDataWhenDone; the shim never frees it (process-lifetime buffers).

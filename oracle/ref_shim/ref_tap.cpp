@@ -15,6 +15,9 @@
 // Record layout (little endian): u32 kind, u32 nCells, u64 payloadBytes, payload.
 //   kind = pst_service id for service records; 1000 = particle dump.
 #include <chrono>
+#include <csignal>
+#include <execinfo.h>
+#include <unistd.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -136,8 +139,19 @@ void tap(mdl::mdlClass *mdl, int sid, int nIn, void *pIn, void *pOut, int /*nOut
     }
 }
 
+void onSegv(int sig) {
+    void *frames[48];
+    int n = backtrace(frames, 48);
+    const char msg[] = "orbit_ref: fatal signal, backtrace:\n";
+    if (write(2, msg, sizeof(msg) - 1) < 0) {}
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
 struct Installer {
     Installer() {
+        std::signal(SIGSEGV, onSegv);
+        std::signal(SIGBUS, onSegv);
         const char *path = std::getenv("ORB_REF_TRACE");
         if (path && *path) {
             g_trace = std::fopen(path, "wb");
@@ -173,6 +187,9 @@ struct Installer {
 extern "C" cudaError_t CUDARTAPI cudaMallocHost(void **ptr, size_t size) {
     typedef cudaError_t (*fn_t)(void **, size_t);
     static fn_t real = (fn_t)dlsym(RTLD_NEXT, "cudaMallocHost");
+    // + one page: MakeAxis copies end-begin+1 floats (blitz Range is inclusive, makeAxis.cpp:23-28), i.e. it reads
+    // one float past the last column; with exact page-granular pinned allocations that read faults
+    size += 4096;
     if (real) {
         cudaError_t rc = real(ptr, size);
         if (rc == cudaSuccess) return rc;
