@@ -146,27 +146,65 @@ __global__ void k_tile_map(const uint32_t *__restrict__ bnd, uint32_t nCells, ui
 // heap node -> number of sorted bins at or below it (cumulative index): node k gets bins [0 .. kSortedRank[k]]
 __device__ __constant__ int kSortedRank7[7] = {3, 1, 5, 0, 2, 4, 6};
 
+// 0xFFFFFFFF if a < b else 0 (one FSET; NaN compares false like the CPU's `<`)
+__device__ __forceinline__ int lt_mask(float a, float b) {
+    int m;
+    asm("set.lt.s32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b));
+    return m;
+}
+// m ? a : b for m in {-1, 0}, on the FMA pipe: b + m * (b - a); `bma` = b - a precomputed per cell
+__device__ __forceinline__ int sel_mask(int m, int bma, int b) {
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(m), "r"(bma), "r"(b));
+    return r;
+}
+
+// Cut set of one cell prepared for the 3-step descent: bit patterns and select deltas (heap order c0..c6).
+struct Cuts7 {
+    float c0;
+    int c2b, d21;        // level 2: m0 ? c1 : c2
+    int c4b, d43;        // level 3 (left subtree):  m1 ? c3 : c4
+    int c6b, d65;        // level 3 (right subtree): m1 ? c5 : c6
+    __device__ __forceinline__ void set(const float *cv) {
+        c0 = cv[0];
+        const int c1b = __float_as_int(cv[1]);
+        c2b = __float_as_int(cv[2]);
+        const int c3b = __float_as_int(cv[3]);
+        c4b = __float_as_int(cv[4]);
+        const int c5b = __float_as_int(cv[5]);
+        c6b = __float_as_int(cv[6]);
+        d21 = c2b - c1b; d43 = c4b - c3b; d65 = c6b - c5b;
+    }
+};
+
+// One particle through the sorted cut tree: 3 float compares (FSET masks), selects as integer multiply-adds on the
+// bit patterns (exact), packed 8-bit bin increment.  Sorted bin s = 7 + 4*m0 + 2*m1 + m2 (masks are -1 / 0).
+__device__ __forceinline__ void bin7(float x, const Cuts7 &k, unsigned &lo, unsigned &hi) {
+    const int m0 = lt_mask(x, k.c0);
+    const int ab = sel_mask(m0, k.d21, k.c2b);
+    const int m1 = lt_mask(x, __int_as_float(ab));
+    const int tb = sel_mask(m1, k.d43, k.c4b);
+    const int ub = sel_mask(m1, k.d65, k.c6b);
+    const int bb = sel_mask(m0, ub - tb, ub);
+    const int m2 = lt_mask(x, __int_as_float(bb));
+    const int sh = sel_mask(m1, 16, sel_mask(m2, 8, 24));   // 8 * (s & 3) = 24 + 16*m1 + 8*m2
+    const unsigned inc = 1u << sh;
+    lo += inc & (unsigned)m0;
+    hi += inc & ~(unsigned)m0;
+}
+
 template <int NC>
 __device__ __forceinline__ void count_vals(const float (&v)[4], const bool (&in)[4], const float (&cv)[NC], unsigned (&cnt)[NC],
                                            unsigned &lo, unsigned &hi) {
     if constexpr (NC == 7) {
+        Cuts7 k;
+        k.set(cv);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float x = v[j];
-            const bool p0 = x < cv[0];
-            const float a = p0 ? cv[1] : cv[2];
-            const bool p1 = x < a;
-            const float t = p1 ? cv[3] : cv[4];
-            const float u = p1 ? cv[5] : cv[6];
-            const float b = p0 ? t : u;
-            const bool p2 = x < b;
-            // sorted bin s = 4*!p0 + 2*!p1 + !p2 ; packed increment 1 << (8*(s&3)) into lo (s<4) or hi
-            const unsigned w0 = p2 ? 0x1u : 0x100u;
-            const unsigned w1 = p2 ? 0x10000u : 0x1000000u;
-            unsigned inc = p1 ? w0 : w1;
-            if (!in[j]) inc = 0u;
-            lo += p0 ? inc : 0u;
-            hi += p0 ? 0u : inc;
+            unsigned l2 = 0u, h2 = 0u;
+            bin7(v[j], k, l2, h2);
+            lo += in[j] ? l2 : 0u;
+            hi += in[j] ? h2 : 0u;
         }
     } else {
 #pragma unroll
@@ -212,6 +250,10 @@ struct Acc {
         unsigned dummy[NC];
         if constexpr (NC == 7) count_vals<NC>(v, in, cv, dummy, lo, hi);
         else count_vals<NC>(v, in, cv, a, lo, hi);
+    }
+    // NC == 7 fast path with the cut set already prepared (no per-call setup)
+    __device__ __forceinline__ void add_f4(const float4 q, const Cuts7 &k) {
+        bin7(q.x, k, lo, hi); bin7(q.y, k, lo, hi); bin7(q.z, k, lo, hi); bin7(q.w, k, lo, hi);
     }
     __device__ __forceinline__ void add_masked(const float (&v)[4], const bool (&in)[4], const float (&cv)[NC]) {
         unsigned dummy[NC];
@@ -330,6 +372,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
     __shared__ uint32_t s_cell[kCountCellsSmem * NC];
     __shared__ uint32_t s_uTile[kMaxUnits], s_uCell[kMaxUnits];   // compacted streamable tiles
     __shared__ int s_uAx[kMaxUnits];
+    __shared__ __align__(16) float s_uCuts[kMaxUnits][kCS];       // their cells' trial cuts (no global load on a cell change)
     __shared__ uint32_t s_fTile[kMaxUnits], s_fCell[kMaxUnits];   // fragmented tiles
     __shared__ uint32_t s_wS[kWarps], s_wF[kWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -340,8 +383,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
     float cv[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) cv[k] = 0.f;
+    Cuts7 k7;
+    k7.c0 = 0.f; k7.c2b = k7.d21 = k7.c4b = k7.d43 = k7.c6b = k7.d65 = 0;
     int cur = -1;
 
+    // One global atomic per block per (cell, cut): warp REDUX -> shared -> global.  Atomics to the few counter
+    // rows of a level all land in one or two L2 slices (~0.65 ns each, serialised), so their number must stay small:
+    // a per-warp flush cost 232K atomics per pass and 150 us at 8 cells (profiles/r01_count_notes.txt).
     auto flush = [&]() {   // block-uniform
         if (cur < 0) return;
         acc.fold();
@@ -363,13 +411,17 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
         __syncthreads();
     };
 
-    for (uint32_t base = blockIdx.x; base < nTiles; base += gridDim.x * (uint32_t)kMaxUnits) {
+    // Block b owns the contiguous tiles [tb0, tb1): its tiles share one or two cells, so counters are flushed
+    // once or twice per pass instead of once per tile.
+    const uint32_t tilesPerBlock = (nTiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t tb0 = min(blockIdx.x * tilesPerBlock, nTiles), tb1 = min(tb0 + tilesPerBlock, nTiles);
+    for (uint32_t base = tb0; base < tb1; base += (uint32_t)kMaxUnits) {
         // ---- phase 1: classify up to 256 tiles of this block ----
-        const uint32_t t = base + (uint32_t)tid * gridDim.x;
+        const uint32_t t = base + (uint32_t)tid;
         int kind = 0;   // 0 none/skip, 1 stream, 2 fragmented
         uint32_t c = 0;
         int ax = 0;
-        if (t < nTiles) {
+        if (t < tb1) {
             const uint32_t t0 = t * (uint32_t)kCountTile, t1 = min(t0 + (uint32_t)kCountTile, nLocal);
             c = tile_first[t * (kCountTile / kMapTile)];
             const uint32_t cb = lv.bnd[c], ce = lv.bnd[c + 1];
@@ -387,7 +439,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
             nS += s_wS[w]; nF += s_wF[w];
         }
         const unsigned ltMask = (1u << lane) - 1u;
-        if (kind == 1) { const uint32_t r = offS + __popc(mS & ltMask); s_uTile[r] = t; s_uCell[r] = c; s_uAx[r] = ax; }
+        if (kind == 1) {
+            const uint32_t r = offS + __popc(mS & ltMask);
+            s_uTile[r] = t; s_uCell[r] = c; s_uAx[r] = ax;
+            const float4 *cp = reinterpret_cast<const float4 *>(lv.cuts + c * kCS);
+            *reinterpret_cast<float4 *>(&s_uCuts[r][0]) = __ldg(cp);
+            *reinterpret_cast<float4 *>(&s_uCuts[r][4]) = __ldg(cp + 1);
+        }
         if (kind == 2) { const uint32_t r = offF + __popc(mF & ltMask); s_fTile[r] = t; s_fCell[r] = c; }
         __syncthreads();
 
@@ -411,9 +469,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
                     flush();
                     cur = (int)cK;
 #pragma unroll
-                    for (int j = 0; j < NC; ++j) cv[j] = lv.cuts[cK * kCS + j];
+                    for (int j = 0; j < NC; ++j) cv[j] = s_uCuts[k][j];
+                    if constexpr (NC == 7) k7.set(cv);
                 }
-                acc.add_f4(q0, cv); acc.add_f4(q1, cv); acc.add_f4(q2, cv); acc.add_f4(q3, cv);
+                if constexpr (NC == 7) { acc.add_f4(q0, k7); acc.add_f4(q1, k7); acc.add_f4(q2, k7); acc.add_f4(q3, k7); }
+                else { acc.add_f4(q0, cv); acc.add_f4(q1, cv); acc.add_f4(q2, cv); acc.add_f4(q3, cv); }
                 if ((k & 7u) == 7u) acc.fold();   // 16 particles per tile per thread: fold before 255
                 q0 = n0; q1 = n1; q2 = n2; q3 = n3;
             }
@@ -458,6 +518,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_cells(const float *__rest
         if (!act) continue;                            // group-uniform
         Acc<NC> acc;
         acc.clear();
+        Cuts7 k7;
+        if constexpr (NC == 7) k7.set(cv);
+        else { k7.c0 = 0.f; k7.c2b = k7.d21 = k7.c4b = k7.d43 = k7.c6b = k7.d65 = 0; }
         if (e > b) {
             const float *col = pick_col(ax, x, y, z);
             const uint32_t a0 = min((b + 3u) & ~3u, e);    // first 16-byte aligned particle
@@ -479,12 +542,14 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_cells(const float *__rest
             int sinceFold = 1;
             for (; i + 3u * G < n4; i += 4u * G) {
                 const float4 q0 = __ldg(p + i), q1 = __ldg(p + i + G), q2 = __ldg(p + i + 2 * G), q3 = __ldg(p + i + 3 * G);
-                acc.add_f4(q0, cv); acc.add_f4(q1, cv); acc.add_f4(q2, cv); acc.add_f4(q3, cv);
+                if constexpr (NC == 7) { acc.add_f4(q0, k7); acc.add_f4(q1, k7); acc.add_f4(q2, k7); acc.add_f4(q3, k7); }
+                else { acc.add_f4(q0, cv); acc.add_f4(q1, cv); acc.add_f4(q2, cv); acc.add_f4(q3, cv); }
                 sinceFold += 16;
                 if (sinceFold > 224) { acc.fold(); sinceFold = 0; }
             }
             for (; i < n4; i += G) {
-                acc.add_f4(__ldg(p + i), cv);
+                if constexpr (NC == 7) acc.add_f4(__ldg(p + i), k7);
+                else acc.add_f4(__ldg(p + i), cv);
                 sinceFold += 4;
                 if (sinceFold > 224) { acc.fold(); sinceFold = 0; }
             }
