@@ -116,7 +116,7 @@ struct orb_ctx {
 
     int occPartStream = 1, occPartCells = 1;   // resident blocks per SM of the partition kernels
     int trialDepth = 3;
-    int runAhead = 2;
+    int runAhead = 1;
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evCount, evPart;
     size_t evCountUsed = 0, evPartUsed = 0;
@@ -189,7 +189,8 @@ int launch_count_nc(orb_ctx *c, uint32_t nCells, const uint32_t *gate) {
     if (avg >= 16ull * kCountTile) {
         const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
         const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * 4u);
-        k_count_stream<NC><<<grid, kThreads, 0, c->stream>>>(x, y, z, c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate);
+        const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
+        k_count_stream<NC><<<grid, kThreads, ringBytes, c->stream>>>(x, y, z, c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate);
     } else if (avg >= 1024) {
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * 4u);
         k_count_cells<NC, 256><<<grid, kThreads, 0, c->stream>>>(x, y, z, c->lv, nCells, gate);
@@ -461,6 +462,12 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaHostAlloc((void **)&c->h_status, sizeof(uint32_t) * kMaxLevels * kPassSlots, cudaHostAllocMapped));
     memset((void *)c->h_status, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots);
     CK(cudaHostGetDevicePointer((void **)&c->h_status_dev, (void *)c->h_status, 0));
+    {
+        const int ringBytes = orb::kCountStages * orb::kCountTile * (int)sizeof(float);
+        CK(cudaFuncSetAttribute(orb::k_count_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
+        CK(cudaFuncSetAttribute(orb::k_count_stream<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
+        CK(cudaFuncSetAttribute(orb::k_count_stream<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
+    }
     CK(cudaFuncSetAttribute(orb::k_partition_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(orb::PartSmem)));
     CK(cudaFuncSetAttribute(orb::k_partition_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(orb::PartSmem)));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occPartStream, orb::k_partition_coop, orb::kThreads, sizeof(orb::PartSmem)));

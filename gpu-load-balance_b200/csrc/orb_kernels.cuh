@@ -146,12 +146,16 @@ __global__ void k_tile_map(const uint32_t *__restrict__ bnd, uint32_t nCells, ui
 // heap node -> number of sorted bins at or below it (cumulative index): node k gets bins [0 .. kSortedRank[k]]
 __device__ __constant__ int kSortedRank7[7] = {3, 1, 5, 0, 2, 4, 6};
 
-// 0xFFFFFFFF if a < b else 0 (one FSET; NaN compares false like the CPU's `<`)
+// 0xFFFFFFFF if a < b else 0, computed as the sign of (a - b): one FADD (FMA pipe) + one arithmetic shift,
+// instead of FSETP + SEL (two ALU-pipe ops; the ALU pipe is the count kernel's bottleneck).
+// Exact for all finite / infinite a, b with a != -0.0: IEEE subtraction never rounds a non-zero difference to a zero
+// of the wrong sign, and a == b gives +0.  Callers canonicalise -0.0 to +0.0 first (canon0).  NaN coordinates are
+// not supported (the CPU `<` yields false, the sign of a NaN difference is unspecified).
 __device__ __forceinline__ int lt_mask(float a, float b) {
-    int m;
-    asm("set.lt.s32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b));
-    return m;
+    return __float_as_int(__fsub_rn(a, b)) >> 31;
 }
+// -0.0 -> +0.0, everything else unchanged (x + (+0) in round-to-nearest)
+__device__ __forceinline__ float canon0(float x) { return __fadd_rn(x, 0.0f); }
 // m ? a : b for m in {-1, 0}, on the FMA pipe: b + m * (b - a); `bma` = b - a precomputed per cell
 __device__ __forceinline__ int sel_mask(int m, int bma, int b) {
     int r;
@@ -179,7 +183,8 @@ struct Cuts7 {
 
 // One particle through the sorted cut tree: 3 float compares (FSET masks), selects as integer multiply-adds on the
 // bit patterns (exact), packed 8-bit bin increment.  Sorted bin s = 7 + 4*m0 + 2*m1 + m2 (masks are -1 / 0).
-__device__ __forceinline__ void bin7(float x, const Cuts7 &k, unsigned &lo, unsigned &hi) {
+__device__ __forceinline__ void bin7(float xin, const Cuts7 &k, unsigned &lo, unsigned &hi) {
+    const float x = canon0(xin);
     const int m0 = lt_mask(x, k.c0);
     const int ab = sel_mask(m0, k.d21, k.c2b);
     const int m1 = lt_mask(x, __int_as_float(ab));
@@ -231,6 +236,15 @@ __device__ __forceinline__ void unpack_bins(unsigned &lo, unsigned &hi, unsigned
     lo = 0u;
     hi = 0u;
 }
+
+// ---- asynchronous tile loads (LDGSTS): global -> shared without staging in registers ----
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // ---- shared pieces of the count kernels -------------------------------------------------------------
 // per-thread accumulators: NC < 7 -> one counter per cut; NC == 7 -> eight sorted bins (+ packed lo/hi)
@@ -359,7 +373,8 @@ __device__ __forceinline__ void count_fragmented_tile(const float *__restrict__ 
 // memory latencies for the whole block instead of a dependent chain per tile.  Phase 2: the streamable
 // tiles run through a register double buffer (the next tile's four 128-bit loads are issued before the
 // current tile is counted); counters persist across tiles of one cell.
-constexpr int kMaxUnits = 256;   // tiles classified per round (one per thread)
+constexpr int kMaxUnits = 64;    // tiles classified per round
+constexpr int kCountStages = 3;  // depth of the per-thread cp.async ring (tiles in flight per block: kCountStages - 1)
 template <int NC>
 __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__restrict__ x, const float *__restrict__ y,
                                                               const float *__restrict__ z, LevelState lv,
@@ -368,6 +383,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
                                                               const uint32_t *__restrict__ gate) {
     if (gate && *gate == 0u) return;   // speculative pass after convergence: nothing to do
     constexpr int NB = Acc<NC>::NB;
+    extern __shared__ __align__(16) unsigned char count_smem[];       // kCountStages x 16 KB ring
+    float4 *ring = reinterpret_cast<float4 *>(count_smem);
     __shared__ uint32_t s_acc[NB];
     __shared__ uint32_t s_cell[kCountCellsSmem * NC];
     __shared__ uint32_t s_uTile[kMaxUnits], s_uCell[kMaxUnits];   // compacted streamable tiles
@@ -416,12 +433,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
     const uint32_t tilesPerBlock = (nTiles + gridDim.x - 1) / gridDim.x;
     const uint32_t tb0 = min(blockIdx.x * tilesPerBlock, nTiles), tb1 = min(tb0 + tilesPerBlock, nTiles);
     for (uint32_t base = tb0; base < tb1; base += (uint32_t)kMaxUnits) {
-        // ---- phase 1: classify up to 256 tiles of this block ----
+        // ---- phase 1: classify up to kMaxUnits tiles of this block ----
         const uint32_t t = base + (uint32_t)tid;
         int kind = 0;   // 0 none/skip, 1 stream, 2 fragmented
         uint32_t c = 0;
         int ax = 0;
-        if (t < tb1) {
+        if (tid < kMaxUnits && t < tb1) {
             const uint32_t t0 = t * (uint32_t)kCountTile, t1 = min(t0 + (uint32_t)kCountTile, nLocal);
             c = tile_first[t * (kCountTile / kMapTile)];
             const uint32_t cb = lv.bnd[c], ce = lv.bnd[c + 1];
@@ -449,22 +466,26 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
         if (kind == 2) { const uint32_t r = offF + __popc(mF & ltMask); s_fTile[r] = t; s_fCell[r] = c; }
         __syncthreads();
 
-        // ---- phase 2a: streamable tiles, software-pipelined ----
+        // ---- phase 2a: streamable tiles through a per-thread cp.async ring: every thread copies the four 16-byte
+        //      pieces it will count itself into its own shared-memory slots, kCountStages-1 tiles ahead, so the wait
+        //      is per thread (cp.async.wait_group) and needs no barrier. ----
         if (nS) {
-            float4 q0, q1, q2, q3;
-            uint32_t cNext = s_uCell[0];
-            {
-                const float4 *p = reinterpret_cast<const float4 *>(pick_col(s_uAx[0], x, y, z) + s_uTile[0] * (uint32_t)kCountTile) + tid;
-                q0 = __ldg(p); q1 = __ldg(p + kThreads); q2 = __ldg(p + 2 * kThreads); q3 = __ldg(p + 3 * kThreads);
+            auto issue = [&](uint32_t k) {
+                const float4 *p = reinterpret_cast<const float4 *>(pick_col(s_uAx[k], x, y, z) + s_uTile[k] * (uint32_t)kCountTile) + tid;
+                float4 *dst = ring + (k % kCountStages) * (4 * kThreads) + tid;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cp_async16(dst + j * kThreads, p + j * kThreads);
+            };
+#pragma unroll
+            for (int pre = 0; pre < kCountStages - 1; ++pre) {
+                if ((uint32_t)pre < nS) issue(pre);
+                cp_async_commit();
             }
             for (uint32_t k = 0; k < nS; ++k) {
-                const uint32_t cK = cNext;
-                float4 n0 = q0, n1 = q1, n2 = q2, n3 = q3;
-                if (k + 1 < nS) {   // issue the next tile's loads before counting this one
-                    cNext = s_uCell[k + 1];
-                    const float4 *p = reinterpret_cast<const float4 *>(pick_col(s_uAx[k + 1], x, y, z) + s_uTile[k + 1] * (uint32_t)kCountTile) + tid;
-                    n0 = __ldg(p); n1 = __ldg(p + kThreads); n2 = __ldg(p + 2 * kThreads); n3 = __ldg(p + 3 * kThreads);
-                }
+                if (k + kCountStages - 1 < nS) issue(k + kCountStages - 1);
+                cp_async_commit();
+                cp_async_wait<kCountStages - 1>();     // tile k has landed in my slots
+                const uint32_t cK = s_uCell[k];
                 if ((int)cK != cur) {
                     flush();
                     cur = (int)cK;
@@ -472,11 +493,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
                     for (int j = 0; j < NC; ++j) cv[j] = s_uCuts[k][j];
                     if constexpr (NC == 7) k7.set(cv);
                 }
+                const float4 *src = ring + (k % kCountStages) * (4 * kThreads) + tid;
+                const float4 q0 = src[0], q1 = src[kThreads], q2 = src[2 * kThreads], q3 = src[3 * kThreads];
                 if constexpr (NC == 7) { acc.add_f4(q0, k7); acc.add_f4(q1, k7); acc.add_f4(q2, k7); acc.add_f4(q3, k7); }
                 else { acc.add_f4(q0, cv); acc.add_f4(q1, cv); acc.add_f4(q2, cv); acc.add_f4(q3, cv); }
                 if ((k & 7u) == 7u) acc.fold();   // 16 particles per tile per thread: fold before 255
-                q0 = n0; q1 = n1; q2 = n2; q3 = n3;
             }
+            cp_async_wait<0>();
             acc.fold();
         }
         // ---- phase 2b: fragmented tiles (cell boundaries, array tail) ----
@@ -623,6 +646,14 @@ __global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCe
     unsigned long long npart = 0, nipart = 0;
     int it = 0;
     if (gate != 0u && c < nCells && lv.active[c]) {
+        // everything the decision needs is fetched up front (one memory latency): the counted nodes are picked from
+        // registers afterwards
+        const uint4 g0 = *reinterpret_cast<const uint4 *>(lv.cnt_g + c * kCS), g1 = *reinterpret_cast<const uint4 *>(lv.cnt_g + c * kCS + 4);
+        const uint4 l0 = *reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS), l1 = *reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS + 4);
+        const float4 q0 = *reinterpret_cast<const float4 *>(lv.cuts + c * kCS), q1 = *reinterpret_cast<const float4 *>(lv.cuts + c * kCS + 4);
+        const uint32_t cg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const uint32_t cl8[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const float cu[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
         float L = lv.mL[c], R = lv.mR[c];
         it = lv.iter[c];
         const int it0 = it;
@@ -635,14 +666,17 @@ __global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCe
         bool fnd = false;
 #pragma unroll
         for (int s = 0; s < M; ++s) {
-            const float cut = lv.cuts[c * kCS + node];
-            const uint32_t cl = lv.cnt_g[c * kCS + node];
-            const int diff = __float2int_rz(__fsub_rn(__uint2float_rn(cl), prod));   // orbit.cpp:205
+            float cut = 0.f;
+            uint32_t cnt = 0, cntl = 0;
+#pragma unroll
+            for (int k = 0; k < NC; ++k)
+                if (k == node) { cut = cu[k]; cnt = cg[k]; cntl = cl8[k]; }
+            const int diff = __float2int_rz(__fsub_rn(__uint2float_rn(cnt), prod));   // orbit.cpp:205
             ++it;
             if (abs(diff) < 3) {                                                      // orbit.cpp:208
                 fnd = true;
-                lv.nleft_g[c] = cl;
-                lv.nleft_l[c] = lv.cnt_l[c * kCS + node];
+                lv.nleft_g[c] = cnt;
+                lv.nleft_l[c] = cntl;
                 break;
             } else if (diff > 0) { R = cut; node = 2 * node + 1; }                    // orbit.cpp:219
             else { L = cut; node = 2 * node + 2; }                                    // orbit.cpp:227
@@ -654,18 +688,20 @@ __global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCe
         else if (it >= kMaxIter) { lv.active[c] = 0u; }
         else {
             still = 1;
-            float cv[7], lo[7], hi[7];
+            float cv[8], lo[7], hi[7];
             lo[0] = L; hi[0] = R;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cv[k] = 0.f;
 #pragma unroll
             for (int k = 0; k < NC; ++k) {
                 cv[k] = mid_cut(lo[k], hi[k]);
                 if (2 * k + 2 < NC) { lo[2 * k + 1] = lo[k]; hi[2 * k + 1] = cv[k]; lo[2 * k + 2] = cv[k]; hi[2 * k + 2] = hi[k]; }
             }
-#pragma unroll
-            for (int k = 0; k < NC; ++k) lv.cuts[c * kCS + k] = cv[k];
+            *reinterpret_cast<float4 *>(lv.cuts + c * kCS) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+            *reinterpret_cast<float4 *>(lv.cuts + c * kCS + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
         }
-#pragma unroll
-        for (int k = 0; k < NC; ++k) lv.cnt_l[c * kCS + k] = 0u;
+        *reinterpret_cast<uint4 *>(lv.cnt_l + c * kCS) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(lv.cnt_l + c * kCS + 4) = make_uint4(0u, 0u, 0u, 0u);
     }
     // block -> grid reduction of (cells still active, particles streamed this pass, max iterations)
     uint32_t wn = __reduce_add_sync(0xffffffffu, still);
@@ -682,18 +718,25 @@ __global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCe
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (s_n) atomicAdd(&ctl.n_active[pass + 1], s_n);
         if (s_p) atomicAdd(ctl.active_particles, s_p);
         if (s_q) atomicAdd(ctl.active_particles + 1, s_q);
         if (s_it) atomicMax(ctl.level_iters, s_it);
-        __threadfence();
-        uint32_t ticket = atomicAdd(&ctl.done[pass], 1u);
-        if (ticket == gridDim.x - 1) {
+        uint32_t n = s_n;
+        bool last = true;
+        if (gridDim.x > 1) {
+            if (n) atomicAdd(&ctl.n_active[pass + 1], n);
             __threadfence();
-            uint32_t n = *((volatile uint32_t *)&ctl.n_active[pass + 1]);
-            ctl.h_status[pass] = n + 1u;   // mapped pinned memory: the host polls this, no stream sync
-            __threadfence_system();
+            last = atomicAdd(&ctl.done[pass], 1u) == gridDim.x - 1;
+            if (last) {
+                __threadfence();
+                n = *((volatile uint32_t *)&ctl.n_active[pass + 1]);
+            }
+        } else {
+            ctl.n_active[pass + 1] = n;
         }
+        // mapped pinned memory: the host polls this word, no stream sync; the store drains at the latest when the
+        // kernel retires, so no system-scope fence is spent on it
+        if (last) ctl.h_status[pass] = n + 1u;
     }
 }
 
@@ -803,15 +846,6 @@ __global__ void k_ranges_from_level(const orb_cell *__restrict__ cells, uint32_t
 // contain a cell boundary publish an inclusive prefix at once, so look-back chains restart at every
 // cell boundary.
 // =====================================================================================
-// ---- asynchronous tile loads (LDGSTS): global -> shared without staging in registers ----
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 // dynamic shared memory of the partition kernels
 struct PartSmem {
     float raw[2][3][kPartTile];       // double-buffered x,y,z tile (48 KB)

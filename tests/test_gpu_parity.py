@@ -126,6 +126,30 @@ def test_build_clustered_and_full_levels(orb, oracle, gen, full):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_signed_zero_coordinates(orb, oracle):
+    """-0.0 / +0.0 coordinates against cuts that are exactly +0.0 (the root's first cut is 0.0): the count kernel's
+    sign-of-difference compare must agree with the CPU's `x < cut` (countLeft.cpp:35)."""
+    n, d = 1 << 14, 8
+    rng = np.random.default_rng(3)
+    x = (rng.random(n, dtype=np.float32) - 0.5).astype(np.float32)
+    x[::3] = np.float32(-0.0)
+    x[1::7] = np.float32(0.0)
+    y = np.where(rng.random(n) < 0.5, np.float32(-0.0), np.float32(0.0)).astype(np.float32)
+    z = (rng.random(n, dtype=np.float32) - 0.5).astype(np.float32)
+    ref = oracle.build(x, y, z, d, ties=oracle.TIES_CANONICAL, full_levels=True)
+    for m in (1, 2, 3):
+        with orb.Orb(n, d) as ctx:
+            ctx.set_trial_depth(m)
+            ctx.upload(x, y, z)
+            heap, st = ctx.build(full_levels=True)
+            gx, gy, gz = ctx.download()
+            rng_ = ctx.ranges()
+        assert heap.tobytes() == ref["heap"].tobytes()
+        assert np.array_equal(rng_, ref["ranges"][0])
+        for a, b in ((gx, ref["x"]), (gy, ref["y"]), (gz, ref["z"])):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 def test_degenerate_inputs(orb, oracle):
     """All-equal coordinates (never converges: 32-iteration cap + extra count), duplicates on the cut."""
     n, d = 1 << 13, 16
