@@ -215,12 +215,11 @@ def main():
     ctx = orb.Orb(n_local, d, device=local)
     if args.trial_depth:
         ctx.set_trial_depth(args.trial_depth)
+    use_peers = os.environ.get("ORB_NO_PEER", "0") != "1"
     if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(orb.Orb.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        ctx.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        from gpu_load_balance_b200 import dist as orb_dist
+
+        orb_dist.connect(ctx, rank, world, device="cuda", peers=use_peers)
 
     def restore():
         ctx.load_device(pristine[0].data_ptr(), pristine[1].data_ptr(), pristine[2].data_ptr())
@@ -237,7 +236,8 @@ def main():
         restore()
         ctx.build(full_levels=args.full_levels, want_heap=False)
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:          # one nvidia-smi poller per job, not one per rank
+        sampler.start()
     barrier()
     t_wall0 = time.perf_counter()
     ms_steps, launches, st_last = [], 0, None
@@ -332,7 +332,8 @@ def main():
             "config": {
                 "workload": f"2^{args.x} {args.dist} particles per GPU (reference xorshf96 stream), 2^{args.y} leaf cells, "
                             f"{n_lv} split levels ({'full' if args.full_levels else 'reference-compatible'})",
-                "particles_total": n_local * world, "leaf_cells": d, "parallelism": f"particle shards x{world}, NCCL count allreduce",
+                "particles_total": n_local * world, "leaf_cells": d, "parallelism": (f"particle shards x{world}; per-cell counts combined " +
+                                                    ("inside the count kernel over NVLink peer memory" if (world > 1 and use_peers) else "by NCCL allreduce")),
                 "l2": "pristine particles restored + 256 MiB buffer written between timed steps (L2 flush)",
                 "trial_depth": args.trial_depth or 3,
             },

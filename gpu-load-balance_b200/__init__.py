@@ -89,6 +89,23 @@ class BuildStats(C.Structure):
         return int(self.count_launches + self.update_launches + self.partition_launches + self.other_launches)
 
 
+class PeerInfo(C.Structure):
+    """orb_peer_info: descriptor of one rank's counter rows for the fused count+combine (include/orb_b200.h)."""
+
+    _fields_ = [
+        ("ipc_cnt", C.c_uint8 * 64),
+        ("ipc_flag", C.c_uint8 * 64),
+        ("ptr_cnt", C.c_uint64),
+        ("ptr_flag", C.c_uint64),
+        ("pid", C.c_int64),
+        ("device", C.c_int32),
+        ("reserved_", C.c_int32),
+    ]
+
+
+PEER_INFO_BYTES = C.sizeof(PeerInfo)
+
+
 class OrbError(RuntimeError):
     pass
 
@@ -129,6 +146,8 @@ def lib() -> C.CDLL:
         "orb_comm_unique_id": ([P], C.c_int),
         "orb_comm_init": ([P, P, C.c_int, C.c_int], C.c_int),
         "orb_comm_attach": ([P, P, C.c_int, C.c_int], C.c_int),
+        "orb_peer_export": ([P, P], C.c_int),
+        "orb_peer_import": ([P, P, C.c_int], C.c_int),
         "orb_upload_xyz": ([P, P, P, P], C.c_int),
         "orb_load_device_xyz": ([P, P, P, P], C.c_int),
         "orb_download_xyz": ([P, P, P, P], C.c_int),
@@ -244,6 +263,18 @@ class Orb:
         assert len(unique_id) == 128
         buf = C.create_string_buffer(unique_id, 128)
         _check(lib().orb_comm_init(self._h, buf, rank, n_ranks), "orb_comm_init")
+
+    def peer_export(self) -> bytes:
+        """This rank's peer descriptor (PEER_INFO_BYTES bytes) for the fused count+combine."""
+        info = PeerInfo()
+        _check(lib().orb_peer_export(self._h, C.byref(info)), "orb_peer_export")
+        return bytes(info)
+
+    def peer_import(self, table: bytes, n_ranks: int):
+        """Descriptors of all ranks, concatenated in rank order (gathered by the caller)."""
+        assert len(table) == n_ranks * PEER_INFO_BYTES
+        buf = C.create_string_buffer(table, len(table))
+        _check(lib().orb_peer_import(self._h, buf, n_ranks), "orb_peer_import")
 
     # ---- particles
     def upload(self, x, y, z):

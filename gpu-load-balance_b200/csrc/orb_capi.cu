@@ -4,6 +4,7 @@
 // host only polling a mapped status word a bounded number of passes behind the GPU.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -126,6 +127,16 @@ struct orb_ctx {
     bool ownComm = false;
     int rank = 0, nRanks = 1;
 
+    // fused combine+update over NVLink peer memory (optional; see PeerSet in orb_kernels.cuh)
+    bool peerEnabled = false;
+    uint32_t peerSeq = 0;
+    uint32_t *d_peer_cnt = nullptr;    // receive rows [2][kMaxPeers][kPeerMaxCells][kCS]
+    uint32_t *d_peer_flag = nullptr;   // flags [2][kMaxPeers][kPeerMaxBlocks]
+    uint32_t *d_cdone = nullptr;       // [kMaxLevels*kPassSlots] per-pass "blocks finished" counters
+    uint32_t *peerCnt[orb::kMaxPeers] = {nullptr};
+    uint32_t *peerFlag[orb::kMaxPeers] = {nullptr};
+    bool peerIpc[orb::kMaxPeers] = {false};
+
     // launch accounting
     uint64_t nCountLaunch = 0, nUpdateLaunch = 0, nPartLaunch = 0, nOtherLaunch = 0;
 };
@@ -201,6 +212,12 @@ int launch_count_nc(orb_ctx *c, uint32_t nCells, const uint32_t *gate) {
     return ORB_OK;
 }
 
+orb::PeerSet no_peers() {
+    orb::PeerSet ps;
+    memset(&ps, 0, sizeof(ps));
+    return ps;
+}
+
 int launch_count(orb_ctx *c, uint32_t nCells, int nc, const uint32_t *gate) {
     using namespace orb;
     if (!c->nLocal) return ORB_OK;
@@ -238,13 +255,13 @@ int allreduce_counts(orb_ctx *c, uint32_t nCells, int nc) {
     return ORB_OK;
 }
 
-int launch_update(orb_ctx *c, uint32_t nCells, int M, int passSlot, orb::PassCtl ctl) {
+int launch_update(orb_ctx *c, uint32_t nCells, int M, int passSlot, orb::PassCtl ctl, const orb::PeerSet &ps) {
     using namespace orb;
     const uint32_t blocks = ceil_div(nCells, kThreads);
     switch (M) {
-    case 1: k_update<1><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl); break;
-    case 2: k_update<2><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl); break;
-    case 3: k_update<3><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl); break;
+    case 1: k_update<1><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl, ps); break;
+    case 2: k_update<2><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl, ps); break;
+    case 3: k_update<3><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl, ps); break;
     default: return fail(ORB_ERR_ARG, "unsupported trial depth %d", M);
     }
     c->nUpdateLaunch++;
@@ -271,13 +288,25 @@ int run_bisection(orb_ctx *c, uint32_t nCells, int M, int slotBase, int levelIdx
     ctl.active_particles = c->d_active_particles;
     ctl.level_iters = c->d_level_iters + levelIdx;
     volatile uint32_t *hs = c->h_status + slotBase;
+    // multi-rank combine: fused into the update kernel over peer memory when the level is small enough,
+    // otherwise an in-stream ncclAllReduce between count and update
+    const bool fused = c->nRanks > 1 && c->peerEnabled && nCells <= kPeerMaxCells;
     int launched = 0;
     for (;;) {
+        PeerSet ps = no_peers();
+        if (fused) {
+            ps.n = c->nRanks;
+            ps.self = c->rank;
+            ps.seq = ++c->peerSeq;
+            for (int r = 0; r < c->nRanks; ++r) { ps.recv[r] = c->peerCnt[r]; ps.flag[r] = c->peerFlag[r]; }
+        }
         int rc = launch_count(c, nCells, nc, ctl.n_active + launched);
         if (rc) return rc;
-        rc = allreduce_counts(c, nCells, nc);
-        if (rc) return rc;
-        rc = launch_update(c, nCells, M, launched, ctl);
+        if (!fused) {
+            rc = allreduce_counts(c, nCells, nc);
+            if (rc) return rc;
+        }
+        rc = launch_update(c, nCells, M, launched, ctl, ps);
         if (rc) return rc;
         launched++;
         if (launched >= maxPasses) break;
@@ -365,6 +394,7 @@ int reset_pass_ctl(orb_ctx *c) {
     CK(cudaMemsetAsync(c->d_nactive, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots, c->stream));
     CK(cudaMemsetAsync(c->d_done, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots, c->stream));
     CK(cudaMemsetAsync(c->d_tickets, 0, sizeof(uint32_t) * kMaxLevels, c->stream));
+    CK(cudaMemsetAsync(c->d_cdone, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots, c->stream));
     CK(cudaMemsetAsync(c->d_level_iters, 0, sizeof(int32_t) * kMaxLevels, c->stream));
     CK(cudaMemsetAsync(c->d_active_particles, 0, 2 * sizeof(unsigned long long), c->stream));
     // the previous call's speculative passes may still be writing status words: drain first
@@ -452,6 +482,11 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaMalloc(&c->d_tickets, sizeof(uint32_t) * kMaxLevels));
     CK(cudaMalloc(&c->d_nactive, sizeof(uint32_t) * kMaxLevels * kPassSlots));
     CK(cudaMalloc(&c->d_done, sizeof(uint32_t) * kMaxLevels * kPassSlots));
+    CK(cudaMalloc(&c->d_cdone, sizeof(uint32_t) * kMaxLevels * kPassSlots));
+    CK(cudaMalloc(&c->d_peer_cnt, sizeof(uint32_t) * 2 * orb::kMaxPeers * orb::kPeerMaxCells * orb::kCS));
+    CK(cudaMemset(c->d_peer_cnt, 0, sizeof(uint32_t) * 2 * orb::kMaxPeers * orb::kPeerMaxCells * orb::kCS));
+    CK(cudaMalloc(&c->d_peer_flag, sizeof(uint32_t) * 2 * orb::kMaxPeers * orb::kPeerMaxBlocks));
+    CK(cudaMemset(c->d_peer_flag, 0, sizeof(uint32_t) * 2 * orb::kMaxPeers * orb::kPeerMaxBlocks));
     CK(cudaMalloc(&c->d_misc, 64));
     CK(cudaMalloc(&c->d_active_particles, 16));
     CK(cudaMalloc(&c->d_level_iters, sizeof(int32_t) * kMaxLevels));
@@ -495,6 +530,9 @@ int orb_destroy(orb_ctx *c) {
     cudaFree(c->lv.nleaf); cudaFree(c->lv.active); cudaFree(c->lv.found); cudaFree(c->lv.iter);
     cudaFree(c->lv.nleft_g); cudaFree(c->lv.nleft_l); cudaFree(c->lv.cuts); cudaFree(c->lv.cnt_l);
     if (c->d_cnt_g_buf) cudaFree(c->d_cnt_g_buf);
+    for (int r = 0; r < orb::kMaxPeers; ++r)
+        if (c->peerIpc[r]) { cudaIpcCloseMemHandle(c->peerCnt[r]); cudaIpcCloseMemHandle(c->peerFlag[r]); }
+    cudaFree(c->d_cdone); cudaFree(c->d_peer_cnt); cudaFree(c->d_peer_flag);
     cudaFree(c->d_final_cut); cudaFree(c->d_tile_first); cudaFree(c->d_blk_left); cudaFree(c->d_blk_restart); cudaFree(c->d_tickets);
     cudaFree(c->d_nactive); cudaFree(c->d_done); cudaFree(c->d_misc); cudaFree(c->d_active_particles);
     cudaFree(c->d_level_iters); cudaFree(c->d_err); cudaFree(c->d_bb); cudaFree(c->d_bb6);
@@ -562,6 +600,59 @@ int orb_comm_attach(orb_ctx *c, void *nccl_comm, int rank, int n_ranks) {
     c->rank = rank;
     c->nRanks = n_ranks;
     return setup_multi(c);
+}
+
+// Peer memory for the fused count+combine.  Every rank exports a descriptor of its counter rows and flags, the caller
+// gathers the descriptors of all ranks (any transport) and hands the table to every rank.
+int orb_peer_export(orb_ctx *c, orb_peer_info *out) {
+    if (!c || !out) return fail(ORB_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    memset(out, 0, sizeof(*out));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->d_peer_cnt));
+    memcpy(out->ipc_cnt, &h, 64);
+    CK(cudaIpcGetMemHandle(&h, c->d_peer_flag));
+    memcpy(out->ipc_flag, &h, 64);
+    out->ptr_cnt = (uint64_t)(uintptr_t)c->d_peer_cnt;
+    out->ptr_flag = (uint64_t)(uintptr_t)c->d_peer_flag;
+    out->pid = (int64_t)getpid();
+    out->device = c->device;
+    return ORB_OK;
+}
+
+int orb_peer_import(orb_ctx *c, const orb_peer_info *all, int n_ranks) {
+    if (!c || !all) return fail(ORB_ERR_ARG, "null argument");
+    if (n_ranks != c->nRanks || n_ranks > orb::kMaxPeers) return fail(ORB_ERR_ARG, "peer table must have one entry per rank (<= %d)", orb::kMaxPeers);
+    CK(cudaSetDevice(c->device));
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == c->rank) {
+            c->peerCnt[r] = c->d_peer_cnt;
+            c->peerFlag[r] = c->d_peer_flag;
+        } else if (all[r].pid == (int64_t)getpid()) {
+            // same process (thread-per-GPU host): plain pointers + peer access
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, c->device, all[r].device));
+            if (!can) return fail(ORB_ERR_CUDA, "device %d cannot access peer %d", c->device, all[r].device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+            cudaGetLastError();
+            c->peerCnt[r] = (uint32_t *)(uintptr_t)all[r].ptr_cnt;
+            c->peerFlag[r] = (uint32_t *)(uintptr_t)all[r].ptr_flag;
+        } else {
+            cudaIpcMemHandle_t h;
+            void *p = nullptr;
+            memcpy(&h, all[r].ipc_cnt, 64);
+            CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            c->peerCnt[r] = (uint32_t *)p;
+            memcpy(&h, all[r].ipc_flag, 64);
+            CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            c->peerFlag[r] = (uint32_t *)p;
+            c->peerIpc[r] = true;
+        }
+    }
+    c->peerEnabled = true;
+    return ORB_OK;
 }
 
 // ---------------------------------------------------------------- particles

@@ -53,6 +53,29 @@ struct LevelState {
     uint32_t *cnt_g;      // [nCells][kCS] counters summed over ranks (== cnt_l on one rank)
 };
 
+// Peer view for the fused combine + bisection update (multi-GPU).  Every rank maps every rank's receive rows
+// and flags (NVLink peer memory).  k_update block b pushes the 32-byte count rows of its cells to all peers with
+// vector stores, raises flag[parity][self][b] on every peer, waits for the peers' block b, sums the rows and runs the
+// reference's decision rule: the collective (Combine of countLeft.cpp:44-53) and the compute are one kernel, there is
+// no NCCL call between count and update for levels of up to kPeerMaxCells cells.  Rows/flags are double-buffered by
+// pass parity (a rank can be at most one pass ahead of a peer).
+constexpr int kMaxPeers = 8;
+constexpr uint32_t kPeerMaxCells = 8192;
+constexpr uint32_t kPeerMaxBlocks = kPeerMaxCells / kThreads;
+struct PeerSet {
+    int n;                         // 0: disabled (single rank, or NCCL path)
+    int self;
+    uint32_t seq;                  // pass sequence number, identical on all ranks; parity = seq & 1
+    uint32_t *recv[kMaxPeers];     // rank r's receive rows: [2][kMaxPeers (source)][kPeerMaxCells][kCS]
+    uint32_t *flag[kMaxPeers];     // rank r's flags:        [2][kMaxPeers (source)][kPeerMaxBlocks]
+};
+__device__ __forceinline__ uint32_t *peer_rows(const PeerSet &ps, int r, int src) {
+    return ps.recv[r] + ((size_t)(ps.seq & 1u) * kMaxPeers + src) * kPeerMaxCells * kCS;
+}
+__device__ __forceinline__ uint32_t *peer_flag(const PeerSet &ps, int r, int src, uint32_t block) {
+    return ps.flag[r] + ((size_t)(ps.seq & 1u) * kMaxPeers + src) * kPeerMaxBlocks + block;
+}
+
 // float midpoint exactly as Cell::getCut (cell.h:74-76): float add, halve, round to float.
 // (R+L)/2.0 in double then cast == correctly rounded half of the float sum == __fmul_rn(sum,0.5f).
 __device__ __forceinline__ float mid_cut(float L, float R) { return __fmul_rn(__fadd_rn(R, L), 0.5f); }
@@ -633,9 +656,33 @@ struct PassCtl {
 };
 
 template <int M>
-__global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCells, int pass, PassCtl ctl) {
+__global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCells, int pass, PassCtl ctl, PeerSet ps) {
     constexpr int NC = (1 << M) - 1;
     const uint32_t gate = ctl.n_active[pass];
+    const uint32_t cT = blockIdx.x * blockDim.x + threadIdx.x;   // this thread's cell
+    if (ps.n && gate != 0u) {
+        // ---- phase A: push this block's local count rows to every peer, then raise this block's flag there ----
+        if (cT < nCells) {
+            const uint4 a0 = *reinterpret_cast<const uint4 *>(lv.cnt_l + cT * kCS), a1 = *reinterpret_cast<const uint4 *>(lv.cnt_l + cT * kCS + 4);
+            for (int r = 0; r < ps.n; ++r) {
+                if (r == ps.self) continue;
+                uint4 *dst = reinterpret_cast<uint4 *>(peer_rows(ps, r, ps.self) + cT * kCS);
+                dst[0] = a0;
+                dst[1] = a1;
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < ps.n && (int)threadIdx.x != ps.self)
+            *((volatile uint32_t *)peer_flag(ps, threadIdx.x, ps.self, blockIdx.x)) = ps.seq;
+        // ---- phase B: wait for block `blockIdx.x` of every peer ----
+        if ((int)threadIdx.x < ps.n && (int)threadIdx.x != ps.self) {
+            volatile uint32_t *f = peer_flag(ps, ps.self, threadIdx.x, blockIdx.x);
+            while ((int32_t)(*f - ps.seq) < 0) {}
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     __shared__ uint32_t s_n;
     __shared__ unsigned long long s_p, s_q;
     __shared__ int s_it;
@@ -648,7 +695,18 @@ __global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCe
     if (gate != 0u && c < nCells && lv.active[c]) {
         // everything the decision needs is fetched up front (one memory latency): the counted nodes are picked from
         // registers afterwards
-        const uint4 g0 = *reinterpret_cast<const uint4 *>(lv.cnt_g + c * kCS), g1 = *reinterpret_cast<const uint4 *>(lv.cnt_g + c * kCS + 4);
+        uint4 g0 = *reinterpret_cast<const uint4 *>(lv.cnt_g + c * kCS), g1 = *reinterpret_cast<const uint4 *>(lv.cnt_g + c * kCS + 4);
+        if (ps.n) {   // ---- phase C: sum over ranks (own row is cnt_l == cnt_g source here, peers' rows arrived in recv) ----
+            g0 = *reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS);
+            g1 = *reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS + 4);
+            for (int r = 0; r < ps.n; ++r) {
+                if (r == ps.self) continue;
+                const uint4 *src = reinterpret_cast<const uint4 *>(peer_rows(ps, ps.self, r) + c * kCS);
+                const uint4 b0 = __ldcg(src), b1 = __ldcg(src + 1);
+                g0.x += b0.x; g0.y += b0.y; g0.z += b0.z; g0.w += b0.w;
+                g1.x += b1.x; g1.y += b1.y; g1.z += b1.z; g1.w += b1.w;
+            }
+        }
         const uint4 l0 = *reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS), l1 = *reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS + 4);
         const float4 q0 = *reinterpret_cast<const float4 *>(lv.cuts + c * kCS), q1 = *reinterpret_cast<const float4 *>(lv.cuts + c * kCS + 4);
         const uint32_t cg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};

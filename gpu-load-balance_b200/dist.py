@@ -41,3 +41,26 @@ def reduce_scalar(value: float, op: str = "max", device="cpu") -> float:
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def all_gather_bytes(payload: bytes, device="cpu") -> bytes:
+    """Concatenation over ranks (in rank order) of equal-length byte strings (peer descriptors)."""
+    import torch
+    import torch.distributed as dist
+
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(device)
+    parts = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, mine)
+    return b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+
+
+def connect(ctx, rank: int, world: int, device="cuda", peers: bool = True):
+    """Give an Orb context its communicator (NCCL id broadcast) and, optionally, the peer-memory table that lets
+    the count kernel combine counts over NVLink by itself."""
+    from . import Orb
+
+    uid = Orb.comm_unique_id() if rank == 0 else None
+    uid = broadcast_bytes(uid, 128, 0, device=device)
+    ctx.comm_init(uid, rank, world)
+    if peers:
+        ctx.peer_import(all_gather_bytes(ctx.peer_export(), device=device), world)

@@ -1,6 +1,7 @@
 // services.cpp — Service()/Combine() bodies: thin calls into the C ABI (include/orb_b200.h).
 #include "services.h"
 
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -20,6 +21,20 @@ inline orb_cell *asOrb(void *cells) { return static_cast<orb_cell *>(cells); }
 // one NCCL id per launch, made by whichever rank thread arrives first
 std::once_flag g_idOnce;
 unsigned char g_ncclId[128];
+
+// peer descriptors of all rank threads (fused count+combine over NVLink); a counting barrier separates
+// "everyone exported" from "everyone imports"
+orb_peer_info g_peers[8];
+std::mutex g_peerMutex;
+std::condition_variable g_peerCv;
+int g_peerArrived = 0;
+void peerBarrier(int nRanks) {
+    std::unique_lock<std::mutex> lk(g_peerMutex);
+    const int target = ((g_peerArrived / nRanks) + 1) * nRanks;
+    ++g_peerArrived;
+    g_peerCv.notify_all();
+    g_peerCv.wait(lk, [&] { return g_peerArrived >= target; });
+}
 }  // namespace
 
 // ------------------------------------------------------------------ Init (init.cu:27-144)
@@ -44,6 +59,13 @@ int ServiceInit::Service(PST pst, void *vin, int, void *, int) {
     if (lcl->nRanks > 1) {
         std::call_once(g_idOnce, [] { ORB_CHECK(orb_comm_unique_id(g_ncclId)); });
         ORB_CHECK(orb_comm_init(lcl->ctx, g_ncclId, lcl->rank, lcl->nRanks));
+        const char *noPeer = std::getenv("ORB_NO_PEER");
+        if (lcl->nRanks <= 8 && !(noPeer && std::atoi(noPeer) != 0)) {
+            ORB_CHECK(orb_peer_export(lcl->ctx, &g_peers[lcl->rank]));
+            peerBarrier(lcl->nRanks);
+            ORB_CHECK(orb_peer_import(lcl->ctx, g_peers, lcl->nRanks));
+            peerBarrier(lcl->nRanks);
+        }
     }
     return 0;
 }

@@ -89,6 +89,24 @@ int orb_comm_unique_id(void *id128);
 int orb_comm_init(orb_ctx *ctx, const void *id128, int rank, int n_ranks);
 int orb_comm_attach(orb_ctx *ctx, void *nccl_comm, int rank, int n_ranks);
 
+/* Optional: fuse the count combine into the bisection-update kernel.  Each rank exports a descriptor of its receive
+ * rows (cudaMalloc memory: CUDA IPC handle for other processes, raw pointer for rank threads of the same process);
+ * the caller gathers all descriptors and imports the table on every rank (after orb_comm_init / orb_comm_attach).
+ * From then on, levels of up to 8192 cells combine their per-cell counts inside the update kernel: every block pushes
+ * its count rows to all peers over NVLink, flags them, waits for the peers' rows and decides - no collective call
+ * between count and update; larger levels keep NCCL. */
+typedef struct orb_peer_info {
+    uint8_t ipc_cnt[64];
+    uint8_t ipc_flag[64];
+    uint64_t ptr_cnt;
+    uint64_t ptr_flag;
+    int64_t pid;
+    int32_t device;
+    int32_t reserved_;
+} orb_peer_info;
+int orb_peer_export(orb_ctx *ctx, orb_peer_info *out);
+int orb_peer_import(orb_ctx *ctx, const orb_peer_info *all, int n_ranks);
+
 /* ---- particles (replaces ServiceCopyParticles o=2: copyParticles.cu:29-57) ---- */
 int orb_upload_xyz(orb_ctx *ctx, const float *x, const float *y, const float *z);     /* host -> device, sets range[0]=[0,n_local) */
 int orb_load_device_xyz(orb_ctx *ctx, const float *dx, const float *dy, const float *dz); /* device -> device */
