@@ -287,6 +287,16 @@ def main():
                         "launches_per_step": int(stp.partition_launches), "ms_per_step": part_ms, "share_of_step": part_ms / tot_prof_ms,
                         "algorithmic_bytes_per_step": part_bytes},
     }
+    # DRAM traffic per launch from the committed ncu --set full capture (profiles/r01_ncu_traffic.json)
+    try:
+        tr = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text())
+        for kname, rec in tr.items():
+            if kname in kernels:
+                kernels[kname]["traffic"] = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+                kernels[kname]["traffic_note"] = (f"ncu dram bytes of one launch ({rec['launch']}); algorithmic bytes of that "
+                                                  f"launch: {rec['algorithmic_bytes_same_launch']}")
+    except Exception:
+        pass
     dom = "k_count" if cnt_ms >= part_ms else "k_partition"
     roofline = dict(kernels[dom], kernel=dom, peak_source=peak_src)
 

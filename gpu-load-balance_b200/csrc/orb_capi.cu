@@ -118,6 +118,7 @@ struct orb_ctx {
     int occPartStream = 1, occPartCells = 1;   // resident blocks per SM of the partition kernels
     int trialDepth = 3;
     int runAhead = 1;
+    bool fuseUpdate = true;
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evCount, evPart;
     size_t evCountUsed = 0, evPartUsed = 0;
@@ -193,7 +194,7 @@ int level_prepare(orb_ctx *c, const orb_cell *d_cells, uint32_t nCells, int nc, 
 //   >= 1024       : k_count_cells, one block per cell
 //   otherwise     : k_count_cells, one warp per cell
 template <int NC>
-int launch_count_nc(orb_ctx *c, uint32_t nCells, const uint32_t *gate) {
+int launch_count_nc(orb_ctx *c, uint32_t nCells, const uint32_t *gate, const orb::FuseCtl &fc) {
     using namespace orb;
     const uint64_t avg = c->nLocal / nCells;
     const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
@@ -201,13 +202,13 @@ int launch_count_nc(orb_ctx *c, uint32_t nCells, const uint32_t *gate) {
         const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
         const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * 4u);
         const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
-        k_count_stream<NC><<<grid, kThreads, ringBytes, c->stream>>>(x, y, z, c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate);
+        k_count_stream<NC><<<grid, kThreads, ringBytes, c->stream>>>(x, y, z, c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate, fc);
     } else if (avg >= 1024) {
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * 4u);
-        k_count_cells<NC, 256><<<grid, kThreads, 0, c->stream>>>(x, y, z, c->lv, nCells, gate);
+        k_count_cells<NC, 256><<<grid, kThreads, 0, c->stream>>>(x, y, z, c->lv, nCells, gate, fc);
     } else {
         const uint32_t grid = std::min<uint32_t>(ceil_div(nCells, kWarps), (uint32_t)c->nSM * 4u);
-        k_count_cells<NC, 32><<<grid, kThreads, 0, c->stream>>>(x, y, z, c->lv, nCells, gate);
+        k_count_cells<NC, 32><<<grid, kThreads, 0, c->stream>>>(x, y, z, c->lv, nCells, gate, fc);
     }
     return ORB_OK;
 }
@@ -218,9 +219,15 @@ orb::PeerSet no_peers() {
     return ps;
 }
 
-int launch_count(orb_ctx *c, uint32_t nCells, int nc, const uint32_t *gate) {
+orb::FuseCtl no_fuse() {
+    orb::FuseCtl fc;
+    memset(&fc, 0, sizeof(fc));
+    return fc;
+}
+
+int launch_count(orb_ctx *c, uint32_t nCells, int nc, const uint32_t *gate, const orb::FuseCtl &fc = no_fuse()) {
     using namespace orb;
-    if (!c->nLocal) return ORB_OK;
+    if (!c->nLocal && !fc.enabled) return ORB_OK;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->profile) {
         if (c->evCountUsed == c->evCount.size()) {
@@ -235,9 +242,9 @@ int launch_count(orb_ctx *c, uint32_t nCells, int nc, const uint32_t *gate) {
         CK(cudaEventRecord(e0, c->stream));
     }
     switch (nc) {
-    case 1: launch_count_nc<1>(c, nCells, gate); break;
-    case 3: launch_count_nc<3>(c, nCells, gate); break;
-    case 7: launch_count_nc<7>(c, nCells, gate); break;
+    case 1: launch_count_nc<1>(c, nCells, gate, fc); break;
+    case 3: launch_count_nc<3>(c, nCells, gate, fc); break;
+    case 7: launch_count_nc<7>(c, nCells, gate, fc); break;
     default: return fail(ORB_ERR_ARG, "unsupported trial count %d", nc);
     }
     if (c->profile) CK(cudaEventRecord(e1, c->stream));
@@ -300,14 +307,21 @@ int run_bisection(orb_ctx *c, uint32_t nCells, int M, int slotBase, int levelIdx
             ps.seq = ++c->peerSeq;
             for (int r = 0; r < c->nRanks; ++r) { ps.recv[r] = c->peerCnt[r]; ps.flag[r] = c->peerFlag[r]; }
         }
-        int rc = launch_count(c, nCells, nc, ctl.n_active + launched);
+        // single rank, small level: the count kernel's last block runs the update itself (one launch per pass)
+        FuseCtl fc = no_fuse();
+        if (c->nRanks == 1 && nCells <= kFuseMaxCells && c->nLocal > 0 && c->fuseUpdate) {
+            fc.enabled = 1; fc.M = M; fc.pass = launched; fc.tickets = c->d_cdone + slotBase; fc.ctl = ctl;
+        }
+        int rc = launch_count(c, nCells, nc, ctl.n_active + launched, fc);
         if (rc) return rc;
-        if (!fused) {
-            rc = allreduce_counts(c, nCells, nc);
+        if (!fc.enabled) {
+            if (!fused) {
+                rc = allreduce_counts(c, nCells, nc);
+                if (rc) return rc;
+            }
+            rc = launch_update(c, nCells, M, launched, ctl, ps);
             if (rc) return rc;
         }
-        rc = launch_update(c, nCells, M, launched, ctl, ps);
-        if (rc) return rc;
         launched++;
         if (launched >= maxPasses) break;
         // Decide deterministically (identically on every rank): look at the status of pass
@@ -512,6 +526,8 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     c->profile = p && atoi(p) != 0;
     const char *td = getenv("ORB_TRIAL_DEPTH");
     if (td && atoi(td) >= 1 && atoi(td) <= 3) c->trialDepth = atoi(td);
+    const char *fu = getenv("ORB_FUSE_UPDATE");
+    if (fu) c->fuseUpdate = atoi(fu) != 0;
     const char *ra = getenv("ORB_RUN_AHEAD");
     if (ra && atoi(ra) >= 0 && atoi(ra) <= 8) c->runAhead = atoi(ra);
     CK(cudaDeviceSynchronize());

@@ -260,6 +260,146 @@ __device__ __forceinline__ void unpack_bins(unsigned &lo, unsigned &hi, unsigned
     hi = 0u;
 }
 
+struct PassCtl {
+    uint32_t *n_active;        // device: [maxPasses+2] active cells after pass p (index p+1); [0] = before first pass
+    uint32_t *done;            // device: [maxPasses+2] block tickets
+    volatile uint32_t *h_status;   // pinned host: [maxPasses+2] n_active+1 after pass p (0 = not yet known)
+    unsigned long long *active_particles;   // device: [0] local particles streamed (cells active in a pass, per HBM pass)
+                                            //         [1] the same weighted by bisection iterations consumed (reference-equivalent)
+    int32_t *level_iters;      // device: max iterations over cells (the reference's j)
+};
+
+
+// One cell's bisection decisions for the pass just counted (orbit.cpp:191-231): up to M steps over the counted
+// trial-cut tree, literal float arithmetic of the reference.  g0/g1 = the eight global counters of the cell.
+// Returns 1 if the cell stays active.  npart / nipart / it feed the pass statistics.
+template <int M>
+__device__ __forceinline__ uint32_t update_cell(const LevelState &lv, uint32_t c, uint4 g0, uint4 g1,
+                                                unsigned long long &npart, unsigned long long &nipart, int &it) {
+    constexpr int NC = (1 << M) - 1;
+    const uint4 l0 = __ldcg(reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS)), l1 = __ldcg(reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS + 4));
+    const float4 q0 = *reinterpret_cast<const float4 *>(lv.cuts + c * kCS), q1 = *reinterpret_cast<const float4 *>(lv.cuts + c * kCS + 4);
+    const uint32_t cg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const uint32_t cl8[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+    const float cu[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    float L = lv.mL[c], R = lv.mR[c];
+    it = lv.iter[c];
+    const int it0 = it;
+    const uint32_t total = lv.total[c];
+    const int nleaf = lv.nleaf[c];
+    const float ratio = (float)(ceil(nleaf / 2.0) / nleaf);          // orbit.cpp:204
+    const float prod = __fmul_rn(__uint2float_rn(total), ratio);      // oCounts[i] * ratio
+    npart = (unsigned long long)(lv.bnd[c + 1] - lv.bnd[c]);
+    int node = 0;
+    bool fnd = false;
+#pragma unroll
+    for (int s = 0; s < M; ++s) {
+        float cut = 0.f;
+        uint32_t cnt = 0, cntl = 0;
+#pragma unroll
+        for (int k = 0; k < NC; ++k)
+            if (k == node) { cut = cu[k]; cnt = cg[k]; cntl = cl8[k]; }
+        const int diff = __float2int_rz(__fsub_rn(__uint2float_rn(cnt), prod));   // orbit.cpp:205
+        ++it;
+        if (abs(diff) < 3) {                                                      // orbit.cpp:208
+            fnd = true;
+            lv.nleft_g[c] = cnt;
+            lv.nleft_l[c] = cntl;
+            break;
+        } else if (diff > 0) { R = cut; node = 2 * node + 1; }                    // orbit.cpp:219
+        else { L = cut; node = 2 * node + 2; }                                    // orbit.cpp:227
+        if (it >= kMaxIter) break;                                                // orbit.cpp:149
+    }
+    lv.mL[c] = L; lv.mR[c] = R; lv.iter[c] = it;
+    nipart = npart * (unsigned long long)(it - it0);
+    uint32_t still = 0;
+    if (fnd) { lv.found[c] = 1u; lv.active[c] = 0u; }
+    else if (it >= kMaxIter) { lv.active[c] = 0u; }
+    else {
+        still = 1;
+        float cv[8], lo[7], hi[7];
+        lo[0] = L; hi[0] = R;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cv[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            cv[k] = mid_cut(lo[k], hi[k]);
+            if (2 * k + 2 < NC) { lo[2 * k + 1] = lo[k]; hi[2 * k + 1] = cv[k]; lo[2 * k + 2] = cv[k]; hi[2 * k + 2] = hi[k]; }
+        }
+        *reinterpret_cast<float4 *>(lv.cuts + c * kCS) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        *reinterpret_cast<float4 *>(lv.cuts + c * kCS + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+    }
+    *reinterpret_cast<uint4 *>(lv.cnt_l + c * kCS) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4 *>(lv.cnt_l + c * kCS + 4) = make_uint4(0u, 0u, 0u, 0u);
+    return still;
+}
+
+// Single-rank fusion of the update into the count kernel: the block that finishes last (ticket) runs the
+// decisions for every cell of the level, so a pass is ONE launch.  Used for levels of up to kFuseMaxCells cells.
+constexpr uint32_t kFuseMaxCells = 4096;
+struct FuseCtl {
+    int enabled;        // 0: separate k_update launch
+    int M;              // bisection steps per pass
+    int pass;
+    uint32_t *tickets;  // [pass slots] blocks finished (zeroed per build)
+    PassCtl ctl;
+};
+
+template <int M>
+__device__ __forceinline__ void fused_update_tail(const LevelState &lv, uint32_t nCells, const FuseCtl &fc) {
+    __shared__ int s_last;
+    __shared__ uint32_t s_n;
+    __shared__ unsigned long long s_p, s_q;
+    __shared__ int s_it;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&fc.tickets[fc.pass], 1u) == gridDim.x - 1) ? 1 : 0;
+        s_n = 0; s_p = 0ull; s_q = 0ull; s_it = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    uint32_t still = 0;
+    unsigned long long npS = 0, nipS = 0;
+    int itMax = 0;
+    for (uint32_t c = threadIdx.x; c < nCells; c += blockDim.x) {
+        if (!lv.active[c]) continue;
+        const uint4 g0 = __ldcg(reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS)), g1 = __ldcg(reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS + 4));
+        unsigned long long np = 0, nip = 0;
+        int it = 0;
+        still += update_cell<M>(lv, c, g0, g1, np, nip, it);
+        npS += np; nipS += nip; itMax = max(itMax, it);
+    }
+    still = __reduce_add_sync(0xffffffffu, still);
+    itMax = __reduce_max_sync(0xffffffffu, itMax);
+    for (int o = 16; o; o >>= 1) {
+        npS += __shfl_xor_sync(0xffffffffu, npS, o);
+        nipS += __shfl_xor_sync(0xffffffffu, nipS, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (still) atomicAdd(&s_n, still);
+        if (npS) atomicAdd(&s_p, npS);
+        if (nipS) atomicAdd(&s_q, nipS);
+        if (itMax) atomicMax(&s_it, itMax);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_p) atomicAdd(fc.ctl.active_particles, s_p);
+        if (s_q) atomicAdd(fc.ctl.active_particles + 1, s_q);
+        if (s_it) atomicMax(fc.ctl.level_iters, s_it);
+        fc.ctl.n_active[fc.pass + 1] = s_n;
+        fc.ctl.h_status[fc.pass] = s_n + 1u;
+    }
+}
+
+__device__ __forceinline__ void fused_update_dispatch(const LevelState &lv, uint32_t nCells, const FuseCtl &fc) {
+    if (!fc.enabled) return;
+    if (fc.M == 3) fused_update_tail<3>(lv, nCells, fc);
+    else if (fc.M == 2) fused_update_tail<2>(lv, nCells, fc);
+    else fused_update_tail<1>(lv, nCells, fc);
+}
+
 // ---- asynchronous tile loads (LDGSTS): global -> shared without staging in registers ----
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -403,8 +543,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
                                                               const float *__restrict__ z, LevelState lv,
                                                               const uint32_t *__restrict__ tile_first, uint32_t nCells,
                                                               uint32_t nLocal, uint32_t nTiles,
-                                                              const uint32_t *__restrict__ gate) {
-    if (gate && *gate == 0u) return;   // speculative pass after convergence: nothing to do
+                                                              const uint32_t *__restrict__ gate, FuseCtl fc) {
+    if (gate && *gate == 0u) {   // speculative pass after convergence: nothing to count
+        if (fc.enabled && blockIdx.x == 0 && threadIdx.x == 0) { fc.ctl.n_active[fc.pass + 1] = 0u; fc.ctl.h_status[fc.pass] = 1u; }
+        return;
+    }
     constexpr int NB = Acc<NC>::NB;
     extern __shared__ __align__(16) unsigned char count_smem[];       // kCountStages x 16 KB ring
     float4 *ring = reinterpret_cast<float4 *>(count_smem);
@@ -538,6 +681,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
         __syncthreads();
     }
     flush();
+    fused_update_dispatch(lv, nCells, fc);
 }
 
 // ---- regime B: cells of at most a few tiles.  One group of G threads per cell (G = 256: block, G = 32: warp);
@@ -545,8 +689,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
 template <int NC, int G>
 __global__ void __launch_bounds__(kThreads, 4) k_count_cells(const float *__restrict__ x, const float *__restrict__ y,
                                                              const float *__restrict__ z, LevelState lv, uint32_t nCells,
-                                                             const uint32_t *__restrict__ gate) {
-    if (gate && *gate == 0u) return;
+                                                             const uint32_t *__restrict__ gate, FuseCtl fc) {
+    if (gate && *gate == 0u) {
+        if (fc.enabled && blockIdx.x == 0 && threadIdx.x == 0) { fc.ctl.n_active[fc.pass + 1] = 0u; fc.ctl.h_status[fc.pass] = 1u; }
+        return;
+    }
     constexpr int NB = Acc<NC>::NB;
     constexpr int GPB = kThreads / G;                 // groups per block
     __shared__ uint32_t s_acc[GPB][kWarps][NB];       // only used when G == 256
@@ -639,6 +786,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_cells(const float *__rest
             }
         }
     }
+    fused_update_dispatch(lv, nCells, fc);
 }
 
 // =====================================================================================
@@ -646,15 +794,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_cells(const float *__rest
 // M steps per pass over the counted trial-cut tree; literal float arithmetic of the reference:
 //   float ratio = ceil(nLeafCells/2.0)/nLeafCells;  int difference = countLeft - count*ratio;
 // =====================================================================================
-struct PassCtl {
-    uint32_t *n_active;        // device: [maxPasses+2] active cells after pass p (index p+1); [0] = before first pass
-    uint32_t *done;            // device: [maxPasses+2] block tickets
-    volatile uint32_t *h_status;   // pinned host: [maxPasses+2] n_active+1 after pass p (0 = not yet known)
-    unsigned long long *active_particles;   // device: [0] local particles streamed (cells active in a pass, per HBM pass)
-                                            //         [1] the same weighted by bisection iterations consumed (reference-equivalent)
-    int32_t *level_iters;      // device: max iterations over cells (the reference's j)
-};
-
 template <int M>
 __global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCells, int pass, PassCtl ctl, PeerSet ps) {
     constexpr int NC = (1 << M) - 1;
@@ -693,10 +832,8 @@ __global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCe
     unsigned long long npart = 0, nipart = 0;
     int it = 0;
     if (gate != 0u && c < nCells && lv.active[c]) {
-        // everything the decision needs is fetched up front (one memory latency): the counted nodes are picked from
-        // registers afterwards
         uint4 g0 = *reinterpret_cast<const uint4 *>(lv.cnt_g + c * kCS), g1 = *reinterpret_cast<const uint4 *>(lv.cnt_g + c * kCS + 4);
-        if (ps.n) {   // ---- phase C: sum over ranks (own row is cnt_l == cnt_g source here, peers' rows arrived in recv) ----
+        if (ps.n) {   // ---- phase C: sum over ranks (own row from cnt_l, the peers' rows have arrived in recv) ----
             g0 = *reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS);
             g1 = *reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS + 4);
             for (int r = 0; r < ps.n; ++r) {
@@ -707,59 +844,7 @@ __global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCe
                 g1.x += b1.x; g1.y += b1.y; g1.z += b1.z; g1.w += b1.w;
             }
         }
-        const uint4 l0 = *reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS), l1 = *reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS + 4);
-        const float4 q0 = *reinterpret_cast<const float4 *>(lv.cuts + c * kCS), q1 = *reinterpret_cast<const float4 *>(lv.cuts + c * kCS + 4);
-        const uint32_t cg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const uint32_t cl8[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-        const float cu[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        float L = lv.mL[c], R = lv.mR[c];
-        it = lv.iter[c];
-        const int it0 = it;
-        const uint32_t total = lv.total[c];
-        const int nleaf = lv.nleaf[c];
-        const float ratio = (float)(ceil(nleaf / 2.0) / nleaf);          // orbit.cpp:204
-        const float prod = __fmul_rn(__uint2float_rn(total), ratio);      // oCounts[i] * ratio
-        npart = (unsigned long long)(lv.bnd[c + 1] - lv.bnd[c]);
-        int node = 0;
-        bool fnd = false;
-#pragma unroll
-        for (int s = 0; s < M; ++s) {
-            float cut = 0.f;
-            uint32_t cnt = 0, cntl = 0;
-#pragma unroll
-            for (int k = 0; k < NC; ++k)
-                if (k == node) { cut = cu[k]; cnt = cg[k]; cntl = cl8[k]; }
-            const int diff = __float2int_rz(__fsub_rn(__uint2float_rn(cnt), prod));   // orbit.cpp:205
-            ++it;
-            if (abs(diff) < 3) {                                                      // orbit.cpp:208
-                fnd = true;
-                lv.nleft_g[c] = cnt;
-                lv.nleft_l[c] = cntl;
-                break;
-            } else if (diff > 0) { R = cut; node = 2 * node + 1; }                    // orbit.cpp:219
-            else { L = cut; node = 2 * node + 2; }                                    // orbit.cpp:227
-            if (it >= kMaxIter) break;                                                // orbit.cpp:149
-        }
-        lv.mL[c] = L; lv.mR[c] = R; lv.iter[c] = it;
-        nipart = npart * (unsigned long long)(it - it0);
-        if (fnd) { lv.found[c] = 1u; lv.active[c] = 0u; }
-        else if (it >= kMaxIter) { lv.active[c] = 0u; }
-        else {
-            still = 1;
-            float cv[8], lo[7], hi[7];
-            lo[0] = L; hi[0] = R;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) cv[k] = 0.f;
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                cv[k] = mid_cut(lo[k], hi[k]);
-                if (2 * k + 2 < NC) { lo[2 * k + 1] = lo[k]; hi[2 * k + 1] = cv[k]; lo[2 * k + 2] = cv[k]; hi[2 * k + 2] = hi[k]; }
-            }
-            *reinterpret_cast<float4 *>(lv.cuts + c * kCS) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-            *reinterpret_cast<float4 *>(lv.cuts + c * kCS + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
-        }
-        *reinterpret_cast<uint4 *>(lv.cnt_l + c * kCS) = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4 *>(lv.cnt_l + c * kCS + 4) = make_uint4(0u, 0u, 0u, 0u);
+        still = update_cell<M>(lv, c, g0, g1, npart, nipart, it);
     }
     // block -> grid reduction of (cells still active, particles streamed this pass, max iterations)
     uint32_t wn = __reduce_add_sync(0xffffffffu, still);

@@ -267,3 +267,64 @@ def test_full_size_properties_c2(orb, oracle):
     leaves = heap[(1 << st.n_levels) - 1:(1 << (st.n_levels + 1)) - 1]
     sizes = rng[leaves["id"], 1] - rng[leaves["id"], 0]
     assert sizes.sum() == n and sizes.min() >= 8188 - 8 and sizes.max() <= 8196 + 8
+
+
+def _check_build_properties(orb, oracle, x, y, z, d, heap, rng, gx, gy, gz, n_levels, sample=48):
+    n = x.size
+    assert oracle.set_hash(gx, gy, gz) == oracle.set_hash(x, y, z)          # multiset of particles conserved
+    cols = (gx, gy, gz)
+    for l in range(1, n_levels + 1):
+        a = (1 << (l - 1)) - 1
+        cells = heap[a:a + (1 << (l - 1))]
+        for c in cells[:: max(1, cells.size // sample)]:
+            lid, rid = 2 * (c["id"] + 1) - 1, 2 * (c["id"] + 1)
+            assert rng[lid][0] == rng[c["id"]][0] and rng[lid][1] == rng[rid][0] and rng[rid][1] == rng[c["id"]][1]
+            cut = oracle.get_cut(c)
+            col = cols[c["cutAxis"]]
+            assert (col[rng[lid][0]:rng[lid][1]] < cut).all()
+            assert (col[rng[rid][0]:rng[rid][1]] >= cut).all()
+    leaves = heap[(1 << n_levels) - 1:(1 << (n_levels + 1)) - 1]
+    sizes = rng[leaves["id"], 1].astype(np.int64) - rng[leaves["id"], 0]
+    assert sizes.sum() == n
+    return sizes
+
+
+def test_full_size_properties_c3(orb, oracle):
+    """BASELINE config 2 per-GPU size class: 2^27 uniform particles, 2^16 leaf cells (beyond the reference's MAX_CELLS):
+    conservation, child partition of parents, left < cut <= right, iteration pattern of SURVEY.md Appendix B."""
+    n, d = 1 << 27, 1 << 16
+    x, y, z = orb.generate_uniform(n)
+    with orb.Orb(n, d) as ctx:
+        ctx.upload(x, y, z)
+        heap, st = ctx.build()
+        gx, gy, gz = ctx.download()
+        rng = ctx.ranges()
+    assert st.n_levels == 15
+    # known answers from the canonical-mode oracle run here on the CPU (`oracle/orb_oracle 27 16 --ties=canonical`,
+    # 42 s): iterations per level, one level-4 cell hits the 32-iteration cap (455 tie particles: the generator's
+    # values sit on a 2^-25 grid, duplicates make |difference| < 3 unreachable there), range hash of the leaf level.
+    # (The verbatim-Hoare run of SURVEY.md Appendix B has 23 iterations at level 4: its tie particles fall differently.)
+    assert list(st.iters[:15]) == [17, 25, 23, 32, 22, 21, 20, 20, 19, 18, 17, 17, 16, 15, 15]
+    assert list(st.not_found[:15]) == [0, 0, 0, 1] + [0] * 11
+    h = 1469598103934665603
+    for i in range((1 << 15) - 1, (1 << 16) - 1):
+        h = ((h ^ int(rng[i][1])) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    assert h == 0xD4F00F38C84CA6F5
+    _check_build_properties(orb, oracle, x, y, z, d, heap, rng, gx, gy, gz, st.n_levels)
+
+
+@pytest.mark.parametrize("kind", ["gaussian", "plummer"])
+def test_full_size_properties_c4_clustered(orb, oracle, kind):
+    """BASELINE config 3: 2^26 clustered particles, 2^14 leaf cells: skewed cells, many iterations, empty regions."""
+    n, d = 1 << 26, 1 << 14
+    x, y, z = orb.generate_clustered(n, kind)
+    with orb.Orb(n, d) as ctx:
+        ctx.upload(x, y, z)
+        heap, st = ctx.build()
+        gx, gy, gz = ctx.download()
+        rng = ctx.ranges()
+    assert st.n_levels == 13
+    sizes = _check_build_properties(orb, oracle, x, y, z, d, heap, rng, gx, gy, gz, st.n_levels)
+    # the reference's |difference| < 3 rule balances every split to within a few particles unless a cell hit the cap
+    if sum(st.not_found[:13]) == 0:
+        assert sizes.max() - sizes.min() <= 64
