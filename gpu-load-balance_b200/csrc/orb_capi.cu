@@ -119,6 +119,11 @@ struct orb_ctx {
     int trialDepth = 3;
     int runAhead = 1;
     bool fuseUpdate = true;
+    bool compaction = true;
+    bool persist = true;           // host-free level loop (k_level_persistent) where it applies
+    int occPersist[4] = {0, 0, 0, 0}; // resident blocks per SM of k_level_persistent<M>
+    int32_t *d_lvl_passes = nullptr;  // [kMaxLevels]
+    uint32_t *d_lvl_unfound = nullptr; // [kMaxLevels]
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evCount, evPart;
     size_t evCountUsed = 0, evPartUsed = 0;
@@ -189,21 +194,29 @@ int level_prepare(orb_ctx *c, const orb_cell *d_cells, uint32_t nCells, int nc, 
     return ORB_OK;
 }
 
+// cells of at least 16 tiles on average: the tile-streaming kernel (and the byte-reducing search) apply
+inline bool count_streams(const orb_ctx *c, uint32_t nCells) { return c->nLocal / nCells >= 16ull * orb::kCountTile; }
+
 // Count pass over all active cells of the level.  Kernel choice by average local cell size:
 //   >= 16 tiles   : k_count_stream (persistent, tile streaming, one atomic per block per (cell,cut))
 //   >= 1024       : k_count_cells, one block per cell
 //   otherwise     : k_count_cells, one warp per cell
 template <int NC>
-int launch_count_nc(orb_ctx *c, uint32_t nCells, const uint32_t *gate, const orb::FuseCtl &fc) {
+int launch_count_nc(orb_ctx *c, uint32_t nCells, const uint32_t *gate, const orb::FuseCtl &fc, int mode) {
     using namespace orb;
-    const uint64_t avg = c->nLocal / nCells;
     const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
-    if (avg >= 16ull * kCountTile) {
+    float *cand = c->x[c->cur ^ 1];   // the idle ping-pong column holds the candidates of the byte-reducing search
+    if (count_streams(c, nCells)) {
         const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
         const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * 4u);
         const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
-        k_count_stream<NC><<<grid, kThreads, ringBytes, c->stream>>>(x, y, z, c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate, fc);
-    } else if (avg >= 1024) {
+        if (NC == 7 && mode == kCountCompact)
+            k_count_stream<7, kCountCompact><<<grid, kThreads, ringBytes, c->stream>>>(x, y, z, cand, c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate, fc);
+        else if (NC == 7 && mode == kCountCand)
+            k_count_stream<7, kCountCand><<<grid, kThreads, ringBytes, c->stream>>>(x, y, z, cand, c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate, fc);
+        else
+            k_count_stream<NC, kCountFull><<<grid, kThreads, ringBytes, c->stream>>>(x, y, z, cand, c->lv, c->d_tile_first, nCells, (uint32_t)c->nLocal, nTiles, gate, fc);
+    } else if (c->nLocal / nCells >= 1024) {
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * 4u);
         k_count_cells<NC, 256><<<grid, kThreads, 0, c->stream>>>(x, y, z, c->lv, nCells, gate, fc);
     } else {
@@ -225,7 +238,7 @@ orb::FuseCtl no_fuse() {
     return fc;
 }
 
-int launch_count(orb_ctx *c, uint32_t nCells, int nc, const uint32_t *gate, const orb::FuseCtl &fc = no_fuse()) {
+int launch_count(orb_ctx *c, uint32_t nCells, int nc, const uint32_t *gate, const orb::FuseCtl &fc = no_fuse(), int mode = 0) {
     using namespace orb;
     if (!c->nLocal && !fc.enabled) return ORB_OK;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -242,9 +255,9 @@ int launch_count(orb_ctx *c, uint32_t nCells, int nc, const uint32_t *gate, cons
         CK(cudaEventRecord(e0, c->stream));
     }
     switch (nc) {
-    case 1: launch_count_nc<1>(c, nCells, gate, fc); break;
-    case 3: launch_count_nc<3>(c, nCells, gate, fc); break;
-    case 7: launch_count_nc<7>(c, nCells, gate, fc); break;
+    case 1: launch_count_nc<1>(c, nCells, gate, fc, mode); break;
+    case 3: launch_count_nc<3>(c, nCells, gate, fc, mode); break;
+    case 7: launch_count_nc<7>(c, nCells, gate, fc, mode); break;
     default: return fail(ORB_ERR_ARG, "unsupported trial count %d", nc);
     }
     if (c->profile) CK(cudaEventRecord(e1, c->stream));
@@ -262,13 +275,13 @@ int allreduce_counts(orb_ctx *c, uint32_t nCells, int nc) {
     return ORB_OK;
 }
 
-int launch_update(orb_ctx *c, uint32_t nCells, int M, int passSlot, orb::PassCtl ctl, const orb::PeerSet &ps) {
+int launch_update(orb_ctx *c, uint32_t nCells, int M, int passSlot, orb::PassCtl ctl, const orb::PeerSet &ps, int baseMode) {
     using namespace orb;
     const uint32_t blocks = ceil_div(nCells, kThreads);
     switch (M) {
-    case 1: k_update<1><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl, ps); break;
-    case 2: k_update<2><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl, ps); break;
-    case 3: k_update<3><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl, ps); break;
+    case 1: k_update<1><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl, ps, baseMode); break;
+    case 2: k_update<2><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl, ps, baseMode); break;
+    case 3: k_update<3><<<blocks, kThreads, 0, c->stream>>>(c->lv, nCells, passSlot, ctl, ps, baseMode); break;
     default: return fail(ORB_ERR_ARG, "unsupported trial depth %d", M);
     }
     c->nUpdateLaunch++;
@@ -307,19 +320,23 @@ int run_bisection(orb_ctx *c, uint32_t nCells, int M, int slotBase, int levelIdx
             ps.seq = ++c->peerSeq;
             for (int r = 0; r < c->nRanks; ++r) { ps.recv[r] = c->peerCnt[r]; ps.flag[r] = c->peerFlag[r]; }
         }
+        // byte-reducing search: pass 0 reads everything and fixes the bracket, pass 1 compacts, later passes read candidates
+        const bool compacting = c->compaction && M == 3 && c->nLocal > 0 && count_streams(c, nCells);
+        const int mode = !compacting ? kCountFull : (launched == 0 ? kCountFull : (launched == 1 ? kCountCompact : kCountCand));
+        const int baseMode = !compacting ? 0 : (launched == 0 ? 1 : 2);
         // single rank, small level: the count kernel's last block runs the update itself (one launch per pass)
         FuseCtl fc = no_fuse();
         if (c->nRanks == 1 && nCells <= kFuseMaxCells && c->nLocal > 0 && c->fuseUpdate) {
-            fc.enabled = 1; fc.M = M; fc.pass = launched; fc.tickets = c->d_cdone + slotBase; fc.ctl = ctl;
+            fc.enabled = 1; fc.M = M; fc.pass = launched; fc.baseMode = baseMode; fc.tickets = c->d_cdone + slotBase; fc.ctl = ctl;
         }
-        int rc = launch_count(c, nCells, nc, ctl.n_active + launched, fc);
+        int rc = launch_count(c, nCells, nc, ctl.n_active + launched, fc, mode);
         if (rc) return rc;
         if (!fc.enabled) {
             if (!fused) {
                 rc = allreduce_counts(c, nCells, nc);
                 if (rc) return rc;
             }
-            rc = launch_update(c, nCells, M, launched, ctl, ps);
+            rc = launch_update(c, nCells, M, launched, ctl, ps, baseMode);
             if (rc) return rc;
         }
         launched++;
@@ -334,6 +351,50 @@ int run_bisection(orb_ctx *c, uint32_t nCells, int M, int slotBase, int levelIdx
         }
     }
     if (passesOut) *passesOut = launched;
+    return ORB_OK;
+}
+
+// Whole bisection loop of a level in ONE cooperative launch (k_level_persistent): single rank, streaming regime.
+bool level_can_persist(const orb_ctx *c, uint32_t nCells, int M) {
+    return c->persist && c->nRanks == 1 && c->nLocal > 0 && nCells <= orb::kPersistMaxCells && count_streams(c, nCells) &&
+           M >= 1 && M <= 3 && c->occPersist[M] >= 1;
+}
+
+int launch_level_persistent(orb_ctx *c, uint32_t nCells, int M, int slotBase, int levelIdx) {
+    using namespace orb;
+    const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
+    const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(c->occPersist[M], 4));
+    const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
+    float *cand = c->x[c->cur ^ 1];
+    uint32_t nC = nCells, nL = (uint32_t)c->nLocal, nT = nTiles;
+    LevelCtl lc;
+    lc.n_active = c->d_nactive + slotBase;
+    lc.active_particles = c->d_active_particles;
+    lc.level_iters = c->d_level_iters + levelIdx;
+    lc.passes_out = c->d_lvl_passes + levelIdx;
+    lc.n_unfound_out = c->d_lvl_unfound + levelIdx;
+    lc.compaction = (c->compaction && M == 3) ? 1 : 0;
+    void *args[] = {(void *)&x, (void *)&y, (void *)&z, (void *)&cand, (void *)&c->lv, (void *)&c->d_tile_first,
+                    (void *)&nC, (void *)&nL, (void *)&nT, (void *)&lc};
+    const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profile) {
+        if (c->evCountUsed == c->evCount.size()) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            c->evCount.emplace_back(a, b);
+        }
+        e0 = c->evCount[c->evCountUsed].first;
+        e1 = c->evCount[c->evCountUsed].second;
+        c->evCountUsed++;
+        CK(cudaEventRecord(e0, c->stream));
+    }
+    const void *fn = M == 3 ? (const void *)k_level_persistent<3> : (M == 2 ? (const void *)k_level_persistent<2> : (const void *)k_level_persistent<1>);
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, ringBytes, c->stream));
+    if (c->profile) CK(cudaEventRecord(e1, c->stream));
+    c->nCountLaunch++;
+    CK(cudaGetLastError());
     return ORB_OK;
 }
 
@@ -409,6 +470,8 @@ int reset_pass_ctl(orb_ctx *c) {
     CK(cudaMemsetAsync(c->d_done, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots, c->stream));
     CK(cudaMemsetAsync(c->d_tickets, 0, sizeof(uint32_t) * kMaxLevels, c->stream));
     CK(cudaMemsetAsync(c->d_cdone, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots, c->stream));
+    CK(cudaMemsetAsync(c->d_lvl_passes, 0, sizeof(int32_t) * kMaxLevels, c->stream));
+    CK(cudaMemsetAsync(c->d_lvl_unfound, 0, sizeof(uint32_t) * kMaxLevels, c->stream));
     CK(cudaMemsetAsync(c->d_level_iters, 0, sizeof(int32_t) * kMaxLevels, c->stream));
     CK(cudaMemsetAsync(c->d_active_particles, 0, 2 * sizeof(unsigned long long), c->stream));
     // the previous call's speculative passes may still be writing status words: drain first
@@ -488,6 +551,15 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaMalloc(&c->lv.cuts, L * orb::kCS * 4));
     CK(cudaMalloc(&c->lv.cnt_l, L * orb::kCS * 4));
     c->lv.cnt_g = c->lv.cnt_l;
+    CK(cudaMalloc(&c->lv.compL, L * 4));
+    CK(cudaMalloc(&c->lv.compR, L * 4));
+    CK(cudaMalloc(&c->lv.base_l, L * 4));
+    CK(cudaMemset(c->lv.base_l, 0, L * 4));
+    {
+        const size_t nCountTiles = ceil_div(n_local, orb::kCountTile) + 1;
+        CK(cudaMalloc(&c->lv.tile_ncand, nCountTiles * orb::kWarps * 4));
+        CK(cudaMemset(c->lv.tile_ncand, 0, nCountTiles * orb::kWarps * 4));
+    }
     CK(cudaMalloc(&c->d_final_cut, L * 4));
     const size_t nMap = ceil_div(n_local, orb::kMapTile) + 1;
     CK(cudaMalloc(&c->d_tile_first, nMap * 4));
@@ -501,6 +573,8 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaMemset(c->d_peer_cnt, 0, sizeof(uint32_t) * 2 * orb::kMaxPeers * orb::kPeerMaxCells * orb::kCS));
     CK(cudaMalloc(&c->d_peer_flag, sizeof(uint32_t) * 2 * orb::kMaxPeers * orb::kPeerMaxBlocks));
     CK(cudaMemset(c->d_peer_flag, 0, sizeof(uint32_t) * 2 * orb::kMaxPeers * orb::kPeerMaxBlocks));
+    CK(cudaMalloc(&c->d_lvl_passes, sizeof(int32_t) * kMaxLevels));
+    CK(cudaMalloc(&c->d_lvl_unfound, sizeof(uint32_t) * kMaxLevels));
     CK(cudaMalloc(&c->d_misc, 64));
     CK(cudaMalloc(&c->d_active_particles, 16));
     CK(cudaMalloc(&c->d_level_iters, sizeof(int32_t) * kMaxLevels));
@@ -513,9 +587,20 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaHostGetDevicePointer((void **)&c->h_status_dev, (void *)c->h_status, 0));
     {
         const int ringBytes = orb::kCountStages * orb::kCountTile * (int)sizeof(float);
-        CK(cudaFuncSetAttribute(orb::k_count_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
-        CK(cudaFuncSetAttribute(orb::k_count_stream<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
-        CK(cudaFuncSetAttribute(orb::k_count_stream<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
+        CK(cudaFuncSetAttribute(orb::k_count_stream<1, orb::kCountFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
+        CK(cudaFuncSetAttribute(orb::k_count_stream<3, orb::kCountFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
+        CK(cudaFuncSetAttribute(orb::k_count_stream<7, orb::kCountFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
+        CK(cudaFuncSetAttribute(orb::k_count_stream<7, orb::kCountCompact>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
+        CK(cudaFuncSetAttribute(orb::k_count_stream<7, orb::kCountCand>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
+    }
+    {
+        const int ringBytes = orb::kCountStages * orb::kCountTile * (int)sizeof(float);
+        CK(cudaFuncSetAttribute(orb::k_level_persistent<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
+        CK(cudaFuncSetAttribute(orb::k_level_persistent<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
+        CK(cudaFuncSetAttribute(orb::k_level_persistent<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ringBytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occPersist[1], orb::k_level_persistent<1>, orb::kThreads, ringBytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occPersist[2], orb::k_level_persistent<2>, orb::kThreads, ringBytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occPersist[3], orb::k_level_persistent<3>, orb::kThreads, ringBytes));
     }
     CK(cudaFuncSetAttribute(orb::k_partition_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(orb::PartSmem)));
     CK(cudaFuncSetAttribute(orb::k_partition_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(orb::PartSmem)));
@@ -526,6 +611,10 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     c->profile = p && atoi(p) != 0;
     const char *td = getenv("ORB_TRIAL_DEPTH");
     if (td && atoi(td) >= 1 && atoi(td) <= 3) c->trialDepth = atoi(td);
+    const char *pe = getenv("ORB_PERSIST");
+    if (pe) c->persist = atoi(pe) != 0;
+    const char *cp = getenv("ORB_COMPACT");
+    if (cp) c->compaction = atoi(cp) != 0;
     const char *fu = getenv("ORB_FUSE_UPDATE");
     if (fu) c->fuseUpdate = atoi(fu) != 0;
     const char *ra = getenv("ORB_RUN_AHEAD");
@@ -545,10 +634,11 @@ int orb_destroy(orb_ctx *c) {
     cudaFree(c->lv.bnd); cudaFree(c->lv.axis); cudaFree(c->lv.mL); cudaFree(c->lv.mR); cudaFree(c->lv.total);
     cudaFree(c->lv.nleaf); cudaFree(c->lv.active); cudaFree(c->lv.found); cudaFree(c->lv.iter);
     cudaFree(c->lv.nleft_g); cudaFree(c->lv.nleft_l); cudaFree(c->lv.cuts); cudaFree(c->lv.cnt_l);
+    cudaFree(c->lv.compL); cudaFree(c->lv.compR); cudaFree(c->lv.base_l); cudaFree(c->lv.tile_ncand);
     if (c->d_cnt_g_buf) cudaFree(c->d_cnt_g_buf);
     for (int r = 0; r < orb::kMaxPeers; ++r)
         if (c->peerIpc[r]) { cudaIpcCloseMemHandle(c->peerCnt[r]); cudaIpcCloseMemHandle(c->peerFlag[r]); }
-    cudaFree(c->d_cdone); cudaFree(c->d_peer_cnt); cudaFree(c->d_peer_flag);
+    cudaFree(c->d_lvl_passes); cudaFree(c->d_lvl_unfound); cudaFree(c->d_cdone); cudaFree(c->d_peer_cnt); cudaFree(c->d_peer_flag);
     cudaFree(c->d_final_cut); cudaFree(c->d_tile_first); cudaFree(c->d_blk_left); cudaFree(c->d_blk_restart); cudaFree(c->d_tickets);
     cudaFree(c->d_nactive); cudaFree(c->d_done); cudaFree(c->d_misc); cudaFree(c->d_active_particles);
     cudaFree(c->d_level_iters); cudaFree(c->d_err); cudaFree(c->d_bb); cudaFree(c->d_bb6);
@@ -925,15 +1015,23 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         rc = level_prepare(c, c->d_heap + first, nCells, (1 << M) - 1, c->d_nactive + slot);
         if (rc) return rc;
         int np = 0;
-        rc = run_bisection(c, nCells, M, slot, l - 1, &np);
-        if (rc) return rc;
-        passes.push_back(np);
         uint32_t nu = 0;
-        // only a level that used every pass can have unfound cells
-        if (np >= (kMaxIter + M - 1) / M) {
-            rc = finalize_unfound(c, nCells, &nu);
+        if (level_can_persist(c, nCells, M)) {
+            // host-free: the whole loop (and the extra count of capped cells) is one cooperative launch;
+            // passes / unfound are read back with the other statistics after the build
+            rc = launch_level_persistent(c, nCells, M, slot, l - 1);
             if (rc) return rc;
+            np = -1;
+        } else {
+            rc = run_bisection(c, nCells, M, slot, l - 1, &np);
+            if (rc) return rc;
+            // only a level that used every pass can have unfound cells
+            if (np >= (kMaxIter + M - 1) / M) {
+                rc = finalize_unfound(c, nCells, &nu);
+                if (rc) return rc;
+            }
         }
+        passes.push_back(np);
         unfound.push_back(nu);
         k_split<<<ceil_div(nCells, 256), 256, 0, c->stream>>>(c->d_heap, first, nCells, c->lv, c->d_range, c->d_total, c->d_final_cut);
         c->nOtherLaunch++;
@@ -954,7 +1052,10 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
     }
     CK(cudaEventRecord(evB, c->stream));
     if (heap_out) CK(cudaMemcpyAsync(heap_out, c->d_heap, (size_t)c->nHeap * sizeof(orb_cell), cudaMemcpyDeviceToHost, c->stream));
-    int32_t iters[kMaxLevels];
+    int32_t iters[kMaxLevels], lvlPasses[kMaxLevels];
+    uint32_t lvlUnfound[kMaxLevels];
+    CK(cudaMemcpyAsync(lvlPasses, c->d_lvl_passes, sizeof(lvlPasses), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(lvlUnfound, c->d_lvl_unfound, sizeof(lvlUnfound), cudaMemcpyDeviceToHost, c->stream));
     unsigned long long ap[2] = {0, 0};
     CK(cudaMemcpyAsync(iters, c->d_level_iters, sizeof(iters), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(ap, c->d_active_particles, 16, cudaMemcpyDeviceToHost, c->stream));
@@ -965,8 +1066,8 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         stats->n_levels = nDone;
         for (int l = 0; l < nDone && l < 64; ++l) {
             stats->iters[l] = iters[l];
-            stats->passes[l] = passes[l];
-            stats->not_found[l] = (int32_t)unfound[l];
+            stats->passes[l] = passes[l] >= 0 ? passes[l] : lvlPasses[l];
+            stats->not_found[l] = passes[l] >= 0 ? (int32_t)unfound[l] : (int32_t)lvlUnfound[l];
         }
         stats->active_passes = ap[0];
         stats->iter_particle_passes = ap[1];

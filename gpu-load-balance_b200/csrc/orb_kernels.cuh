@@ -51,6 +51,11 @@ struct LevelState {
     float *cuts;          // [nCells][kCS] trial cuts of the next pass, heap order of the bisection tree
     uint32_t *cnt_l;      // [nCells][kCS] local counters (k_count output)
     uint32_t *cnt_g;      // [nCells][kCS] counters summed over ranks (== cnt_l on one rank)
+    // byte-reducing search: once the first pass of a level has fixed the bracket [compL, compR),
+    // the second pass compacts the particles inside it; later passes only read those candidates
+    float *compL, *compR; // [nCells] bracket at compaction time (-inf / +inf if that side never moved)
+    uint32_t *base_l;     // [nCells] local particles below compL in compacted tiles (added to every later count)
+    uint32_t *tile_ncand; // [nCountTiles][kWarps] candidates stored per (tile, warp)
 };
 
 // Peer view for the fused combine + bisection update (multi-GPU).  Every rank maps every rank's receive rows
@@ -273,9 +278,12 @@ struct PassCtl {
 // One cell's bisection decisions for the pass just counted (orbit.cpp:191-231): up to M steps over the counted
 // trial-cut tree, literal float arithmetic of the reference.  g0/g1 = the eight global counters of the cell.
 // Returns 1 if the cell stays active.  npart / nipart / it feed the pass statistics.
+// baseMode: 0 = counters restart from zero; 1 = this was the first pass of a level that will compact: record the
+// bracket, clear the base; 2 = candidates are in place: counters restart from the cell's base.
 template <int M>
 __device__ __forceinline__ uint32_t update_cell(const LevelState &lv, uint32_t c, uint4 g0, uint4 g1,
-                                                unsigned long long &npart, unsigned long long &nipart, int &it) {
+                                                unsigned long long &npart, unsigned long long &nipart, int &it,
+                                                int baseMode = 0) {
     constexpr int NC = (1 << M) - 1;
     const uint4 l0 = __ldcg(reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS)), l1 = __ldcg(reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS + 4));
     const float4 q0 = *reinterpret_cast<const float4 *>(lv.cuts + c * kCS), q1 = *reinterpret_cast<const float4 *>(lv.cuts + c * kCS + 4);
@@ -291,7 +299,7 @@ __device__ __forceinline__ uint32_t update_cell(const LevelState &lv, uint32_t c
     const float prod = __fmul_rn(__uint2float_rn(total), ratio);      // oCounts[i] * ratio
     npart = (unsigned long long)(lv.bnd[c + 1] - lv.bnd[c]);
     int node = 0;
-    bool fnd = false;
+    bool fnd = false, movedL = false, movedR = false;
 #pragma unroll
     for (int s = 0; s < M; ++s) {
         float cut = 0.f;
@@ -306,11 +314,16 @@ __device__ __forceinline__ uint32_t update_cell(const LevelState &lv, uint32_t c
             lv.nleft_g[c] = cnt;
             lv.nleft_l[c] = cntl;
             break;
-        } else if (diff > 0) { R = cut; node = 2 * node + 1; }                    // orbit.cpp:219
-        else { L = cut; node = 2 * node + 2; }                                    // orbit.cpp:227
+        } else if (diff > 0) { R = cut; movedR = true; node = 2 * node + 1; }     // orbit.cpp:219
+        else { L = cut; movedL = true; node = 2 * node + 2; }                     // orbit.cpp:227
         if (it >= kMaxIter) break;                                                // orbit.cpp:149
     }
     lv.mL[c] = L; lv.mR[c] = R; lv.iter[c] = it;
+    if (baseMode == 1) {
+        lv.compL[c] = movedL ? L : __int_as_float(0xff800000);
+        lv.compR[c] = movedR ? R : __int_as_float(0x7f800000);
+        lv.base_l[c] = 0u;
+    }
     nipart = npart * (unsigned long long)(it - it0);
     uint32_t still = 0;
     if (fnd) { lv.found[c] = 1u; lv.active[c] = 0u; }
@@ -329,8 +342,9 @@ __device__ __forceinline__ uint32_t update_cell(const LevelState &lv, uint32_t c
         *reinterpret_cast<float4 *>(lv.cuts + c * kCS) = make_float4(cv[0], cv[1], cv[2], cv[3]);
         *reinterpret_cast<float4 *>(lv.cuts + c * kCS + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
     }
-    *reinterpret_cast<uint4 *>(lv.cnt_l + c * kCS) = make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4 *>(lv.cnt_l + c * kCS + 4) = make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t b0 = (baseMode == 2) ? __ldcg(lv.base_l + c) : 0u;
+    *reinterpret_cast<uint4 *>(lv.cnt_l + c * kCS) = make_uint4(b0, b0, b0, b0);
+    *reinterpret_cast<uint4 *>(lv.cnt_l + c * kCS + 4) = make_uint4(b0, b0, b0, b0);
     return still;
 }
 
@@ -341,6 +355,7 @@ struct FuseCtl {
     int enabled;        // 0: separate k_update launch
     int M;              // bisection steps per pass
     int pass;
+    int baseMode;       // see update_cell
     uint32_t *tickets;  // [pass slots] blocks finished (zeroed per build)
     PassCtl ctl;
 };
@@ -368,7 +383,7 @@ __device__ __forceinline__ void fused_update_tail(const LevelState &lv, uint32_t
         const uint4 g0 = __ldcg(reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS)), g1 = __ldcg(reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS + 4));
         unsigned long long np = 0, nip = 0;
         int it = 0;
-        still += update_cell<M>(lv, c, g0, g1, np, nip, it);
+        still += update_cell<M>(lv, c, g0, g1, np, nip, it, fc.baseMode);
         npS += np; nipS += nip; itMax = max(itMax, it);
     }
     still = __reduce_add_sync(0xffffffffu, still);
@@ -469,7 +484,7 @@ __device__ __forceinline__ void count_fragmented_tile(const float *__restrict__ 
             const uint32_t b = lv.bnd[cc], e = lv.bnd[cc + 1];
             if (b >= segEnd) break;
             const uint32_t lo_e = max(b, seg), hi_e = min(e, segEnd);
-            if (hi_e > lo_e && lv.active[cc]) {
+            if (hi_e > lo_e && __ldcg(&lv.active[cc])) {
                 const float *cl = pick_col(lv.axis[cc], x, y, z);
                 float v[4];
                 bool in[4];
@@ -487,7 +502,7 @@ __device__ __forceinline__ void count_fragmented_tile(const float *__restrict__ 
                 }
                 float ccv[NC];
 #pragma unroll
-                for (int k = 0; k < NC; ++k) ccv[k] = lv.cuts[cc * kCS + k];
+                for (int k = 0; k < NC; ++k) ccv[k] = __ldcg(&lv.cuts[cc * kCS + k]);
                 unsigned n[NC];
 #pragma unroll
                 for (int k = 0; k < NC; ++k) n[k] = 0u;
@@ -531,43 +546,65 @@ __device__ __forceinline__ void count_fragmented_tile(const float *__restrict__ 
     __syncthreads();
 }
 
-// ---- regime A: cells much larger than a tile.  Persistent blocks, tile u = blockIdx + i*grid. ------------
-// Phase 1: every thread classifies one of the block's tiles (cell, stream / skip / fragmented) - two
-// memory latencies for the whole block instead of a dependent chain per tile.  Phase 2: the streamable
-// tiles run through a register double buffer (the next tile's four 128-bit loads are issued before the
-// current tile is counted); counters persist across tiles of one cell.
+// ---- regime A: cells much larger than a tile.  Persistent blocks, block b owns a contiguous range of tiles. ----
+// Phase 1: every thread classifies one of the block's tiles (cell, stream / skip / fragmented) and caches the cell's
+// cuts in shared memory - two memory latencies for the whole block instead of a dependent chain per tile.
+// Phase 2: the streamable tiles run through a per-thread cp.async ring; counters persist across tiles of one cell.
+//
+// MODE (byte-reducing search; only with NC == 7):
+//   kCountFull     every pass reads the whole cut-axis column of the active cells;
+//   kCountCompact  second pass of a level: particles inside the bracket [compL, compR) fixed by the first pass are
+//                  binned AND written, per warp, to the warp's 512-slot region of the idle ping-pong column
+//                  (`cand`), the number kept per (tile, warp) goes to tile_ncand; particles below compL are only
+//                  counted (they are left of every later cut) and summed into base_l;
+//   kCountCand     later passes read just those candidates: counts = base_l + #{cand < cut}.
+// Tiles that contain a cell boundary are never compacted: they are recounted in full every pass.
 constexpr int kMaxUnits = 64;    // tiles classified per round
 constexpr int kCountStages = 3;  // depth of the per-thread cp.async ring (tiles in flight per block: kCountStages - 1)
+constexpr int kCountFull = 0, kCountCompact = 1, kCountCand = 2;
+constexpr int kWarpSlots = kCountTile / kWarps;   // candidate slots per (tile, warp)
+
+// static shared memory of one streaming count pass (one instance per kernel)
 template <int NC>
-__global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__restrict__ x, const float *__restrict__ y,
-                                                              const float *__restrict__ z, LevelState lv,
-                                                              const uint32_t *__restrict__ tile_first, uint32_t nCells,
-                                                              uint32_t nLocal, uint32_t nTiles,
-                                                              const uint32_t *__restrict__ gate, FuseCtl fc) {
-    if (gate && *gate == 0u) {   // speculative pass after convergence: nothing to count
-        if (fc.enabled && blockIdx.x == 0 && threadIdx.x == 0) { fc.ctl.n_active[fc.pass + 1] = 0u; fc.ctl.h_status[fc.pass] = 1u; }
-        return;
-    }
+struct CountSmem {
+    uint32_t acc[Acc<NC>::NB + 1];                        // [NB] = particles below compL (compact mode)
+    uint32_t cell[kCountCellsSmem * NC];
+    uint32_t uTile[kMaxUnits], uCell[kMaxUnits];          // compacted streamable tiles
+    int uAx[kMaxUnits];
+    alignas(16) float uCuts[kMaxUnits][kCS];              // their cells' trial cuts (no global load on a cell change)
+    float uBr[kMaxUnits][2];                              // compact mode: bracket of the unit's cell
+    alignas(16) uint32_t uN[kMaxUnits][kWarps];           // cand mode: candidates per warp region
+    uint32_t fTile[kMaxUnits], fCell[kMaxUnits];          // fragmented tiles
+    uint32_t wS[kWarps], wF[kWarps];
+};
+
+// One streaming count pass over this block's tiles (block-uniform call; ends with all counters flushed).
+template <int NC, int MODE>
+__device__ __forceinline__ void stream_count_pass(const float *__restrict__ x, const float *__restrict__ y,
+                                                  const float *__restrict__ z, float *__restrict__ cand,
+                                                  const LevelState &lv, const uint32_t *__restrict__ tile_first,
+                                                  uint32_t nCells, uint32_t nLocal, uint32_t nTiles, float4 *ring,
+                                                  CountSmem<NC> &sm) {
     constexpr int NB = Acc<NC>::NB;
-    extern __shared__ __align__(16) unsigned char count_smem[];       // kCountStages x 16 KB ring
-    float4 *ring = reinterpret_cast<float4 *>(count_smem);
-    __shared__ uint32_t s_acc[NB];
-    __shared__ uint32_t s_cell[kCountCellsSmem * NC];
-    __shared__ uint32_t s_uTile[kMaxUnits], s_uCell[kMaxUnits];   // compacted streamable tiles
-    __shared__ int s_uAx[kMaxUnits];
-    __shared__ __align__(16) float s_uCuts[kMaxUnits][kCS];       // their cells' trial cuts (no global load on a cell change)
-    __shared__ uint32_t s_fTile[kMaxUnits], s_fCell[kMaxUnits];   // fragmented tiles
-    __shared__ uint32_t s_wS[kWarps], s_wF[kWarps];
+    uint32_t *s_acc = sm.acc, *s_cell = sm.cell, *s_uTile = sm.uTile, *s_uCell = sm.uCell, *s_fTile = sm.fTile, *s_fCell = sm.fCell;
+    uint32_t *s_wS = sm.wS, *s_wF = sm.wF;
+    int *s_uAx = sm.uAx;
+    float(*s_uCuts)[kCS] = sm.uCuts;
+    float(*s_uBr)[2] = sm.uBr;
+    uint32_t(*s_uN)[kWarps] = sm.uN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < NB) s_acc[tid] = 0u;
+    __syncthreads();
+    if (tid <= NB) s_acc[tid] = 0u;
 
     Acc<NC> acc;
     acc.clear();
+    unsigned below = 0u;
     float cv[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) cv[k] = 0.f;
     Cuts7 k7;
     k7.c0 = 0.f; k7.c2b = k7.d21 = k7.c4b = k7.d43 = k7.c6b = k7.d65 = 0;
+    float brL = 0.f, brR = 0.f;
     int cur = -1;
 
     // One global atomic per block per (cell, cut): warp REDUX -> shared -> global.  Atomics to the few counter
@@ -582,15 +619,22 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
             if (lane == 0 && v) atomicAdd(&s_acc[k], v);
             acc.a[k] = 0u;
         }
+        if (MODE == kCountCompact) {
+            const unsigned v = __reduce_add_sync(0xffffffffu, below);
+            if (lane == 0 && v) atomicAdd(&s_acc[NB], v);
+            below = 0u;
+        }
         __syncthreads();
         if (tid < NC) {
             unsigned v;
             if constexpr (NC == 7) v = cum_from_bins(s_acc, tid);
             else v = s_acc[tid];
+            if (MODE == kCountCompact) v += s_acc[NB];            // particles below the bracket are left of every cut
             if (v) atomicAdd(&lv.cnt_l[(uint32_t)cur * kCS + tid], v);
         }
+        if (MODE == kCountCompact && tid == NC && s_acc[NB]) atomicAdd(&lv.base_l[cur], s_acc[NB]);
         __syncthreads();
-        if (tid < NB) s_acc[tid] = 0u;
+        if (tid <= NB) s_acc[tid] = 0u;
         __syncthreads();
     };
 
@@ -598,6 +642,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
     // once or twice per pass instead of once per tile.
     const uint32_t tilesPerBlock = (nTiles + gridDim.x - 1) / gridDim.x;
     const uint32_t tb0 = min(blockIdx.x * tilesPerBlock, nTiles), tb1 = min(tb0 + tilesPerBlock, nTiles);
+
     for (uint32_t base = tb0; base < tb1; base += (uint32_t)kMaxUnits) {
         // ---- phase 1: classify up to kMaxUnits tiles of this block ----
         const uint32_t t = base + (uint32_t)tid;
@@ -609,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
             c = tile_first[t * (kCountTile / kMapTile)];
             const uint32_t cb = lv.bnd[c], ce = lv.bnd[c + 1];
             ax = lv.axis[c];
-            if (cb <= t0 && ce >= t1 && (t1 - t0) == (uint32_t)kCountTile) kind = lv.active[c] ? 1 : 0;
+            if (cb <= t0 && ce >= t1 && (t1 - t0) == (uint32_t)kCountTile) kind = __ldcg(&lv.active[c]) ? 1 : 0;
             else kind = 2;
         }
         const unsigned mS = __ballot_sync(0xffffffffu, kind == 1), mF = __ballot_sync(0xffffffffu, kind == 2);
@@ -626,16 +671,34 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
             const uint32_t r = offS + __popc(mS & ltMask);
             s_uTile[r] = t; s_uCell[r] = c; s_uAx[r] = ax;
             const float4 *cp = reinterpret_cast<const float4 *>(lv.cuts + c * kCS);
-            *reinterpret_cast<float4 *>(&s_uCuts[r][0]) = __ldg(cp);
-            *reinterpret_cast<float4 *>(&s_uCuts[r][4]) = __ldg(cp + 1);
+            // per-pass mutable state is read past L1 (the persistent level kernel re-reads it every pass)
+            *reinterpret_cast<float4 *>(&s_uCuts[r][0]) = __ldcg(cp);
+            *reinterpret_cast<float4 *>(&s_uCuts[r][4]) = __ldcg(cp + 1);
+            if (MODE == kCountCompact) { s_uBr[r][0] = __ldcg(&lv.compL[c]); s_uBr[r][1] = __ldcg(&lv.compR[c]); }
+            if (MODE == kCountCand) {
+                const uint4 *np = reinterpret_cast<const uint4 *>(lv.tile_ncand + (size_t)t * kWarps);
+                *reinterpret_cast<uint4 *>(&s_uN[r][0]) = __ldcg(np);
+                *reinterpret_cast<uint4 *>(&s_uN[r][4]) = __ldcg(np + 1);
+            }
         }
         if (kind == 2) { const uint32_t r = offF + __popc(mF & ltMask); s_fTile[r] = t; s_fCell[r] = c; }
         __syncthreads();
 
-        // ---- phase 2a: streamable tiles through a per-thread cp.async ring: every thread copies the four 16-byte
-        //      pieces it will count itself into its own shared-memory slots, kCountStages-1 tiles ahead, so the wait
-        //      is per thread (cp.async.wait_group) and needs no barrier. ----
-        if (nS) {
+        auto enter_cell = [&](uint32_t k) {   // block-uniform: unit k starts a new cell
+            const uint32_t cK = s_uCell[k];
+            if ((int)cK == cur) return;
+            flush();
+            cur = (int)cK;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) cv[j] = s_uCuts[k][j];
+            if constexpr (NC == 7) k7.set(cv);
+            if (MODE == kCountCompact) { brL = s_uBr[k][0]; brR = s_uBr[k][1]; }
+        };
+
+        if (nS && MODE != kCountCand) {
+            // ---- phase 2a: streamable tiles through a per-thread cp.async ring: every thread copies the four 16-byte
+            //      pieces it will count itself into its own shared-memory slots, kCountStages-1 tiles ahead, so the
+            //      wait is per thread (cp.async.wait_group) and needs no barrier. ----
             auto issue = [&](uint32_t k) {
                 const float4 *p = reinterpret_cast<const float4 *>(pick_col(s_uAx[k], x, y, z) + s_uTile[k] * (uint32_t)kCountTile) + tid;
                 float4 *dst = ring + (k % kCountStages) * (4 * kThreads) + tid;
@@ -651,24 +714,88 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
                 if (k + kCountStages - 1 < nS) issue(k + kCountStages - 1);
                 cp_async_commit();
                 cp_async_wait<kCountStages - 1>();     // tile k has landed in my slots
-                const uint32_t cK = s_uCell[k];
-                if ((int)cK != cur) {
-                    flush();
-                    cur = (int)cK;
-#pragma unroll
-                    for (int j = 0; j < NC; ++j) cv[j] = s_uCuts[k][j];
-                    if constexpr (NC == 7) k7.set(cv);
-                }
+                enter_cell(k);
                 const float4 *src = ring + (k % kCountStages) * (4 * kThreads) + tid;
                 const float4 q0 = src[0], q1 = src[kThreads], q2 = src[2 * kThreads], q3 = src[3 * kThreads];
-                if constexpr (NC == 7) { acc.add_f4(q0, k7); acc.add_f4(q1, k7); acc.add_f4(q2, k7); acc.add_f4(q3, k7); }
-                else { acc.add_f4(q0, cv); acc.add_f4(q1, cv); acc.add_f4(q2, cv); acc.add_f4(q3, cv); }
+                if constexpr (MODE == kCountCompact && NC == 7) {
+                    // bin + keep the particles inside [brL, brR); count the ones below brL
+                    const float v[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+                    unsigned keep = 0u;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float xv = canon0(v[j]);
+                        const int mLo = lt_mask(xv, brL), mHi = lt_mask(xv, brR);
+                        const unsigned in = (unsigned)(mHi & ~mLo);
+                        below += (unsigned)mLo & 1u;
+                        unsigned l2 = 0u, h2 = 0u;
+                        bin7(v[j], k7, l2, h2);
+                        acc.lo += l2 & in;
+                        acc.hi += h2 & in;
+                        keep |= (in & 1u) << j;
+                    }
+                    // warp-private compaction: exclusive scan of the per-thread keep counts, then each kept particle
+                    // goes to the warp's region of this tile in `cand` (order is irrelevant for counting)
+                    const unsigned mine = __popc(keep);
+                    unsigned incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += up;
+                    }
+                    const unsigned wtot = __shfl_sync(0xffffffffu, incl, 31);
+                    float *dstc = cand + (size_t)s_uTile[k] * kCountTile + warp * kWarpSlots + (incl - mine);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (keep & (1u << j)) dstc[__popc(keep & ((1u << j) - 1u))] = v[j];
+                    if (lane == 0) lv.tile_ncand[(size_t)s_uTile[k] * kWarps + warp] = wtot;
+                } else if constexpr (NC == 7) {
+                    acc.add_f4(q0, k7); acc.add_f4(q1, k7); acc.add_f4(q2, k7); acc.add_f4(q3, k7);
+                } else {
+                    acc.add_f4(q0, cv); acc.add_f4(q1, cv); acc.add_f4(q2, cv); acc.add_f4(q3, cv);
+                }
                 if ((k & 7u) == 7u) acc.fold();   // 16 particles per tile per thread: fold before 255
             }
             cp_async_wait<0>();
             acc.fold();
         }
-        // ---- phase 2b: fragmented tiles (cell boundaries, array tail) ----
+        if (nS && MODE == kCountCand) {
+            // ---- phase 2a': candidates only.  Warp w reads the slots it filled in the compaction pass; loads of up to
+            //      eight tiles are issued together so the pass pays one memory latency per eight tiles. ----
+            if constexpr (NC == 7) {
+                for (uint32_t k0 = 0; k0 < nS; k0 += 8u) {
+                    float v0[8], v1[8];
+                    unsigned n[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        n[u] = (k0 + u < nS) ? s_uN[k0 + u][warp] : 0u;
+                        const float *src = cand + (size_t)((k0 + u < nS) ? s_uTile[k0 + u] : 0u) * kCountTile + warp * kWarpSlots;
+                        v0[u] = ((unsigned)lane < n[u]) ? __ldcg(src + lane) : 0.f;
+                        v1[u] = ((unsigned)lane + 32u < n[u]) ? __ldcg(src + lane + 32) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (k0 + u >= nS) break;               // block-uniform
+                        enter_cell(k0 + u);
+                        unsigned l2 = 0u, h2 = 0u;
+                        bin7(v0[u], k7, l2, h2);
+                        if ((unsigned)lane < n[u]) { acc.lo += l2; acc.hi += h2; }
+                        l2 = h2 = 0u;
+                        bin7(v1[u], k7, l2, h2);
+                        if ((unsigned)lane + 32u < n[u]) { acc.lo += l2; acc.hi += h2; }
+                        if (n[u] > 64u) {                      // warp-uniform: rare long tail (clustered data)
+                            const float *src = cand + (size_t)s_uTile[k0 + u] * kCountTile + warp * kWarpSlots;
+                            for (unsigned i = 64u + lane; i < n[u]; i += 32u) {
+                                l2 = h2 = 0u;
+                                bin7(__ldcg(src + i), k7, l2, h2);
+                                acc.lo += l2; acc.hi += h2;
+                            }
+                        }
+                        acc.fold();                            // <= 2 + 14 particles per thread per tile
+                    }
+                }
+            }
+        }
+        // ---- phase 2b: fragmented tiles (cell boundaries, array tail) are always counted in full ----
         if (nF) {
             flush();
             cur = -1;
@@ -681,7 +808,138 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
         __syncthreads();
     }
     flush();
+}
+
+
+template <int NC, int MODE>
+__global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__restrict__ x, const float *__restrict__ y,
+                                                              const float *__restrict__ z, float *__restrict__ cand,
+                                                              LevelState lv, const uint32_t *__restrict__ tile_first,
+                                                              uint32_t nCells, uint32_t nLocal, uint32_t nTiles,
+                                                              const uint32_t *__restrict__ gate, FuseCtl fc) {
+    if (gate && *gate == 0u) {   // speculative pass after convergence: nothing to count
+        if (fc.enabled && blockIdx.x == 0 && threadIdx.x == 0) { fc.ctl.n_active[fc.pass + 1] = 0u; fc.ctl.h_status[fc.pass] = 1u; }
+        return;
+    }
+    extern __shared__ __align__(16) unsigned char count_smem[];       // kCountStages x 16 KB ring
+    __shared__ CountSmem<NC> sm;
+    stream_count_pass<NC, MODE>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, reinterpret_cast<float4 *>(count_smem), sm);
     fused_update_dispatch(lv, nCells, fc);
+}
+
+// ---- N2: host-free level loop.  ONE cooperative launch runs the whole bisection of a level (orbit.cpp:146-232):
+// every pass = streaming count (full / compact / candidates) -> grid barrier -> bisection update spread over the
+// blocks -> grid barrier; the loop ends on the device when no cell is active (or after 32 iterations).  Cells that hit
+// the iteration cap get their extra count at the final cut in the same launch.  No kernel launch, no host polling and
+// no speculative pass per bisection pass.  Single rank, levels of up to kPersistMaxCells cells in the streaming regime.
+constexpr uint32_t kPersistMaxCells = 8192;
+struct LevelCtl {
+    uint32_t *n_active;                     // [maxPasses + 2] cells active after pass p at [p + 1]; zeroed per level
+    unsigned long long *active_particles;   // [2] statistics (see PassCtl)
+    int32_t *level_iters;
+    int32_t *passes_out;                    // passes executed in this level
+    uint32_t *n_unfound_out;                // cells that hit the iteration cap
+    int compaction;                         // 1: full, compact, then candidate passes
+};
+
+template <int M>
+__global__ void __launch_bounds__(kThreads, 4) k_level_persistent(const float *__restrict__ x, const float *__restrict__ y,
+                                                                  const float *__restrict__ z, float *__restrict__ cand,
+                                                                  LevelState lv, const uint32_t *__restrict__ tile_first,
+                                                                  uint32_t nCells, uint32_t nLocal, uint32_t nTiles,
+                                                                  LevelCtl lc) {
+    constexpr int NC = (1 << M) - 1;
+    constexpr int maxPasses = (kMaxIter + M - 1) / M;
+    extern __shared__ __align__(16) unsigned char count_smem[];
+    __shared__ CountSmem<NC> sm;
+    __shared__ uint32_t s_n;
+    __shared__ unsigned long long s_p, s_q;
+    __shared__ int s_it;
+    float4 *ring = reinterpret_cast<float4 *>(count_smem);
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+
+    int pass = 0;
+    for (; pass < maxPasses; ++pass) {
+        const int mode = !lc.compaction ? kCountFull : (pass == 0 ? kCountFull : (pass == 1 ? kCountCompact : kCountCand));
+        const int baseMode = !lc.compaction ? 0 : (pass == 0 ? 1 : 2);
+        if constexpr (NC == 7) {
+            if (mode == kCountCompact) stream_count_pass<NC, kCountCompact>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm);
+            else if (mode == kCountCand) stream_count_pass<NC, kCountCand>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm);
+            else stream_count_pass<NC, kCountFull>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm);
+        } else {
+            stream_count_pass<NC, kCountFull>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm);
+        }
+        __threadfence();
+        grid.sync();
+        // ---- bisection update, one thread per cell across the whole grid ----
+        if (threadIdx.x == 0) { s_n = 0; s_p = 0ull; s_q = 0ull; s_it = 0; }
+        __syncthreads();
+        uint32_t still = 0;
+        unsigned long long npS = 0, nipS = 0;
+        int itMax = 0;
+        for (uint32_t c = gtid; c < nCells; c += gsize) {
+            if (!__ldcg(&lv.active[c])) continue;
+            const uint4 g0 = __ldcg(reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS)), g1 = __ldcg(reinterpret_cast<const uint4 *>(lv.cnt_l + c * kCS + 4));
+            unsigned long long np = 0, nip = 0;
+            int it = 0;
+            still += update_cell<M>(lv, c, g0, g1, np, nip, it, baseMode);
+            npS += np; nipS += nip; itMax = max(itMax, it);
+        }
+        still = __reduce_add_sync(0xffffffffu, still);
+        itMax = __reduce_max_sync(0xffffffffu, itMax);
+        for (int o = 16; o; o >>= 1) {
+            npS += __shfl_xor_sync(0xffffffffu, npS, o);
+            nipS += __shfl_xor_sync(0xffffffffu, nipS, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (still) atomicAdd(&s_n, still);
+            if (npS) atomicAdd(&s_p, npS);
+            if (nipS) atomicAdd(&s_q, nipS);
+            if (itMax) atomicMax(&s_it, itMax);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (s_n) atomicAdd(&lc.n_active[pass + 1], s_n);
+            if (s_p) atomicAdd(lc.active_particles, s_p);
+            if (s_q) atomicAdd(lc.active_particles + 1, s_q);
+            if (s_it) atomicMax(lc.level_iters, s_it);
+        }
+        __threadfence();
+        grid.sync();
+        if (__ldcg(&lc.n_active[pass + 1]) == 0u) { ++pass; break; }
+    }
+    // ---- cells that hit the 32-iteration cap: one count at getCut() of their last margins (never counted before) ----
+    if (pass >= maxPasses) {
+        uint32_t need = 0;
+        for (uint32_t c = gtid; c < nCells; c += gsize) {
+            const uint32_t nf = lv.found[c] ? 0u : 1u;
+            lv.active[c] = nf;
+            if (nf) {
+                lv.cuts[c * kCS] = mid_cut(lv.mL[c], lv.mR[c]);
+                *reinterpret_cast<uint4 *>(lv.cnt_l + c * kCS) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4 *>(lv.cnt_l + c * kCS + 4) = make_uint4(0u, 0u, 0u, 0u);
+                ++need;
+            }
+        }
+        need = __reduce_add_sync(0xffffffffu, need);
+        if ((threadIdx.x & 31) == 0 && need) atomicAdd(lc.n_unfound_out, need);
+        __threadfence();
+        grid.sync();
+        if (__ldcg(lc.n_unfound_out) != 0u) {
+            stream_count_pass<NC, kCountFull>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm);
+            __threadfence();
+            grid.sync();
+            for (uint32_t c = gtid; c < nCells; c += gsize)
+                if (__ldcg(&lv.active[c])) {
+                    const uint32_t v = __ldcg(lv.cnt_l + c * kCS);
+                    lv.nleft_g[c] = v;
+                    lv.nleft_l[c] = v;
+                    lv.active[c] = 0u;
+                }
+        }
+    }
+    if (gtid == 0) *lc.passes_out = pass;
 }
 
 // ---- regime B: cells of at most a few tiles.  One group of G threads per cell (G = 256: block, G = 32: warp);
@@ -795,7 +1053,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_cells(const float *__rest
 //   float ratio = ceil(nLeafCells/2.0)/nLeafCells;  int difference = countLeft - count*ratio;
 // =====================================================================================
 template <int M>
-__global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCells, int pass, PassCtl ctl, PeerSet ps) {
+__global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCells, int pass, PassCtl ctl, PeerSet ps, int baseMode) {
     constexpr int NC = (1 << M) - 1;
     const uint32_t gate = ctl.n_active[pass];
     const uint32_t cT = blockIdx.x * blockDim.x + threadIdx.x;   // this thread's cell
@@ -844,7 +1102,7 @@ __global__ void __launch_bounds__(kThreads) k_update(LevelState lv, uint32_t nCe
                 g1.x += b1.x; g1.y += b1.y; g1.z += b1.z; g1.w += b1.w;
             }
         }
-        still = update_cell<M>(lv, c, g0, g1, npart, nipart, it);
+        still = update_cell<M>(lv, c, g0, g1, npart, nipart, it, baseMode);
     }
     // block -> grid reduction of (cells still active, particles streamed this pass, max iterations)
     uint32_t wn = __reduce_add_sync(0xffffffffu, still);
