@@ -143,6 +143,7 @@ def lib() -> C.CDLL:
         "orb_version": ([], C.c_int),
         "orb_set_trial_depth": ([P, C.c_int], C.c_int),
         "orb_set_profile": ([P, C.c_int], C.c_int),
+        "orb_set_tie_mode": ([P, C.c_int], C.c_int),
         "orb_comm_unique_id": ([P], C.c_int),
         "orb_comm_init": ([P, P, C.c_int, C.c_int], C.c_int),
         "orb_comm_attach": ([P, P, C.c_int, C.c_int], C.c_int),
@@ -248,6 +249,10 @@ class Orb:
     # ---- tuning
     def set_trial_depth(self, m: int):
         _check(lib().orb_set_trial_depth(self._h, m), "orb_set_trial_depth")
+
+    def set_tie_mode(self, mode: str):
+        """'canonical' (stable x<cut, default) or 'hoare' (reference-exact ties and particle order)."""
+        _check(lib().orb_set_tie_mode(self._h, {"canonical": 0, "hoare": 1}[mode]), "orb_set_tie_mode")
 
     def set_profile(self, on: bool):
         _check(lib().orb_set_profile(self._h, int(on)), "orb_set_profile")

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #if defined(__x86_64__)
@@ -119,6 +120,9 @@ struct orb_ctx {
     int trialDepth = 3;
     int runAhead = 1;
     bool fuseUpdate = true;
+    int tieMode = 0;               // 0 canonical (stable x<cut), 1 Hoare-exact (partition.cpp:30-60)
+    int occHoare = 1;
+    uint32_t *d_blk_le = nullptr, *d_nGE = nullptr, *d_nLE = nullptr;
     bool compaction = true;
     bool persist = true;           // host-free level loop (k_level_persistent) where it applies
     int occPersist[4] = {0, 0, 0, 0}; // resident blocks per SM of k_level_persistent<M>
@@ -465,6 +469,54 @@ int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket) {
     return ORB_OK;
 }
 
+// Hoare-exact partition of every cell of the level, in place (no ping-pong flip): rank scan -> pair swaps -> finish.
+// Leaves the local left counts in lv.nleft_l and their sum over ranks in lv.nleft_g.
+int launch_partition_hoare(orb_ctx *c, uint32_t nCells) {
+    using namespace orb;
+    const uint32_t nTiles = ceil_div(c->nLocal, kPartTile);
+    const uint32_t cb = ceil_div(nCells, 256);
+    k_final_cut<<<cb, 256, 0, c->stream>>>(c->lv, nCells, c->d_final_cut);
+    c->nOtherLaunch++;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profile) {
+        if (c->evPartUsed == c->evPart.size()) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            c->evPart.emplace_back(a, b);
+        }
+        e0 = c->evPart[c->evPartUsed].first;
+        e1 = c->evPart[c->evPartUsed].second;
+        c->evPartUsed++;
+        CK(cudaEventRecord(e0, c->stream));
+    }
+    if (nTiles) {
+        float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
+        const float *cx = x, *cy = y, *cz = z;
+        HoareLists hl;
+        hl.posI = reinterpret_cast<uint32_t *>(c->y[c->cur ^ 1]);   // the idle ping-pong columns hold the stopper lists
+        hl.posJ = reinterpret_cast<uint32_t *>(c->z[c->cur ^ 1]);
+        hl.nGE = c->d_nGE;
+        hl.nLE = c->d_nLE;
+        const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(c->occHoare, 4));
+        uint32_t nLocal32 = (uint32_t)c->nLocal, nT = nTiles, nC = nCells;
+        void *args[] = {(void *)&cx, (void *)&cy, (void *)&cz, (void *)&c->lv, (void *)&c->d_final_cut, (void *)&c->d_tile_first,
+                        (void *)&nC, (void *)&nLocal32, (void *)&nT, (void *)&hl, (void *)&c->d_blk_left, (void *)&c->d_blk_le,
+                        (void *)&c->d_blk_restart};
+        CK(cudaLaunchCooperativeKernel((const void *)k_hoare_scan, dim3(grid), dim3(kThreads), args, 0, c->stream));
+        const uint32_t sgrid = std::min<uint32_t>(ceil_div(c->nLocal, kThreads), (uint32_t)c->nSM * 8u);
+        k_hoare_swap<<<sgrid, kThreads, 0, c->stream>>>(x, y, z, c->lv.bnd, c->d_tile_first, nCells, nLocal32, hl);
+        k_hoare_finish<<<cb, 256, 0, c->stream>>>(x, y, z, c->lv, nCells, hl, c->d_err);
+        c->nPartLaunch += 3;
+    }
+    if (c->profile) CK(cudaEventRecord(e1, c->stream));
+    if (c->nRanks > 1) NK(g_nccl.AllReduce(c->lv.nleft_l, c->lv.nleft_g, nCells, ncclUint32, ncclSum, c->comm, c->stream));
+    else k_copy_u32<<<cb, 256, 0, c->stream>>>(c->lv.nleft_l, c->lv.nleft_g, nCells);
+    c->nOtherLaunch++;
+    CK(cudaGetLastError());
+    return ORB_OK;
+}
+
 int reset_pass_ctl(orb_ctx *c) {
     CK(cudaMemsetAsync(c->d_nactive, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots, c->stream));
     CK(cudaMemsetAsync(c->d_done, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots, c->stream));
@@ -565,6 +617,9 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaMalloc(&c->d_tile_first, nMap * 4));
     CK(cudaMalloc(&c->d_blk_left, sizeof(uint32_t) * 64 * (size_t)c->nSM));
     CK(cudaMalloc(&c->d_blk_restart, sizeof(uint32_t) * 64 * (size_t)c->nSM));
+    CK(cudaMalloc(&c->d_blk_le, sizeof(uint32_t) * 64 * (size_t)c->nSM));
+    CK(cudaMalloc(&c->d_nGE, (size_t)std::max<uint32_t>(1u, n_leaf_cells) * 4));
+    CK(cudaMalloc(&c->d_nLE, (size_t)std::max<uint32_t>(1u, n_leaf_cells) * 4));
     CK(cudaMalloc(&c->d_tickets, sizeof(uint32_t) * kMaxLevels));
     CK(cudaMalloc(&c->d_nactive, sizeof(uint32_t) * kMaxLevels * kPassSlots));
     CK(cudaMalloc(&c->d_done, sizeof(uint32_t) * kMaxLevels * kPassSlots));
@@ -607,6 +662,10 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occPartStream, orb::k_partition_coop, orb::kThreads, sizeof(orb::PartSmem)));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occPartCells, orb::k_partition_cells, orb::kThreads, sizeof(orb::PartSmem)));
     if (c->occPartStream < 1 || c->occPartCells < 1) return fail(ORB_ERR_CUDA, "partition kernels do not fit on this device");
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occHoare, orb::k_hoare_scan, orb::kThreads, 0));
+    if (c->occHoare < 1) c->occHoare = 1;
+    const char *tm = getenv("ORB_TIES");
+    if (tm && std::string(tm) == "hoare") c->tieMode = 1;
     const char *p = getenv("ORB_PROFILE");
     c->profile = p && atoi(p) != 0;
     const char *td = getenv("ORB_TRIAL_DEPTH");
@@ -639,7 +698,7 @@ int orb_destroy(orb_ctx *c) {
     for (int r = 0; r < orb::kMaxPeers; ++r)
         if (c->peerIpc[r]) { cudaIpcCloseMemHandle(c->peerCnt[r]); cudaIpcCloseMemHandle(c->peerFlag[r]); }
     cudaFree(c->d_lvl_passes); cudaFree(c->d_lvl_unfound); cudaFree(c->d_cdone); cudaFree(c->d_peer_cnt); cudaFree(c->d_peer_flag);
-    cudaFree(c->d_final_cut); cudaFree(c->d_tile_first); cudaFree(c->d_blk_left); cudaFree(c->d_blk_restart); cudaFree(c->d_tickets);
+    cudaFree(c->d_final_cut); cudaFree(c->d_tile_first); cudaFree(c->d_blk_left); cudaFree(c->d_blk_restart); cudaFree(c->d_blk_le); cudaFree(c->d_nGE); cudaFree(c->d_nLE); cudaFree(c->d_tickets);
     cudaFree(c->d_nactive); cudaFree(c->d_done); cudaFree(c->d_misc); cudaFree(c->d_active_particles);
     cudaFree(c->d_level_iters); cudaFree(c->d_err); cudaFree(c->d_bb); cudaFree(c->d_bb6);
     cudaFreeHost((void *)c->h_status);
@@ -656,6 +715,13 @@ int orb_set_trial_depth(orb_ctx *c, int m) {
     if (m == 0) m = 3;
     if (m < 1 || m > 3) return fail(ORB_ERR_ARG, "trial depth must be 1..3");
     c->trialDepth = m;
+    return ORB_OK;
+}
+
+int orb_set_tie_mode(orb_ctx *c, int mode) {
+    if (!c) return fail(ORB_ERR_ARG, "null ctx");
+    if (mode != 0 && mode != 1) return fail(ORB_ERR_ARG, "tie mode must be 0 (canonical) or 1 (hoare)");
+    c->tieMode = mode;
     return ORB_OK;
 }
 
@@ -885,11 +951,18 @@ int orb_partition(orb_ctx *c, const orb_cell *cells, uint32_t n_cells) {
     rc = allreduce_counts(c, n_cells, 1);
     if (rc) return rc;
     orb::k_finalize_apply<<<ceil_div(n_cells, 256), 256, 0, c->stream>>>(c->lv, n_cells);
+    c->nOtherLaunch++;
+    if (c->tieMode == 1) {
+        rc = launch_partition_hoare(c, n_cells);
+        if (rc) return rc;
+    }
     orb::k_ranges_from_level<<<ceil_div(n_cells, 256), 256, 0, c->stream>>>(c->d_cells, n_cells, c->lv, c->d_range, c->d_final_cut);
-    c->nOtherLaunch += 2;
-    CK(cudaMemsetAsync(c->d_tickets, 0, 4, c->stream));
-    rc = launch_partition(c, n_cells, c->d_tickets);
-    if (rc) return rc;
+    c->nOtherLaunch++;
+    if (c->tieMode != 1) {
+        CK(cudaMemsetAsync(c->d_tickets, 0, 4, c->stream));
+        rc = launch_partition(c, n_cells, c->d_tickets);
+        if (rc) return rc;
+    }
     return check_device_err(c);
 }
 
@@ -1033,10 +1106,16 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         }
         passes.push_back(np);
         unfound.push_back(nu);
+        if (c->tieMode == 1) {   // reference-exact ties: partition first (it decides the child sizes), then split
+            rc = launch_partition_hoare(c, nCells);
+            if (rc) return rc;
+        }
         k_split<<<ceil_div(nCells, 256), 256, 0, c->stream>>>(c->d_heap, first, nCells, c->lv, c->d_range, c->d_total, c->d_final_cut);
         c->nOtherLaunch++;
-        rc = launch_partition(c, nCells, c->d_tickets + (l - 1));
-        if (rc) return rc;
+        if (c->tieMode != 1) {
+            rc = launch_partition(c, nCells, c->d_tickets + (l - 1));
+            if (rc) return rc;
+        }
         if (tight) {   // children boxes from their particles; needs the children's ranges as a level
             const uint32_t cf = (1u << l) - 1u, cn = 1u << l;
             if (cn <= c->maxLevelCells) {

@@ -1669,6 +1669,208 @@ __global__ void __launch_bounds__(kThreads, 3) k_partition_cells(const float *__
 }
 
 // =====================================================================================
+// Hoare-exact partition: reproduces partition.cpp:30-60 bit for bit, including WHICH particles
+// with coord == cut land on which side and the resulting particle ORDER (later tie decisions depend on it).
+//
+// The sequential two-pointer loop is equivalent to (checked against a verbatim loop, tests/test_hoare_model.py):
+//   S_i = positions with v >= cut, ascending ("i-stoppers"); S_j = positions with v <= cut, descending;
+//   swap k happens iff S_i[k] < S_j[k]; K = number of swaps; i_stop = min(S_i[K], S_j[K-1]);
+//   then rows i_stop and end-1 are exchanged (partition.cpp:52); left child = [begin, i_stop).
+// Kernels: k_hoare_scan ranks the stoppers of every cell (exclusive prefix counts inside the cell) and writes their
+// positions into two lists (stored in the idle ping-pong columns); k_hoare_swap exchanges the K pairs in place;
+// k_hoare_finish finds K and i_stop per cell, does the final exchange and records the local left count.
+// A cell without any particle >= cut makes the reference read (and swap) rows outside the cell; such degenerate
+// cells are reported (ORB_ERR_RANGE) instead of emulated.
+// =====================================================================================
+struct HoareLists {
+    uint32_t *posI;   // [n_local] cell c, rank k (from the left) of its v >= cut particles  -> position, at bnd[c] + k
+    uint32_t *posJ;   // [n_local] cell c, rank r (from the left) of its v <= cut particles  -> position, at bnd[c] + r
+    uint32_t *nGE;    // [nCells]
+    uint32_t *nLE;    // [nCells]
+};
+
+// ranks + list writes for up to 256 consecutive particles [p0, p0+cnt) of one cell (one per thread), block-uniform call
+__device__ __forceinline__ void hoare_row(const float *__restrict__ col, float cutv, uint32_t p0, uint32_t cnt, uint32_t listBase,
+                                          uint32_t &carryGE, uint32_t &carryLE, const HoareLists &hl, uint32_t *s_w) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    bool ge = false, le = false;
+    if ((uint32_t)tid < cnt) {
+        const float v = __ldg(col + p0 + tid);
+        ge = v >= cutv;
+        le = v <= cutv;
+    }
+    const unsigned mg = __ballot_sync(0xffffffffu, ge), ml = __ballot_sync(0xffffffffu, le);
+    if (lane == 0) { s_w[warp] = __popc(mg); s_w[kWarps + warp] = __popc(ml); }
+    __syncthreads();
+    uint32_t og = 0, ol = 0, tg = 0, tl = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        const uint32_t a = s_w[w], b = s_w[kWarps + w];
+        if (w < warp) { og += a; ol += b; }
+        tg += a; tl += b;
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    if (ge) hl.posI[listBase + carryGE + og + __popc(mg & lt)] = p0 + tid;
+    if (le) hl.posJ[listBase + carryLE + ol + __popc(ml & lt)] = p0 + tid;
+    carryGE += tg;
+    carryLE += tl;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads, 4) k_hoare_scan(const float *__restrict__ x, const float *__restrict__ y,
+                                                           const float *__restrict__ z, LevelState lv,
+                                                           const float *__restrict__ final_cut,
+                                                           const uint32_t *__restrict__ tile_first, uint32_t nCells,
+                                                           uint32_t nLocal, uint32_t nTiles, HoareLists hl,
+                                                           uint32_t *blkGE, uint32_t *blkLE, uint32_t *blkRestart) {
+    __shared__ uint32_t s_w[2 * kWarps];
+    __shared__ uint32_t s_c[2];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tilesPerBlock = (nTiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t tb0 = min(blockIdx.x * tilesPerBlock, nTiles), tb1 = min(tb0 + tilesPerBlock, nTiles);
+    const uint32_t chunkStart = tb0 * (uint32_t)kPartTile, chunkEnd = min(tb1 * (uint32_t)kPartTile, nLocal);
+
+    // ---- phase 1: stoppers of the trailing segment (the cell that continues into the next block) ----
+    {
+        uint32_t cg = 0, cl = 0, restart = 0;
+        if (tb0 < tb1) {
+            uint32_t c = tile_first[tb1 - 1];
+            while (lv.bnd[c + 1] < chunkEnd) ++c;
+            const uint32_t cb = lv.bnd[c];
+            restart = cb >= chunkStart ? 1u : 0u;
+            const float *col = pick_col(lv.axis[c], x, y, z);
+            const float cutv = final_cut[c];
+            for (uint32_t p = max(cb, chunkStart) + tid; p < chunkEnd; p += kThreads) {
+                const float v = __ldg(col + p);
+                cg += (v >= cutv);
+                cl += (v <= cutv);
+            }
+        }
+        cg = __reduce_add_sync(0xffffffffu, cg);
+        cl = __reduce_add_sync(0xffffffffu, cl);
+        if (lane == 0) { s_w[warp] = cg; s_w[kWarps + warp] = cl; }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t a = 0, b = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) { a += s_w[w]; b += s_w[kWarps + w]; }
+            blkGE[blockIdx.x] = a;
+            blkLE[blockIdx.x] = b;
+            blkRestart[blockIdx.x] = restart;
+        }
+        __syncthreads();
+    }
+    grid.sync();
+    if (tb0 >= tb1) return;
+
+    // ---- phase 2: carries of the first cell, then rank every particle of the chunk cell by cell ----
+    uint32_t c = tile_first[tb0];
+    uint32_t carryGE = 0, carryLE = 0;
+    if (lv.bnd[c] < chunkStart) {
+        if (warp == 0) {
+            uint32_t ag = 0, al = 0;
+            int pos = (int)blockIdx.x - 1;
+            for (;;) {
+                const int idx = pos - lane;
+                const uint32_t vg = idx >= 0 ? blkGE[idx] : 0u, vl = idx >= 0 ? blkLE[idx] : 0u;
+                const uint32_t r = idx >= 0 ? blkRestart[idx] : 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, r != 0u);
+                const int fp = m ? (__ffs(m) - 1) : 32;
+                ag += __reduce_add_sync(0xffffffffu, lane <= fp ? vg : 0u);
+                al += __reduce_add_sync(0xffffffffu, lane <= fp ? vl : 0u);
+                if (fp < 32) break;
+                pos -= 32;
+            }
+            if (lane == 0) { s_c[0] = ag; s_c[1] = al; }
+        }
+        __syncthreads();
+        carryGE = s_c[0];
+        carryLE = s_c[1];
+    }
+    uint32_t p = chunkStart;
+    while (p < chunkEnd) {
+        const uint32_t cb = lv.bnd[c], ce = lv.bnd[c + 1];
+        const uint32_t segEnd = min(ce, chunkEnd);
+        if (segEnd > p) {
+            const float *col = pick_col(lv.axis[c], x, y, z);
+            const float cutv = final_cut[c];
+            for (uint32_t q = p; q < segEnd; q += kThreads)
+                hoare_row(col, cutv, q, min((uint32_t)kThreads, segEnd - q), cb, carryGE, carryLE, hl, s_w);
+            p = segEnd;
+        }
+        if (ce <= chunkEnd) {   // the cell ends inside this chunk: its totals are complete
+            if (tid == 0) { hl.nGE[c] = carryGE; hl.nLE[c] = carryLE; }
+            carryGE = carryLE = 0;
+            ++c;
+            if (c >= nCells) break;
+        }
+    }
+}
+
+// final cut of every cell of the level = getCut() of its last margins (cell.h:74-76)
+__global__ void k_final_cut(LevelState lv, uint32_t nCells, float *__restrict__ final_cut) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nCells) final_cut[c] = mid_cut(lv.mL[c], lv.mR[c]);
+}
+__global__ void k_copy_u32(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+// exchange the K swap pairs of every cell, in place (all three columns)
+__global__ void __launch_bounds__(kThreads) k_hoare_swap(float *__restrict__ x, float *__restrict__ y, float *__restrict__ z,
+                                                        const uint32_t *__restrict__ bnd, const uint32_t *__restrict__ tile_first,
+                                                        uint32_t nCells, uint32_t nLocal, HoareLists hl) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < nLocal; g += gridDim.x * blockDim.x) {
+        uint32_t c = tile_first[g / (uint32_t)kMapTile];
+        while (bnd[c + 1] <= g) ++c;
+        const uint32_t b = bnd[c], k = g - b;
+        const uint32_t nG = hl.nGE[c], nL = hl.nLE[c];
+        if (k >= min(nG, nL)) continue;
+        const uint32_t a = hl.posI[b + k], q = hl.posJ[b + nL - 1u - k];
+        if (a < q) {
+            float t;
+            t = x[a]; x[a] = x[q]; x[q] = t;
+            t = y[a]; y[a] = y[q]; y[q] = t;
+            t = z[a]; z[a] = z[q]; z[q] = t;
+        }
+    }
+}
+
+// per cell: number of swaps K (the swap condition is monotone in k), i_stop, the final exchange with row end-1,
+// local left count
+__global__ void k_hoare_finish(float *__restrict__ x, float *__restrict__ y, float *__restrict__ z, LevelState lv,
+                               uint32_t nCells, HoareLists hl, int *__restrict__ err) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    const uint32_t b = lv.bnd[c], e = lv.bnd[c + 1];
+    if (e <= b) { lv.nleft_l[c] = 0u; return; }
+    const uint32_t nG = hl.nGE[c], nL = hl.nLE[c];
+    if (nG == 0u) {   // the reference would scan past the end of the cell (partition.cpp:38): not emulated
+        atomicExch(err, ORB_ERR_RANGE);
+        lv.nleft_l[c] = e - b;
+        return;
+    }
+    uint32_t lo = 0, hi = min(nG, nL);   // K in [lo, hi]: first k with posI[k] >= posJ[nL-1-k]
+    while (lo < hi) {
+        const uint32_t m = (lo + hi) >> 1;
+        if (hl.posI[b + m] < hl.posJ[b + nL - 1u - m]) lo = m + 1; else hi = m;
+    }
+    const uint32_t K = lo;
+    uint32_t iStop = 0xffffffffu;
+    if (K < nG) iStop = hl.posI[b + K];
+    if (K > 0u) iStop = min(iStop, hl.posJ[b + nL - K]);
+    if (iStop < e - 1u) {   // partition.cpp:52: swap(particles, i, endInd - 1)
+        float t;
+        t = x[iStop]; x[iStop] = x[e - 1u]; x[e - 1u] = t;
+        t = y[iStop]; y[iStop] = y[e - 1u]; y[e - 1u] = t;
+        t = z[iStop]; z[iStop] = z[e - 1u]; z[e - 1u] = t;
+    }
+    lv.nleft_l[c] = iStop - b;
+}
+
+// =====================================================================================
 // Bounding boxes (north-star extension): per-cell min/max of x,y,z.
 // Floats are mapped to order-preserving uint32 so warp REDUX and global atomicMin/Max apply.
 // =====================================================================================

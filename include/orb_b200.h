@@ -77,6 +77,13 @@ int orb_version(void);
 
 /* tuning: trial-cut depth m per count pass (1..3: 2^m-1 cuts per cell per HBM pass); 0 = default */
 int orb_set_trial_depth(orb_ctx *ctx, int m);
+/* tie handling of the partition: 0 = canonical (stable, x < cut goes left; default),
+ * 1 = Hoare-exact: reproduces partition.cpp:30-60 including which particles with coord == cut go to which side and
+ * the particle order (in place; also selected by env ORB_TIES=hoare).  Cells without any particle >= cut make the
+ * reference touch rows outside the cell; they are reported as ORB_ERR_RANGE instead of emulated. */
+#define ORB_TIES_CANONICAL 0
+#define ORB_TIES_HOARE 1
+int orb_set_tie_mode(orb_ctx *ctx, int mode);
 /* profiling: when on, every count / partition kernel launch is bracketed by CUDA events on the context's
  * stream and orb_build_stats.ms_count / ms_partition are filled (also enabled by env ORB_PROFILE=1) */
 int orb_set_profile(orb_ctx *ctx, int on);
