@@ -231,6 +231,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     # ---- device-resident timing
     for _ in range(W):
         restore()
@@ -300,6 +306,23 @@ def main():
     dom = "k_count" if cnt_ms >= part_ms else "k_partition"
     roofline = dict(kernels[dom], kernel=dom, peak_source=peak_src)
 
+    # ---- the same build in the reference-exact tie mode (Hoare emulation), for information ----
+    hoare = None
+    try:
+        ctx.set_tie_mode("hoare")
+        hms = []
+        for i in range(4):
+            restore()
+            _, sth = ctx.build(full_levels=args.full_levels, want_heap=False)
+            if i:
+                hms.append(sth.ms_total)
+        hoare = {"build_ms": reduce_max(sum(hms) / len(hms)),
+                 "note": "ORB_TIES_HOARE: cells, ranges and particle order equal to the reference CPU path even with tie particles"}
+    except Exception as exc:   # informational leg must not break the bench line
+        hoare = {"build_ms": None, "note": f"failed: {exc}"}
+    finally:
+        ctx.set_tie_mode("canonical")
+
     # ---- end to end through the public API with host buffers (H2D + build + D2H inside the timed region)
     e2e_times = []
     h2d = 12 * n_local
@@ -358,6 +381,8 @@ def main():
             "roofline": roofline,
             "kernels": kernels,
             "cpu_baseline": cpu,
+            "tie_mode": "canonical (stable x<cut; equals the reference whenever no particle sits exactly on a cut)",
+            "reference_exact_mode": hoare,
         }
         print(json.dumps(line))
     ctx.close()

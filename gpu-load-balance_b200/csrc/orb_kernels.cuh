@@ -1689,31 +1689,47 @@ struct HoareLists {
     uint32_t *nLE;    // [nCells]
 };
 
-// ranks + list writes for up to 256 consecutive particles [p0, p0+cnt) of one cell (one per thread), block-uniform call
-__device__ __forceinline__ void hoare_row(const float *__restrict__ col, float cutv, uint32_t p0, uint32_t cnt, uint32_t listBase,
-                                          uint32_t &carryGE, uint32_t &carryLE, const HoareLists &hl, uint32_t *s_w) {
+// ranks + list writes for up to 2048 consecutive particles [p0, p0+cnt) of one cell: eight rows of 256 (row k, thread
+// t <-> particle p0 + 256 k + t), one barrier pair for all rows.  Block-uniform call.
+constexpr int kHoareRows = 8;
+__device__ __forceinline__ void hoare_rows(const float *__restrict__ col, float cutv, uint32_t p0, uint32_t cnt, uint32_t listBase,
+                                           uint32_t &carryGE, uint32_t &carryLE, const HoareLists &hl, uint32_t *s_w) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    bool ge = false, le = false;
-    if ((uint32_t)tid < cnt) {
-        const float v = __ldg(col + p0 + tid);
-        ge = v >= cutv;
-        le = v <= cutv;
-    }
-    const unsigned mg = __ballot_sync(0xffffffffu, ge), ml = __ballot_sync(0xffffffffu, le);
-    if (lane == 0) { s_w[warp] = __popc(mg); s_w[kWarps + warp] = __popc(ml); }
-    __syncthreads();
-    uint32_t og = 0, ol = 0, tg = 0, tl = 0;
+    bool ge[kHoareRows], le[kHoareRows];
+    unsigned mg[kHoareRows], ml[kHoareRows];
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-        const uint32_t a = s_w[w], b = s_w[kWarps + w];
-        if (w < warp) { og += a; ol += b; }
-        tg += a; tl += b;
+    for (int k = 0; k < kHoareRows; ++k) {
+        const uint32_t i = (uint32_t)k * kThreads + tid;
+        ge[k] = le[k] = false;
+        if (i < cnt) {
+            const float v = __ldg(col + p0 + i);
+            ge[k] = v >= cutv;
+            le[k] = v <= cutv;
+        }
+        mg[k] = __ballot_sync(0xffffffffu, ge[k]);
+        ml[k] = __ballot_sync(0xffffffffu, le[k]);
+        if (lane == 0) { s_w[(k * kWarps + warp) * 2] = __popc(mg[k]); s_w[(k * kWarps + warp) * 2 + 1] = __popc(ml[k]); }
     }
+    __syncthreads();
     const unsigned lt = (1u << lane) - 1u;
-    if (ge) hl.posI[listBase + carryGE + og + __popc(mg & lt)] = p0 + tid;
-    if (le) hl.posJ[listBase + carryLE + ol + __popc(ml & lt)] = p0 + tid;
-    carryGE += tg;
-    carryLE += tl;
+    uint32_t baseG = carryGE, baseL = carryLE;
+#pragma unroll
+    for (int k = 0; k < kHoareRows; ++k) {
+        uint32_t preG = 0, preL = 0, totG = 0, totL = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t a = s_w[(k * kWarps + w) * 2], b = s_w[(k * kWarps + w) * 2 + 1];
+            if (w < warp) { preG += a; preL += b; }
+            totG += a; totL += b;
+        }
+        const uint32_t pos = p0 + (uint32_t)k * kThreads + tid;
+        if (ge[k]) hl.posI[listBase + baseG + preG + __popc(mg[k] & lt)] = pos;
+        if (le[k]) hl.posJ[listBase + baseL + preL + __popc(ml[k] & lt)] = pos;
+        baseG += totG;
+        baseL += totL;
+    }
+    carryGE = baseG;
+    carryLE = baseL;
     __syncthreads();
 }
 
@@ -1723,7 +1739,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_hoare_scan(const float *__restr
                                                            const uint32_t *__restrict__ tile_first, uint32_t nCells,
                                                            uint32_t nLocal, uint32_t nTiles, HoareLists hl,
                                                            uint32_t *blkGE, uint32_t *blkLE, uint32_t *blkRestart) {
-    __shared__ uint32_t s_w[2 * kWarps];
+    __shared__ uint32_t s_w[2 * kWarps * kHoareRows];
     __shared__ uint32_t s_c[2];
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1795,8 +1811,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_hoare_scan(const float *__restr
         if (segEnd > p) {
             const float *col = pick_col(lv.axis[c], x, y, z);
             const float cutv = final_cut[c];
-            for (uint32_t q = p; q < segEnd; q += kThreads)
-                hoare_row(col, cutv, q, min((uint32_t)kThreads, segEnd - q), cb, carryGE, carryLE, hl, s_w);
+            for (uint32_t q = p; q < segEnd; q += kThreads * kHoareRows)
+                hoare_rows(col, cutv, q, min((uint32_t)(kThreads * kHoareRows), segEnd - q), cb, carryGE, carryLE, hl, s_w);
             p = segEnd;
         }
         if (ce <= chunkEnd) {   // the cell ends inside this chunk: its totals are complete

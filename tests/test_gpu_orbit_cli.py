@@ -81,3 +81,36 @@ def test_orbit_two_ranks_match_sharded_oracle(oracle, tmp_path, o):
         _, rng, gx, gy, gz = read_dump(tmp_path, oracle, r)
         assert np.array_equal(rng, ref["ranges"][r])
         assert np.array_equal(gx.view(np.uint32), ref["x"][r * per:(r + 1) * per].view(np.uint32))
+
+
+def test_orbit_reference_exact_ties_env(oracle, tmp_path):
+    """ORB_TIES=hoare: the C++ host leaves exactly the reference CPU path's result (verbatim-Hoare oracle)."""
+    x, y = 17, 6
+    run_orbit(x, y, 0, tmp_path, env_extra={"ORB_TIES": "hoare"})
+    heap, rng, gx, gy, gz = read_dump(tmp_path, oracle)
+    xs, ys, zs = oracle.generate_uniform(1 << x)
+    ref = oracle.build(xs, ys, zs, 1 << y, ties=oracle.TIES_HOARE)
+    assert heap.tobytes() == ref["heap"].tobytes()
+    assert np.array_equal(rng, ref["ranges"][0])
+    assert np.array_equal(gx.view(np.uint32), ref["x"].view(np.uint32))
+    assert np.array_equal(gz.view(np.uint32), ref["z"].view(np.uint32))
+
+
+@pytest.mark.parametrize("o", [0, 2])
+def test_orbit_two_ranks_reference_exact(oracle, tmp_path, o):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    x, y, R = 17, 7, 2
+    run_orbit(x, y, o, tmp_path, threads=R, env_extra={"ORB_TIES": "hoare"})
+    xs, ys, zs = oracle.generate_uniform(1 << x)
+    ref = oracle.build(xs, ys, zs, 1 << y, ties=oracle.TIES_HOARE, n_shards=R)
+    heap = np.fromfile(tmp_path / "dump.heap", dtype=oracle.CELL_DTYPE)
+    heap["pad_"] = 0
+    assert heap.tobytes() == ref["heap"].tobytes()
+    per = (1 << x) // R
+    for r in range(R):
+        _, rng, gx, gy, gz = read_dump(tmp_path, oracle, r)
+        assert np.array_equal(rng, ref["ranges"][r])
+        assert np.array_equal(gx.view(np.uint32), ref["x"][r * per:(r + 1) * per].view(np.uint32))
