@@ -123,10 +123,12 @@ struct orb_ctx {
     int tieMode = 0;               // 0 canonical (stable x<cut), 1 Hoare-exact (partition.cpp:30-60)
     int occHoare = 1;
     uint32_t *d_blk_le = nullptr, *d_nGE = nullptr, *d_nLE = nullptr;
+    int streamMinTiles = 16;       // average cell size (in 16 KB tiles) from which the tile-streaming count kernel is used
     bool compaction = true;
     bool persist = true;           // host-free level loop (k_level_persistent) where it applies
     int occPersist[4] = {0, 0, 0, 0}; // resident blocks per SM of k_level_persistent<M>
     int32_t *d_lvl_passes = nullptr;  // [kMaxLevels]
+    unsigned long long *d_dbg = nullptr; // ORB_DEBUG_TIMES: [kMaxLevels][64] globaltimer stamps
     uint32_t *d_lvl_unfound = nullptr; // [kMaxLevels]
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evCount, evPart;
@@ -199,7 +201,7 @@ int level_prepare(orb_ctx *c, const orb_cell *d_cells, uint32_t nCells, int nc, 
 }
 
 // cells of at least 16 tiles on average: the tile-streaming kernel (and the byte-reducing search) apply
-inline bool count_streams(const orb_ctx *c, uint32_t nCells) { return c->nLocal / nCells >= 16ull * orb::kCountTile; }
+inline bool count_streams(const orb_ctx *c, uint32_t nCells) { return c->nLocal / nCells >= (uint64_t)c->streamMinTiles * orb::kCountTile; }
 
 // Count pass over all active cells of the level.  Kernel choice by average local cell size:
 //   >= 16 tiles   : k_count_stream (persistent, tile streaming, one atomic per block per (cell,cut))
@@ -378,6 +380,8 @@ int launch_level_persistent(orb_ctx *c, uint32_t nCells, int M, int slotBase, in
     lc.passes_out = c->d_lvl_passes + levelIdx;
     lc.n_unfound_out = c->d_lvl_unfound + levelIdx;
     lc.compaction = (c->compaction && M == 3) ? 1 : 0;
+    lc.barrier = c->d_cdone + slotBase;   // per-level counter, zeroed with the pass-control arrays
+    lc.dbg = c->d_dbg ? c->d_dbg + (size_t)levelIdx * 64 : nullptr;
     void *args[] = {(void *)&x, (void *)&y, (void *)&z, (void *)&cand, (void *)&c->lv, (void *)&c->d_tile_first,
                     (void *)&nC, (void *)&nL, (void *)&nT, (void *)&lc};
     const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
@@ -670,6 +674,12 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     c->profile = p && atoi(p) != 0;
     const char *td = getenv("ORB_TRIAL_DEPTH");
     if (td && atoi(td) >= 1 && atoi(td) <= 3) c->trialDepth = atoi(td);
+    if (getenv("ORB_DEBUG_TIMES")) {
+        CK(cudaMalloc(&c->d_dbg, sizeof(unsigned long long) * 64 * kMaxLevels));
+        CK(cudaMemset(c->d_dbg, 0, sizeof(unsigned long long) * 64 * kMaxLevels));
+    }
+    const char *smt = getenv("ORB_STREAM_MIN_TILES");
+    if (smt && atoi(smt) >= 1) c->streamMinTiles = atoi(smt);
     const char *pe = getenv("ORB_PERSIST");
     if (pe) c->persist = atoi(pe) != 0;
     const char *cp = getenv("ORB_COMPACT");
@@ -1140,6 +1150,19 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
     CK(cudaMemcpyAsync(ap, c->d_active_particles, 16, cudaMemcpyDeviceToHost, c->stream));
     rc = check_device_err(c);
     if (rc) return rc;
+    if (c->d_dbg) {
+        std::vector<unsigned long long> t(64 * kMaxLevels);
+        cudaMemcpy(t.data(), c->d_dbg, t.size() * 8, cudaMemcpyDeviceToHost);
+        for (int l = 0; l < nDone; ++l) {
+            fprintf(stderr, "dbg level %d:", l + 1);
+            for (int p = 0; p < 11 && t[l * 64 + p * 5]; ++p) {
+                const unsigned long long *q = &t[l * 64 + p * 5];
+                fprintf(stderr, " [count %.1f bar %.1f upd %.1f bar %.1f]", (q[1] - q[0]) * 1e-3, (q[2] - q[1]) * 1e-3, (q[3] - q[2]) * 1e-3, (q[4] - q[3]) * 1e-3);
+            }
+            fprintf(stderr, "\n");
+        }
+        cudaMemset(c->d_dbg, 0, sizeof(unsigned long long) * 64 * kMaxLevels);
+    }
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->n_levels = nDone;

@@ -466,84 +466,124 @@ __device__ __forceinline__ unsigned cum_from_bins(const unsigned *bins, int k) {
     return v;
 }
 
-// Fragmented tile [t0,t1): several cells.  Per-warp 128-particle segments, shared per-cell accumulators,
-// one global atomic per (cell, cut) per tile.  Block-uniform call (contains barriers).
+// Fragmented tile [t0,t1): several cells.  The tile's cell table (bounds, axis, active flag, trial cuts of up to
+// kCountCellsSmem cells) is staged in shared memory once - one memory latency for the whole tile instead of a chain of
+// dependent loads per warp segment - then every warp bins its 128-particle segments against the table and adds into
+// shared per-cell accumulators; one global atomic per (cell, cut) per tile.  Block-uniform call (contains barriers).
+// Tiles with more cells than the table are processed in several rounds.
+template <int NC>
+struct FragSmem {
+    uint32_t beg[kCountCellsSmem + 1];
+    uint32_t act[kCountCellsSmem];
+    int ax[kCountCellsSmem];
+    float cuts[kCountCellsSmem][kCS];
+};
+
 template <int NC>
 __device__ __forceinline__ void count_fragmented_tile(const float *__restrict__ x, const float *__restrict__ y,
                                                       const float *__restrict__ z, const LevelState &lv, uint32_t nCells,
                                                       uint32_t cT, uint32_t t0, uint32_t t1, uint32_t *s_cell) {
+    __shared__ FragSmem<NC> fs;
+    __shared__ uint32_t s_nc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < kCountCellsSmem * NC; i += kThreads) s_cell[i] = 0u;
-    __syncthreads();
-    for (uint32_t seg = t0 + warp * 128u; seg < t1; seg += kWarps * 128u) {
-        const uint32_t segEnd = min(seg + 128u, t1);
-        uint32_t cc = cT;
-        while (lv.bnd[cc + 1] <= seg) ++cc;
-        const uint32_t e0 = seg + lane * 4u;
-        while (cc < nCells) {
-            const uint32_t b = lv.bnd[cc], e = lv.bnd[cc + 1];
-            if (b >= segEnd) break;
-            const uint32_t lo_e = max(b, seg), hi_e = min(e, segEnd);
-            if (hi_e > lo_e && __ldcg(&lv.active[cc])) {
-                const float *cl = pick_col(lv.axis[cc], x, y, z);
-                float v[4];
-                bool in[4];
-                if (e0 >= lo_e && e0 + 4u <= hi_e) {
-                    const float4 q = __ldg(reinterpret_cast<const float4 *>(cl + e0));
-                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-                    in[0] = in[1] = in[2] = in[3] = true;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t ee = e0 + j;
-                        in[j] = (ee >= lo_e && ee < hi_e);
-                        v[j] = in[j] ? __ldg(cl + ee) : 0.f;
-                    }
-                }
-                float ccv[NC];
-#pragma unroll
-                for (int k = 0; k < NC; ++k) ccv[k] = __ldcg(&lv.cuts[cc * kCS + k]);
-                unsigned n[NC];
-#pragma unroll
-                for (int k = 0; k < NC; ++k) n[k] = 0u;
-                if constexpr (NC == 7) {
-                    // <=128 particles per warp segment: packed 8-bit bins survive the warp sum
-                    unsigned plo = 0u, phi = 0u;
-                    count_vals<NC>(v, in, ccv, n, plo, phi);
-                    plo = __reduce_add_sync(0xffffffffu, plo);
-                    phi = __reduce_add_sync(0xffffffffu, phi);
-                    unsigned run = 0u, cum[8];
-#pragma unroll
-                    for (int sIdx = 0; sIdx < 4; ++sIdx) { run += (plo >> (8 * sIdx)) & 0xffu; cum[sIdx] = run; }
-#pragma unroll
-                    for (int sIdx = 0; sIdx < 4; ++sIdx) { run += (phi >> (8 * sIdx)) & 0xffu; cum[4 + sIdx] = run; }
-                    n[0] = cum[3]; n[1] = cum[1]; n[2] = cum[5]; n[3] = cum[0]; n[4] = cum[2]; n[5] = cum[4]; n[6] = cum[6];
-                } else {
-                    unsigned dlo = 0u, dhi = 0u;
-                    count_vals<NC>(v, in, ccv, n, dlo, dhi);
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) n[k] = __reduce_add_sync(0xffffffffu, n[k]);
-                }
-                if (lane == 0) {
-                    const uint32_t j = cc - cT;
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) {
-                        if (!n[k]) continue;
-                        if (j < (uint32_t)kCountCellsSmem) atomicAdd(&s_cell[j * NC + k], n[k]);
-                        else atomicAdd(&lv.cnt_l[cc * kCS + k], n[k]);
-                    }
-                }
+    uint32_t cFirst = cT, r0 = t0;               // round: cells cFirst.., particles from r0
+    while (r0 < t1) {
+        // ---- stage the table: thread i owns cell cFirst + i ----
+        {
+            const uint32_t cc = cFirst + tid;
+            bool valid = false;
+            uint32_t b = 0;
+            if (tid <= kCountCellsSmem && cc <= nCells) {
+                b = lv.bnd[min(cc, nCells)];
+                valid = (tid == 0) || (b < t1);
             }
-            if (e > segEnd) break;
-            ++cc;
+            if (tid <= kCountCellsSmem) fs.beg[tid] = valid ? b : 0xffffffffu;   // entry n = end of cell n-1; beyond the tile: +inf
+            if (tid < kCountCellsSmem && valid && cc < nCells) {
+                fs.act[tid] = __ldcg(&lv.active[cc]);
+                fs.ax[tid] = lv.axis[cc];
+                const float4 *cp = reinterpret_cast<const float4 *>(lv.cuts + cc * kCS);
+                *reinterpret_cast<float4 *>(&fs.cuts[tid][0]) = __ldcg(cp);
+                *reinterpret_cast<float4 *>(&fs.cuts[tid][4]) = __ldcg(cp + 1);
+            }
+            const int nv = __syncthreads_count(tid < kCountCellsSmem && valid && cc < nCells);
+            if (tid == 0) s_nc = (uint32_t)nv;
         }
+        for (int i = tid; i < kCountCellsSmem * NC; i += kThreads) s_cell[i] = 0u;
+        __syncthreads();
+        const uint32_t nc = s_nc;                                  // cells in the table (>= 1)
+        // the table covers particles up to the begin of the first cell that did not fit (or the tile end)
+        uint32_t r1 = t1;
+        if (nc == (uint32_t)kCountCellsSmem) r1 = min(t1, fs.beg[kCountCellsSmem] == 0xffffffffu ? t1 : fs.beg[kCountCellsSmem]);
+        // segments stay 128-aligned relative to the tile (vector loads need 16-byte alignment); particles before r0
+        // belong to cells of an earlier round and are masked out by the cell bounds
+        const uint32_t segBase = t0 + ((r0 - t0) / 128u) * 128u;
+        for (uint32_t seg = segBase + warp * 128u; seg < r1; seg += kWarps * 128u) {
+            const uint32_t segEnd = min(seg + 128u, r1);
+            uint32_t j = 0;
+            while (j + 1 < nc && fs.beg[j + 1] <= seg) ++j;
+            const uint32_t e0 = seg + lane * 4u;
+            for (; j < nc; ++j) {
+                const uint32_t b = fs.beg[j], e = min(fs.beg[j + 1], r1);
+                if (b >= segEnd) break;
+                const uint32_t lo_e = max(b, seg), hi_e = min(e, segEnd);
+                if (hi_e > lo_e && fs.act[j]) {
+                    const float *cl = pick_col(fs.ax[j], x, y, z);
+                    float v[4];
+                    bool in[4];
+                    if (e0 >= lo_e && e0 + 4u <= hi_e) {
+                        const float4 q = __ldg(reinterpret_cast<const float4 *>(cl + e0));
+                        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                        in[0] = in[1] = in[2] = in[3] = true;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t ee = e0 + k;
+                            in[k] = (ee >= lo_e && ee < hi_e);
+                            v[k] = in[k] ? __ldg(cl + ee) : 0.f;
+                        }
+                    }
+                    float ccv[NC];
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) ccv[k] = fs.cuts[j][k];
+                    unsigned n[NC];
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) n[k] = 0u;
+                    if constexpr (NC == 7) {
+                        // <=128 particles per warp segment: packed 8-bit bins survive the warp sum
+                        unsigned plo = 0u, phi = 0u;
+                        count_vals<NC>(v, in, ccv, n, plo, phi);
+                        plo = __reduce_add_sync(0xffffffffu, plo);
+                        phi = __reduce_add_sync(0xffffffffu, phi);
+                        unsigned run = 0u, cum[8];
+#pragma unroll
+                        for (int sIdx = 0; sIdx < 4; ++sIdx) { run += (plo >> (8 * sIdx)) & 0xffu; cum[sIdx] = run; }
+#pragma unroll
+                        for (int sIdx = 0; sIdx < 4; ++sIdx) { run += (phi >> (8 * sIdx)) & 0xffu; cum[4 + sIdx] = run; }
+                        n[0] = cum[3]; n[1] = cum[1]; n[2] = cum[5]; n[3] = cum[0]; n[4] = cum[2]; n[5] = cum[4]; n[6] = cum[6];
+                    } else {
+                        unsigned dlo = 0u, dhi = 0u;
+                        count_vals<NC>(v, in, ccv, n, dlo, dhi);
+#pragma unroll
+                        for (int k = 0; k < NC; ++k) n[k] = __reduce_add_sync(0xffffffffu, n[k]);
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < NC; ++k)
+                            if (n[k]) atomicAdd(&s_cell[j * NC + k], n[k]);
+                    }
+                }
+                if (e > segEnd) break;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < (int)nc * NC; i += kThreads) {
+            const unsigned v = s_cell[i];
+            if (v) atomicAdd(&lv.cnt_l[(cFirst + i / NC) * kCS + (i % NC)], v);
+        }
+        __syncthreads();
+        r0 = r1;
+        cFirst += nc;
     }
-    __syncthreads();
-    for (int i = tid; i < kCountCellsSmem * NC; i += kThreads) {
-        const unsigned v = s_cell[i];
-        if (v) atomicAdd(&lv.cnt_l[(cT + i / NC) * kCS + (i % NC)], v);
-    }
-    __syncthreads();
 }
 
 // ---- regime A: cells much larger than a tile.  Persistent blocks, block b owns a contiguous range of tiles. ----
@@ -833,14 +873,37 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_stream(const float *__res
 // the iteration cap get their extra count at the final cut in the same launch.  No kernel launch, no host polling and
 // no speculative pass per bisection pass.  Single rank, levels of up to kPersistMaxCells cells in the streaming regime.
 constexpr uint32_t kPersistMaxCells = 8192;
+
+// Lightweight grid barrier for co-resident blocks (cooperative launch): one monotonic counter, barrier number `gen`
+// is complete when the counter reaches (gen + 1) * gridDim.x.  One atomic and one polling thread per block - cheaper
+// than cooperative_groups::grid_group::sync() for two barriers per bisection pass.
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int &gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned int target = (gen + 1u) * gridDim.x;
+        while (*((volatile unsigned int *)counter) < target) {}
+        __threadfence();
+    }
+    ++gen;
+    __syncthreads();
+}
 struct LevelCtl {
     uint32_t *n_active;                     // [maxPasses + 2] cells active after pass p at [p + 1]; zeroed per level
     unsigned long long *active_particles;   // [2] statistics (see PassCtl)
     int32_t *level_iters;
     int32_t *passes_out;                    // passes executed in this level
     uint32_t *n_unfound_out;                // cells that hit the iteration cap
+    unsigned int *barrier;                  // grid barrier counter, zeroed before the launch
     int compaction;                         // 1: full, compact, then candidate passes
+    unsigned long long *dbg;                // optional (ORB_DEBUG_TIMES): globaltimer stamps of block 0, 5 per pass
 };
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 template <int M>
 __global__ void __launch_bounds__(kThreads, 4) k_level_persistent(const float *__restrict__ x, const float *__restrict__ y,
@@ -856,13 +919,15 @@ __global__ void __launch_bounds__(kThreads, 4) k_level_persistent(const float *_
     __shared__ unsigned long long s_p, s_q;
     __shared__ int s_it;
     float4 *ring = reinterpret_cast<float4 *>(count_smem);
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    unsigned int gen = 0;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
 
     int pass = 0;
     for (; pass < maxPasses; ++pass) {
         const int mode = !lc.compaction ? kCountFull : (pass == 0 ? kCountFull : (pass == 1 ? kCountCompact : kCountCand));
         const int baseMode = !lc.compaction ? 0 : (pass == 0 ? 1 : 2);
+        const bool stamp = lc.dbg && blockIdx.x == 0 && threadIdx.x == 0;
+        if (stamp) lc.dbg[pass * 5 + 0] = gtimer();
         if constexpr (NC == 7) {
             if (mode == kCountCompact) stream_count_pass<NC, kCountCompact>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm);
             else if (mode == kCountCand) stream_count_pass<NC, kCountCand>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm);
@@ -870,8 +935,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_level_persistent(const float *_
         } else {
             stream_count_pass<NC, kCountFull>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm);
         }
-        __threadfence();
-        grid.sync();
+        if (stamp) lc.dbg[pass * 5 + 1] = gtimer();
+        grid_barrier(lc.barrier, gen);
+        if (stamp) lc.dbg[pass * 5 + 2] = gtimer();
         // ---- bisection update, one thread per cell across the whole grid ----
         if (threadIdx.x == 0) { s_n = 0; s_p = 0ull; s_q = 0ull; s_it = 0; }
         __syncthreads();
@@ -905,8 +971,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_level_persistent(const float *_
             if (s_q) atomicAdd(lc.active_particles + 1, s_q);
             if (s_it) atomicMax(lc.level_iters, s_it);
         }
-        __threadfence();
-        grid.sync();
+        if (stamp) lc.dbg[pass * 5 + 3] = gtimer();
+        grid_barrier(lc.barrier, gen);
+        if (stamp) lc.dbg[pass * 5 + 4] = gtimer();
         if (__ldcg(&lc.n_active[pass + 1]) == 0u) { ++pass; break; }
     }
     // ---- cells that hit the 32-iteration cap: one count at getCut() of their last margins (never counted before) ----
@@ -924,12 +991,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_level_persistent(const float *_
         }
         need = __reduce_add_sync(0xffffffffu, need);
         if ((threadIdx.x & 31) == 0 && need) atomicAdd(lc.n_unfound_out, need);
-        __threadfence();
-        grid.sync();
+        grid_barrier(lc.barrier, gen);
         if (__ldcg(lc.n_unfound_out) != 0u) {
             stream_count_pass<NC, kCountFull>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm);
-            __threadfence();
-            grid.sync();
+            grid_barrier(lc.barrier, gen);
             for (uint32_t c = gtid; c < nCells; c += gsize)
                 if (__ldcg(&lv.active[c])) {
                     const uint32_t v = __ldcg(lv.cnt_l + c * kCS);
