@@ -12,7 +12,8 @@
 //                    call per iteration (orbit.cpp:166-177), PST_PARTITIONGPU per level
 //   o = 2          : per level one PST_FINDCUTS (device-side bisection loop) + PST_PARTITIONGPU
 // Environment: ORB_MDL_THREADS=<ranks = GPUs>, ORB_FULL_LEVELS=1, ORB_TIGHT_BOX=1 (o=0 only),
-//              ORB_DIST=uniform|gaussian|plummer, ORB_DUMP=<prefix> (heap + per-rank ranges/particles).
+//              ORB_DIST=uniform|gaussian|plummer, ORB_TIPSY=<snapshot> (positions from a tipsy file; x = 0 takes
+//              all its bodies), ORB_DUMP=<prefix> (heap + per-rank ranges/particles).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -29,6 +30,7 @@
 #include "services/pst.h"
 #include "services/services.h"
 #include "services/setadd.h"
+#include "tipsy/tipsy.h"
 
 namespace {
 
@@ -92,8 +94,26 @@ int master(MDL vmdl, void *vpst) {
 
     const int pN = (int)std::strtol(mdl->argv[1], nullptr, 0);
     const int pd = (int)std::strtol(mdl->argv[2], nullptr, 0);
-    const int N = 1 << pN;
+    int N = 1 << pN;
     const int d = 1 << pd;
+    // ORB_TIPSY=<file>: positions come from a tipsy snapshot (the reference's dead `generate == false` branch,
+    // init.cu:54-59); x = 0 takes every body of the file, otherwise the first 2^x
+    const char *tipsyPath = std::getenv("ORB_TIPSY");
+    if (tipsyPath && *tipsyPath) {
+        TipsyIO io;
+        if (!io.open(tipsyPath)) {
+            std::fprintf(stderr, "orbit: %s\n", io.error().c_str());
+            return 1;
+        }
+        std::fprintf(stderr, "Count %llu n %d\n", (unsigned long long)io.count(), pN ? N : (int)io.count());   // init.cu:57
+        if (pN == 0) N = (int)io.count();
+        if ((unsigned long long)N > io.count() || N < mdl->Threads()) {
+            std::fprintf(stderr, "orbit: %s holds %llu bodies, fewer than the 2^%d requested\n", tipsyPath, (unsigned long long)io.count(), pN);
+            return 1;
+        }
+    } else {
+        tipsyPath = nullptr;
+    }
     const int mode = mdl->argc > 3 ? (int)std::strtol(mdl->argv[3], nullptr, 0) : 0;
     if (mode < 0 || mode > 2) {
         std::fprintf(stderr, "orbit: o must be 0, 1 or 2\n");
@@ -117,7 +137,7 @@ int master(MDL vmdl, void *vpst) {
     std::memset(heap.data(), 0, heap.size() * sizeof(Cell));
     heap[0] = root;
 
-    ServiceInit::input iInit{N / mdl->Threads(), d, true, params};
+    ServiceInit::input iInit{N / mdl->Threads(), d, tipsyPath == nullptr, params, N};
     ServiceInit::output oInit[1];
     mdl->RunService(PST_INIT, sizeof(iInit), &iInit, oInit);
 

@@ -1,7 +1,10 @@
 // services.cpp — Service()/Combine() bodies: thin calls into the C ABI (include/orb_b200.h).
 #include "services.h"
+#include "../tipsy/tipsy.h"
 
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -43,19 +46,34 @@ int ServiceInit::Service(PST pst, void *vin, int, void *, int) {
     const input in = *static_cast<input *>(vin);
     lcl->rank = mdlSelf(pst->mdl);
     lcl->nRanks = mdlThreads(pst->mdl);
-    lcl->nParticles = in.nParticles;
     lcl->nLeafCells = in.d;
-    lcl->firstParticle = (unsigned long long)lcl->rank * (unsigned long long)in.nParticles;
-    lcl->x.resize(in.nParticles);
-    lcl->y.resize(in.nParticles);
-    lcl->z.resize(in.nParticles);
+    if (in.generate) {
+        lcl->nParticles = in.nParticles;
+        lcl->firstParticle = (unsigned long long)lcl->rank * (unsigned long long)in.nParticles;
+    } else {
+        // contiguous slice [r*T/R, (r+1)*T/R) of the first T bodies of the file
+        const unsigned long long T = (unsigned long long)in.nTotal, R = (unsigned long long)lcl->nRanks;
+        lcl->firstParticle = (unsigned long long)lcl->rank * T / R;
+        lcl->nParticles = (int)(((unsigned long long)lcl->rank + 1) * T / R - lcl->firstParticle);
+    }
+    lcl->x.resize(lcl->nParticles);
+    lcl->y.resize(lcl->nParticles);
+    lcl->z.resize(lcl->nParticles);
     // deterministic slice of the single xorshf96 stream (the reference's generator state is a racy
     // file-scope static, init.cu:11, so its multi-thread runs are not reproducible; this is)
     const char *dist = std::getenv("ORB_DIST");
-    if (dist && std::string(dist) == "gaussian") orb_generate_clustered(0, lcl->firstParticle, in.nParticles, lcl->x.data(), lcl->y.data(), lcl->z.data());
+    if (!in.generate) {
+        // init.cu:54-59: `TipsyIO io; io.open(...); io.load(particles)` — every rank reads only its slice
+        const char *path = std::getenv("ORB_TIPSY");
+        TipsyIO io;
+        if (!path || !io.open(path) || !io.load(lcl->firstParticle, (uint64_t)lcl->nParticles, lcl->x.data(), lcl->y.data(), lcl->z.data())) {
+            std::fprintf(stderr, "orbit: tipsy input: %s\n", path ? io.error().c_str() : "ORB_TIPSY is not set");
+            std::exit(1);
+        }
+    } else if (dist && std::string(dist) == "gaussian") orb_generate_clustered(0, lcl->firstParticle, in.nParticles, lcl->x.data(), lcl->y.data(), lcl->z.data());
     else if (dist && std::string(dist) == "plummer") orb_generate_clustered(1, lcl->firstParticle, in.nParticles, lcl->x.data(), lcl->y.data(), lcl->z.data());
     else orb_generate_uniform(lcl->firstParticle, in.nParticles, lcl->x.data(), lcl->y.data(), lcl->z.data());
-    ORB_CHECK(orb_create(&lcl->ctx, lcl->rank, (uint64_t)in.nParticles, (uint32_t)in.d));
+    ORB_CHECK(orb_create(&lcl->ctx, lcl->rank, (uint64_t)lcl->nParticles, (uint32_t)in.d));
     if (lcl->nRanks > 1) {
         std::call_once(g_idOnce, [] { ORB_CHECK(orb_comm_unique_id(g_ncclId)); });
         ORB_CHECK(orb_comm_init(lcl->ctx, g_ncclId, lcl->rank, lcl->nRanks));

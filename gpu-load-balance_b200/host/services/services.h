@@ -19,8 +19,9 @@ public:
     struct input {
         int nParticles;     // per rank (N / Threads, orbit.cpp:83)
         int d;
-        bool generate;
+        bool generate;      // false: read positions from the tipsy file named by ORB_TIPSY (init.cu:54-59)
         META_PARAMS params;
+        int nTotal;         // generate == false: bodies taken from the file, split in contiguous slices over the ranks
     };
     typedef int output;
     explicit ServiceInit(PST pst) : TraverseCombinePST(pst, PST_INIT, sizeof(input), sizeof(output), "Init") {}

@@ -217,6 +217,13 @@ uint64_t orb_oracle_particle_hash(float x, float y, float z) {
     return mix64(a ^ mix64(b));
 }
 
+uint64_t orb_oracle_fnv1a(const void *bytes, size_t n) {
+    const unsigned char *b = (const unsigned char *)bytes;
+    uint64_t h = 1469598103934665603ULL;
+    for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ULL;
+    return h;
+}
+
 void orb_oracle_range_hashes(const float *x, const float *y, const float *z, int64_t begin, int64_t end,
                              uint64_t *set_hash, uint64_t *ordered_hash) {
     uint64_t set = 0, ord = 1469598103934665603ULL;

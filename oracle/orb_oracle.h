@@ -18,6 +18,7 @@
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -96,6 +97,7 @@ int orb_oracle_build(const orb_oracle_params *p, float *x, float *y, float *z, c
 
 /* hashes used in traces and tests */
 uint64_t orb_oracle_particle_hash(float x, float y, float z);
+uint64_t orb_oracle_fnv1a(const void *bytes, size_t n);   /* FNV-1a 64 over a byte string (heapHash of the CLI) */
 void orb_oracle_range_hashes(const float *x, const float *y, const float *z, int64_t begin, int64_t end,
                              uint64_t *set_hash, uint64_t *ordered_hash);
 

@@ -54,5 +54,7 @@ int main(int argc, char **argv) {
     unsigned long long h = 1469598103934665603ULL;
     for (int id = (1 << lastL) - 1; id <= (1 << (lastL + 1)) - 2; ++id) h = (h ^ ranges[2 * id + 1]) * 1099511628211ULL;
     fprintf(stderr, "rangeHash %016llx\n", h);
+    /* heapHash: FNV-1a over the bytes of the whole cell heap (padding bytes are zero) */
+    fprintf(stderr, "heapHash %016llx\n", (unsigned long long)orb_oracle_fnv1a(heap, nHeap * sizeof(orb_oracle_cell)));
     return 0;
 }

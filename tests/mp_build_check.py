@@ -11,6 +11,39 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 
+FNV_OFFSET, FNV_PRIME = 1469598103934665603, 1099511628211
+
+
+def known_answer_summary(out, rank, heap, st, rng, before, after):
+    """Full-size runs (too large to ship particle dumps): digests comparable with `oracle/orb_oracle`'s stderr
+    (iters, rangeHash of shard 0, heapHash) plus size-independent properties of this rank's slice."""
+    import json
+    import oracle_py
+
+    L = st.n_levels
+    ids = np.arange((1 << L) - 1, (1 << (L + 1)) - 1)
+    b, e = rng[ids, 0].astype(np.int64), rng[ids, 1].astype(np.int64)
+    n = before[0].size
+    props = {"tiles": bool(b[0] == 0 and e[-1] == n and np.array_equal(b[1:], e[:-1]) and np.all(e >= b))}
+    ne = e > b
+    inside = True
+    for a, col in enumerate(after):
+        lo = np.minimum.reduceat(col, np.minimum(b, n - 1))[ne]
+        hi = np.maximum.reduceat(col, np.minimum(b, n - 1))[ne]
+        inside &= bool(np.all(lo >= heap["lower"][ids, a][ne]) and np.all(hi <= heap["upper"][ids, a][ne]))
+    props["leaf_particles_inside_leaf_boxes"] = inside
+    props["multiset_preserved"] = oracle_py.range_hashes(*before, 0, n)[0] == oracle_py.range_hashes(*after, 0, n)[0]
+    rec = {"rank": rank, "props": props}
+    if rank == 0:
+        h = FNV_OFFSET
+        for v in e.tolist():
+            h = ((h ^ v) * FNV_PRIME) & 0xFFFFFFFFFFFFFFFF
+        hb = np.frombuffer(heap.tobytes(), np.uint8)
+        rec.update(iters=list(st.iters[:L]), passes=list(st.passes[:L]), not_found=list(st.not_found[:L]),
+                   rangeHash=f"{h:016x}", heapHash=f"{oracle_py.fnv1a(hb):016x}", ms_total=st.ms_total)
+    (out / f"known{rank}.json").write_text(json.dumps(rec))
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -18,6 +51,7 @@ def main():
     from gpu_load_balance_b200 import dist as od
 
     out = Path(sys.argv[1]); x_log2 = int(sys.argv[2]); y_log2 = int(sys.argv[3]); peers = sys.argv[4] == "1"
+    known = len(sys.argv) > 5 and sys.argv[5] == "known"
     rank, world, local = od.env_rank_world()
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -30,7 +64,10 @@ def main():
     heap, st = ctx.build()
     gx, gy, gz = ctx.download()
     rng = ctx.ranges()
-    np.savez(out / f"rank{rank}.npz", heap=heap.view(np.uint8), rng=rng, x=gx, y=gy, z=gz, iters=np.array(st.iters[:st.n_levels]))
+    if known:
+        known_answer_summary(out, rank, heap, st, rng, (x, y, z), (gx, gy, gz))
+    else:
+            np.savez(out / f"rank{rank}.npz", heap=heap.view(np.uint8), rng=rng, x=gx, y=gy, z=gz, iters=np.array(st.iters[:st.n_levels]))
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -117,6 +117,14 @@ def partition_canonical(x, y, z, begin, end, axis, cut) -> int:
     return int(lib().orb_oracle_partition_canonical(_p(x), _p(y), _p(z), begin, end, axis, C.c_float(float(cut))))
 
 
+def fnv1a(buf: np.ndarray) -> int:
+    buf = np.ascontiguousarray(buf).view(np.uint8)
+    f = lib().orb_oracle_fnv1a
+    f.restype = C.c_uint64
+    f.argtypes = [C.c_void_p, C.c_size_t]
+    return int(f(buf.ctypes.data, buf.size))
+
+
 def range_hashes(x, y, z, begin, end):
     a, b = C.c_uint64(0), C.c_uint64(0)
     lib().orb_oracle_range_hashes(_p(x), _p(y), _p(z), begin, end, C.byref(a), C.byref(b))
@@ -231,3 +239,42 @@ def particle_hash(x, y, z) -> np.ndarray:
 def set_hash(x, y, z) -> int:
     with np.errstate(over="ignore"):
         return int(particle_hash(x, y, z).sum(dtype=np.uint64))
+
+
+# ---- tipsy snapshots (checker-side numpy restatement of the file layout; the product reader is
+# gpu-load-balance_b200/host/tipsy/tipsy.cpp, standing in for the reference's missing src/tipsy, init.cu:54-59) ----
+TIPSY_FLOATS = {"gas": 12, "dark": 9, "star": 11}
+
+
+def write_tipsy(path, gas, dark, star, *, standard=True, header_bytes=32, time=0.25, seed=0):
+    """gas / dark / star: (n_k, 3) float32 positions; the other fields get arbitrary non-zero filler."""
+    e = ">" if standard else "<"
+    rng = np.random.default_rng(seed)
+    parts = [np.asarray(p, np.float32).reshape(-1, 3) for p in (gas, dark, star)]
+    n = [len(p) for p in parts]
+    hdr = np.array([time], e + "f8").tobytes() + np.array([sum(n), 3, n[0], n[1], n[2]], e + "i4").tobytes()
+    hdr += b"\0" * (header_bytes - 28)
+    with open(path, "wb") as f:
+        f.write(hdr)
+        for pos, kind in zip(parts, ("gas", "dark", "star")):
+            rec = rng.random((len(pos), TIPSY_FLOATS[kind]), dtype=np.float32) + 1.0
+            rec[:, 1:4] = pos
+            f.write(rec.astype(e + "f4").tobytes())
+
+
+def read_tipsy(path):
+    """Returns (x, y, z) float32 columns of all bodies, file order (gas, dark, star)."""
+    raw = Path(path).read_bytes()
+    e = "<" if 1 <= int(np.frombuffer(raw, "<i4", 1, 12)[0]) <= 3 else ">"
+    n_all, ndim, ns, nd, nst = (int(v) for v in np.frombuffer(raw, e + "i4", 5, 8))
+    assert ndim == 3 and ns + nd + nst == n_all
+    body = 4 * (12 * ns + 9 * nd + 11 * nst)
+    off = len(raw) - body
+    assert off in (28, 32)
+    cols = []
+    for cnt, fl in ((ns, 12), (nd, 9), (nst, 11)):
+        rec = np.frombuffer(raw, e + "f4", cnt * fl, off).reshape(cnt, fl)
+        cols.append(rec[:, 1:4].astype(np.float32))
+        off += 4 * cnt * fl
+    pos = np.concatenate(cols)
+    return (np.ascontiguousarray(pos[:, 0]), np.ascontiguousarray(pos[:, 1]), np.ascontiguousarray(pos[:, 2]))

@@ -33,3 +33,44 @@ def test_two_process_build_matches_sharded_oracle(oracle, tmp_path, peers):
         assert np.array_equal(got["rng"], ref["ranges"][rank])
         assert np.array_equal(got["x"].view(np.uint32), ref["x"][rank * per:(rank + 1) * per].view(np.uint32))
         assert list(got["iters"]) == list(ref["stats"].iters[:len(got["iters"])])
+
+
+def _torchrun(nproc, port, *args, timeout=1800):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "tests" / "mp_build_check.py"), *[str(a) for a in args]]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+# `oracle/orb_oracle <x> <y> --ties=canonical --shards=R --threads=8` (stderr: iters, rangeHash of shard 0, heapHash),
+# run once on the CPU; the cuts do not depend on R, the shard-0 ranges do
+KNOWN = {
+    # deepest level has 2^14 cells: crosses from the peer-memory combine (<= 8192 cells) to the NCCL allreduce
+    (24, 16, 2): dict(iters=[21, 22, 20, 19, 19, 18, 17, 16, 16, 15, 15, 13, 12, 12, 11],
+                      rangeHash="9112c3e5038b9242", heapHash="95ff3821b0e9c3f8"),
+    # C5 of SURVEY.md §8: 2^30 particles -> 2^20 leaf cells on 8 GPUs (oracle: 77 s on 8 host threads)
+    (30, 20, 8): dict(iters=[24, 24, 32, 32, 32, 32, 32, 22, 22, 21, 20, 19, 19, 18, 17, 17, 16, 15, 15],
+                      rangeHash="1ddd9f5319d9728b", heapHash="5b50073ca40e7109"),
+}
+
+
+@pytest.mark.parametrize("x,y,R", [(24, 16, 2), (30, 20, 8)])
+def test_full_size_known_answers(tmp_path, x, y, R):
+    """Full-size runs (C5: 2^30 -> 2^20 on 8 GPUs), one process per GPU: digests equal the CPU oracle's, and on every rank the leaf ranges tile
+    the slice, every particle lies inside its leaf's box and the particle multiset is preserved."""
+    import json
+    import torch
+
+    if torch.cuda.device_count() < R:
+        pytest.skip(f"needs {R} GPUs")
+    _torchrun(R, 29950 + os.getpid() % 40, tmp_path, x, y, 1, "known")
+    want = KNOWN[(x, y, R)]
+    for rank in range(R):
+        rec = json.loads((tmp_path / f"known{rank}.json").read_text())
+        assert all(rec["props"].values()), rec
+        if rank == 0:
+            assert rec["iters"] == want["iters"]
+            assert rec["rangeHash"] == want["rangeHash"]
+            if want["heapHash"]:
+                assert rec["heapHash"] == want["heapHash"]
+            print(f"{x}/{y}/{R} build ms", rec["ms_total"], "passes", rec["passes"], "not_found", rec["not_found"])

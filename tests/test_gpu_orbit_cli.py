@@ -114,3 +114,64 @@ def test_orbit_two_ranks_reference_exact(oracle, tmp_path, o):
         _, rng, gx, gy, gz = read_dump(tmp_path, oracle, r)
         assert np.array_equal(rng, ref["ranges"][r])
         assert np.array_equal(gx.view(np.uint32), ref["x"][r * per:(r + 1) * per].view(np.uint32))
+
+
+def _snapshot(oracle, tmp_path, n):
+    """Clustered positions in a big-endian tipsy file holding gas, dark and star bodies."""
+    rng = np.random.default_rng(11)
+    centres = rng.uniform(-0.35, 0.35, (16, 3))
+    pos = (centres[rng.integers(0, 16, n)] + rng.normal(0.0, 0.03, (n, 3))).clip(-0.5, 0.5).astype(np.float32)
+    path = tmp_path / "snap.std"
+    oracle.write_tipsy(path, pos[:n // 5], pos[n // 5:n - 777], pos[n - 777:], standard=True)
+    return path, pos
+
+
+@pytest.mark.parametrize("o", [0, 1])
+def test_orbit_tipsy_snapshot_input(oracle, tmp_path, o):
+    """ORB_TIPSY: positions come from a tipsy snapshot (init.cu:54-59); x = 0 takes every body, here a count that
+    is not a power of two.  Tree, ranges and particle order equal the oracle's on the same positions."""
+    n, y = 50001, 6
+    path, pos = _snapshot(oracle, tmp_path, n)
+    out = run_orbit(0, y, o, tmp_path, env_extra={"ORB_TIPSY": str(path)})
+    assert re.search(rf"^CountCopy-0-{y}, \d+ $", out, re.M)
+    heap, rng, gx, gy, gz = read_dump(tmp_path, oracle)
+    ref = oracle.build(pos[:, 0], pos[:, 1], pos[:, 2], 1 << y, ties=oracle.TIES_CANONICAL)
+    assert heap.tobytes() == ref["heap"].tobytes()
+    assert np.array_equal(rng, ref["ranges"][0])
+    assert np.array_equal(gx.view(np.uint32), ref["x"].view(np.uint32))
+    assert np.array_equal(gy.view(np.uint32), ref["y"].view(np.uint32))
+    assert np.array_equal(gz.view(np.uint32), ref["z"].view(np.uint32))
+
+
+def test_orbit_tipsy_prefix_and_errors(oracle, tmp_path):
+    """x > 0 takes the first 2^x bodies; a snapshot that is too small is refused."""
+    path, pos = _snapshot(oracle, tmp_path, 50001)
+    run_orbit(15, 5, 0, tmp_path, env_extra={"ORB_TIPSY": str(path)})
+    heap, rng, gx, *_ = read_dump(tmp_path, oracle)
+    m = 1 << 15
+    ref = oracle.build(pos[:m, 0], pos[:m, 1], pos[:m, 2], 1 << 5, ties=oracle.TIES_CANONICAL)
+    assert heap.tobytes() == ref["heap"].tobytes()
+    assert np.array_equal(gx.view(np.uint32), ref["x"].view(np.uint32))
+    env = dict(os.environ, ORB_MDL_THREADS="1", ORB_TIPSY=str(path))
+    r = subprocess.run([str(ORBIT), "16", "5", "0"], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "fewer than" in r.stderr
+
+
+def test_orbit_tipsy_two_ranks_uneven_slices(oracle, tmp_path):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n, y, R = 50001, 6, 2
+    path, pos = _snapshot(oracle, tmp_path, n)
+    run_orbit(0, y, 0, tmp_path, threads=R, env_extra={"ORB_TIPSY": str(path)})
+    off = [r * n // R for r in range(R + 1)]
+    ref = oracle.build(pos[:, 0], pos[:, 1], pos[:, 2], 1 << y, ties=oracle.TIES_CANONICAL, n_shards=R, shard_off=off)
+    heap = np.fromfile(tmp_path / "dump.heap", dtype=oracle.CELL_DTYPE)
+    heap["pad_"] = 0
+    assert heap.tobytes() == ref["heap"].tobytes()
+    for r in range(R):
+        _, rng, gx, gy, gz = read_dump(tmp_path, oracle, r)
+        assert np.array_equal(rng, ref["ranges"][r])
+        assert np.array_equal(gx.view(np.uint32), ref["x"][off[r]:off[r + 1]].view(np.uint32))
+        assert np.array_equal(gz.view(np.uint32), ref["z"][off[r]:off[r + 1]].view(np.uint32))
