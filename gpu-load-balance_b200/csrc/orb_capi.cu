@@ -75,6 +75,8 @@ struct NcclApi {
     } while (0)
 
 constexpr int kMaxLevels = 40;
+constexpr int kDbgPasses = 12;      // ORB_DEBUG_TIMES=2: passes and blocks recorded per level
+constexpr uint32_t kDbgBlocks = 1024;
 constexpr int kPassSlots = 40;   // >= 32 passes + slack, per level
 
 }  // namespace
@@ -129,6 +131,8 @@ struct orb_ctx {
     int occPersist[4] = {0, 0, 0, 0}; // resident blocks per SM of k_level_persistent<M>
     int32_t *d_lvl_passes = nullptr;  // [kMaxLevels]
     unsigned long long *d_dbg = nullptr; // ORB_DEBUG_TIMES: [kMaxLevels][64] globaltimer stamps
+    unsigned long long *d_dbg_blocks = nullptr;   // ORB_DEBUG_TIMES=2: [kMaxLevels][kDbgPasses][kDbgBlocks][4] per-block stamps
+    uint32_t dbgGrid[kMaxLevels] = {};
     uint32_t *d_lvl_unfound = nullptr; // [kMaxLevels]
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evCount, evPart;
@@ -382,6 +386,8 @@ int launch_level_persistent(orb_ctx *c, uint32_t nCells, int M, int slotBase, in
     lc.compaction = (c->compaction && M == 3) ? 1 : 0;
     lc.barrier = c->d_cdone + slotBase;   // per-level counter, zeroed with the pass-control arrays
     lc.dbg = c->d_dbg ? c->d_dbg + (size_t)levelIdx * 64 : nullptr;
+    lc.dbg_blocks = (c->d_dbg_blocks && grid <= kDbgBlocks) ? c->d_dbg_blocks + (size_t)levelIdx * kDbgPasses * kDbgBlocks * 4 : nullptr;
+    if (lc.dbg_blocks) c->dbgGrid[levelIdx] = grid;
     void *args[] = {(void *)&x, (void *)&y, (void *)&z, (void *)&cand, (void *)&c->lv, (void *)&c->d_tile_first,
                     (void *)&nC, (void *)&nL, (void *)&nT, (void *)&lc};
     const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
@@ -677,6 +683,11 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     if (getenv("ORB_DEBUG_TIMES")) {
         CK(cudaMalloc(&c->d_dbg, sizeof(unsigned long long) * 64 * kMaxLevels));
         CK(cudaMemset(c->d_dbg, 0, sizeof(unsigned long long) * 64 * kMaxLevels));
+        if (atoi(getenv("ORB_DEBUG_TIMES")) >= 2) {
+            const size_t bytes = sizeof(unsigned long long) * (size_t)kMaxLevels * kDbgPasses * kDbgBlocks * 4;
+            CK(cudaMalloc(&c->d_dbg_blocks, bytes));
+            CK(cudaMemset(c->d_dbg_blocks, 0, bytes));
+        }
     }
     const char *smt = getenv("ORB_STREAM_MIN_TILES");
     if (smt && atoi(smt) >= 1) c->streamMinTiles = atoi(smt);
@@ -705,6 +716,7 @@ int orb_destroy(orb_ctx *c) {
     cudaFree(c->lv.nleft_g); cudaFree(c->lv.nleft_l); cudaFree(c->lv.cuts); cudaFree(c->lv.cnt_l);
     cudaFree(c->lv.compL); cudaFree(c->lv.compR); cudaFree(c->lv.base_l); cudaFree(c->lv.tile_ncand);
     if (c->d_cnt_g_buf) cudaFree(c->d_cnt_g_buf);
+    cudaFree(c->d_dbg); cudaFree(c->d_dbg_blocks);
     for (int r = 0; r < orb::kMaxPeers; ++r)
         if (c->peerIpc[r]) { cudaIpcCloseMemHandle(c->peerCnt[r]); cudaIpcCloseMemHandle(c->peerFlag[r]); }
     cudaFree(c->d_lvl_passes); cudaFree(c->d_lvl_unfound); cudaFree(c->d_cdone); cudaFree(c->d_peer_cnt); cudaFree(c->d_peer_flag);
@@ -1162,6 +1174,25 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             fprintf(stderr, "\n");
         }
         cudaMemset(c->d_dbg, 0, sizeof(unsigned long long) * 64 * kMaxLevels);
+    }
+    if (c->d_dbg_blocks) {
+        // raw dump for offline analysis: per level u32 level, u32 grid, then [kDbgPasses][grid][4] u64 stamps
+        const char *path = getenv("ORB_DEBUG_TIMES_FILE");
+        FILE *f = fopen(path ? path : "orb_block_times.bin", "wb");
+        if (f) {
+            std::vector<unsigned long long> t((size_t)kDbgPasses * kDbgBlocks * 4);
+            for (int l = 0; l < nDone; ++l) {
+                const uint32_t g = c->dbgGrid[l];
+                if (!g) continue;
+                cudaMemcpy(t.data(), c->d_dbg_blocks + (size_t)l * kDbgPasses * kDbgBlocks * 4, (size_t)kDbgPasses * g * 4 * 8, cudaMemcpyDeviceToHost);
+                const uint32_t hdr[2] = {(uint32_t)l + 1u, g};
+                fwrite(hdr, 4, 2, f);
+                fwrite(t.data(), 8, (size_t)kDbgPasses * g * 4, f);
+            }
+            fclose(f);
+        }
+        cudaMemset(c->d_dbg_blocks, 0, sizeof(unsigned long long) * (size_t)kMaxLevels * kDbgPasses * kDbgBlocks * 4);
+        memset(c->dbgGrid, 0, sizeof(c->dbgGrid));
     }
     if (stats) {
         memset(stats, 0, sizeof(*stats));

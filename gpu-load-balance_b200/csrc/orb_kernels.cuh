@@ -604,6 +604,12 @@ constexpr int kCountStages = 3;  // depth of the per-thread cp.async ring (tiles
 constexpr int kCountFull = 0, kCountCompact = 1, kCountCand = 2;
 constexpr int kWarpSlots = kCountTile / kWarps;   // candidate slots per (tile, warp)
 
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // static shared memory of one streaming count pass (one instance per kernel)
 template <int NC>
 struct CountSmem {
@@ -624,7 +630,7 @@ __device__ __forceinline__ void stream_count_pass(const float *__restrict__ x, c
                                                   const float *__restrict__ z, float *__restrict__ cand,
                                                   const LevelState &lv, const uint32_t *__restrict__ tile_first,
                                                   uint32_t nCells, uint32_t nLocal, uint32_t nTiles, float4 *ring,
-                                                  CountSmem<NC> &sm) {
+                                                  CountSmem<NC> &sm, unsigned long long *stamps = nullptr) {
     constexpr int NB = Acc<NC>::NB;
     uint32_t *s_acc = sm.acc, *s_cell = sm.cell, *s_uTile = sm.uTile, *s_uCell = sm.uCell, *s_fTile = sm.fTile, *s_fCell = sm.fCell;
     uint32_t *s_wS = sm.wS, *s_wF = sm.wF;
@@ -723,6 +729,7 @@ __device__ __forceinline__ void stream_count_pass(const float *__restrict__ x, c
         }
         if (kind == 2) { const uint32_t r = offF + __popc(mF & ltMask); s_fTile[r] = t; s_fCell[r] = c; }
         __syncthreads();
+        if (stamps && tid == 0 && base == tb0) stamps[1] = gtimer();   // classified
 
         auto enter_cell = [&](uint32_t k) {   // block-uniform: unit k starts a new cell
             const uint32_t cK = s_uCell[k];
@@ -847,6 +854,7 @@ __device__ __forceinline__ void stream_count_pass(const float *__restrict__ x, c
         }
         __syncthreads();
     }
+    if (stamps && tid == 0) stamps[2] = gtimer();   // streamed, before the last flush
     flush();
 }
 
@@ -898,12 +906,8 @@ struct LevelCtl {
     unsigned int *barrier;                  // grid barrier counter, zeroed before the launch
     int compaction;                         // 1: full, compact, then candidate passes
     unsigned long long *dbg;                // optional (ORB_DEBUG_TIMES): globaltimer stamps of block 0, 5 per pass
+    unsigned long long *dbg_blocks;         // optional (ORB_DEBUG_TIMES=2): [pass][block][4] start, classified, streamed, flushed
 };
-__device__ __forceinline__ unsigned long long gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
 
 template <int M>
 __global__ void __launch_bounds__(kThreads, 4) k_level_persistent(const float *__restrict__ x, const float *__restrict__ y,
@@ -928,13 +932,16 @@ __global__ void __launch_bounds__(kThreads, 4) k_level_persistent(const float *_
         const int baseMode = !lc.compaction ? 0 : (pass == 0 ? 1 : 2);
         const bool stamp = lc.dbg && blockIdx.x == 0 && threadIdx.x == 0;
         if (stamp) lc.dbg[pass * 5 + 0] = gtimer();
+        unsigned long long *bs = lc.dbg_blocks ? lc.dbg_blocks + ((size_t)pass * gridDim.x + blockIdx.x) * 4 : nullptr;
+        if (bs && threadIdx.x == 0) bs[0] = gtimer();
         if constexpr (NC == 7) {
-            if (mode == kCountCompact) stream_count_pass<NC, kCountCompact>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm);
-            else if (mode == kCountCand) stream_count_pass<NC, kCountCand>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm);
-            else stream_count_pass<NC, kCountFull>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm);
+            if (mode == kCountCompact) stream_count_pass<NC, kCountCompact>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm, bs);
+            else if (mode == kCountCand) stream_count_pass<NC, kCountCand>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm, bs);
+            else stream_count_pass<NC, kCountFull>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm, bs);
         } else {
-            stream_count_pass<NC, kCountFull>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm);
+            stream_count_pass<NC, kCountFull>(x, y, z, cand, lv, tile_first, nCells, nLocal, nTiles, ring, sm, bs);
         }
+        if (bs && threadIdx.x == 0) bs[3] = gtimer();
         if (stamp) lc.dbg[pass * 5 + 1] = gtimer();
         grid_barrier(lc.barrier, gen);
         if (stamp) lc.dbg[pass * 5 + 2] = gtimer();
