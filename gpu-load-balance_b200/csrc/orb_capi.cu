@@ -21,6 +21,7 @@
 #endif
 
 #include "orb_kernels.cuh"
+#include "orb_select.cuh"
 
 namespace {
 
@@ -75,6 +76,7 @@ struct NcclApi {
     } while (0)
 
 constexpr int kMaxLevels = 40;
+constexpr uint32_t kSelValsCap = 49152;   // values one block of the selection search stages in shared memory (192 KB)
 constexpr int kDbgPasses = 12;      // ORB_DEBUG_TIMES=2: passes and blocks recorded per level
 constexpr uint32_t kDbgBlocks = 1024;
 constexpr int kPassSlots = 40;   // >= 32 passes + slack, per level
@@ -134,7 +136,16 @@ struct orb_ctx {
     unsigned long long *d_dbg_blocks = nullptr;   // ORB_DEBUG_TIMES=2: [kMaxLevels][kDbgPasses][kDbgBlocks][4] per-block stamps
     uint32_t dbgGrid[kMaxLevels] = {};
     uint32_t *d_lvl_unfound = nullptr; // [kMaxLevels]
+    // selection-based cut search (orb_select.cuh): single rank, default trial depth
+    bool select = true;
+    orb::SelState sel{};
+    size_t selHistWords = 0;
+    uint32_t *d_sel_nflag = nullptr;   // [kMaxLevels] cells left to the iterative path per level
+    int occSelStream[2] = {1, 1};
     bool profile = false;
+    struct LabelledEvent { const char *label; int level; cudaEvent_t e0, e1; };
+    std::vector<LabelledEvent> evAux;      // profile mode: per-kernel times of the selection search
+    size_t evAuxUsed = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evCount, evPart;
     size_t evCountUsed = 0, evPartUsed = 0;
 
@@ -370,7 +381,8 @@ bool level_can_persist(const orb_ctx *c, uint32_t nCells, int M) {
            M >= 1 && M <= 3 && c->occPersist[M] >= 1;
 }
 
-int launch_level_persistent(orb_ctx *c, uint32_t nCells, int M, int slotBase, int levelIdx) {
+int launch_level_persistent(orb_ctx *c, uint32_t nCells, int M, int slotBase, int levelIdx, const uint32_t *gate = nullptr,
+                            const uint32_t *only = nullptr) {
     using namespace orb;
     const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
     const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(c->occPersist[M], 4));
@@ -385,8 +397,10 @@ int launch_level_persistent(orb_ctx *c, uint32_t nCells, int M, int slotBase, in
     lc.n_unfound_out = c->d_lvl_unfound + levelIdx;
     lc.compaction = (c->compaction && M == 3) ? 1 : 0;
     lc.barrier = c->d_cdone + slotBase;   // per-level counter, zeroed with the pass-control arrays
-    lc.dbg = c->d_dbg ? c->d_dbg + (size_t)levelIdx * 64 : nullptr;
-    lc.dbg_blocks = (c->d_dbg_blocks && grid <= kDbgBlocks) ? c->d_dbg_blocks + (size_t)levelIdx * kDbgPasses * kDbgBlocks * 4 : nullptr;
+    lc.dbg = (c->d_dbg && !gate) ? c->d_dbg + (size_t)levelIdx * 64 : nullptr;
+    lc.gate = gate;
+    lc.only = only;
+    lc.dbg_blocks = (c->d_dbg_blocks && grid <= kDbgBlocks && !gate) ? c->d_dbg_blocks + (size_t)levelIdx * kDbgPasses * kDbgBlocks * 4 : nullptr;
     if (lc.dbg_blocks) c->dbgGrid[levelIdx] = grid;
     void *args[] = {(void *)&x, (void *)&y, (void *)&z, (void *)&cand, (void *)&c->lv, (void *)&c->d_tile_first,
                     (void *)&nC, (void *)&nL, (void *)&nT, (void *)&lc};
@@ -410,6 +424,138 @@ int launch_level_persistent(orb_ctx *c, uint32_t nCells, int M, int slotBase, in
     c->nCountLaunch++;
     CK(cudaGetLastError());
     return ORB_OK;
+}
+
+// profile mode: time one kernel of the selection search under a label
+int aux_begin(orb_ctx *c, const char *label, int level) {
+    if (!c->profile) return ORB_OK;
+    if (c->evAuxUsed == c->evAux.size()) {
+        orb_ctx::LabelledEvent ev{label, level, nullptr, nullptr};
+        CK(cudaEventCreate(&ev.e0));
+        CK(cudaEventCreate(&ev.e1));
+        c->evAux.push_back(ev);
+    }
+    c->evAux[c->evAuxUsed].label = label;
+    c->evAux[c->evAuxUsed].level = level;
+    CK(cudaEventRecord(c->evAux[c->evAuxUsed].e0, c->stream));
+    return ORB_OK;
+}
+int aux_end(orb_ctx *c) {
+    if (!c->profile) return ORB_OK;
+    CK(cudaEventRecord(c->evAux[c->evAuxUsed].e1, c->stream));
+    c->evAuxUsed++;
+    return ORB_OK;
+}
+
+// Selection-based cut search of a level (orb_select.cuh): two streaming passes + a per-cell finish where cells are
+// large, one read per cell where they fit in shared memory; then the iterative search (gated on the device, no host
+// round trip) for the cells it flagged.  Single rank, default trial depth.
+bool level_can_select(const orb_ctx *c, uint32_t nCells, int M) {
+    return c->select && c->nRanks == 1 && c->nLocal > 0 && M == 3 && c->persist && c->occPersist[3] >= 1 && nCells >= 1;
+}
+
+// event pair of one particle-streaming kernel (counted in ms_count: these are the HBM-bound kernels of the search)
+int count_event_begin(orb_ctx *c) {
+    if (!c->profile) return ORB_OK;
+    if (c->evCountUsed == c->evCount.size()) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        c->evCount.emplace_back(a, b);
+    }
+    CK(cudaEventRecord(c->evCount[c->evCountUsed].first, c->stream));
+    return ORB_OK;
+}
+int count_event_end(orb_ctx *c) {
+    if (!c->profile) return ORB_OK;
+    CK(cudaEventRecord(c->evCount[c->evCountUsed].second, c->stream));
+    c->evCountUsed++;
+    return ORB_OK;
+}
+
+int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx) {
+    using namespace orb;
+    const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
+    float *cand = c->x[c->cur ^ 1];
+    SelState ss = c->sel;
+    ss.n_flagged = c->d_sel_nflag + levelIdx;
+    SelCtl sc;
+    sc.active_particles = c->d_active_particles;
+    sc.level_iters = c->d_level_iters + levelIdx;
+    sc.passes_out = c->d_lvl_passes + levelIdx;
+    sc.n_unfound_out = c->d_lvl_unfound + levelIdx;
+    int rc;
+    const uint64_t avg = c->nLocal / nCells;
+    const uint64_t cellCap = avg + avg / 8 + 256;
+    // block size of the per-cell search kernels: big blocks when shared memory allows one block per SM anyway
+    auto search_threads = [](size_t smem) { return smem > 112 * 1024 ? 1024 : (smem > 56 * 1024 ? 512 : 256); };
+    if (cellCap <= kSelValsCap) {
+        // ---- cells fit in shared memory: one read per cell ----
+        const size_t smem = sel_search_smem_bytes((uint32_t)cellCap);
+        const int threads = search_threads(smem);
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_cells, threads, smem));
+        const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
+        if ((rc = count_event_begin(c))) return rc;
+        k_sel_cells<<<grid, threads, smem, c->stream>>>(x, y, z, c->lv, ss, sc, nCells, (uint32_t)cellCap);
+        if ((rc = count_event_end(c))) return rc;
+        c->nCountLaunch++;
+    } else {
+        // ---- HIST (+ RESOLVE by the last block of each cell), COMPACT, FINISH ----
+        int nb1 = kSelBinsMin;
+        while (nb1 < kSelBinsMax && avg / (uint64_t)nb1 > 16384) nb1 <<= 1;
+        const int rep = nb1 <= 512 ? 4 : (nb1 <= 1024 ? 2 : 1);
+        const size_t words = (size_t)nCells * (size_t)nb1;
+        if (words > c->selHistWords) return fail(ORB_ERR_STATE, "selection histogram of %zu words exceeds the buffer", words);
+        // candidates one block will stage per cell: a few bins' worth; cells beyond it go to the iterative search
+        const uint32_t candCap = (uint32_t)std::min<uint64_t>(kSelValsCap, 4 * (avg / (uint64_t)nb1) + 4096);
+        CK(cudaMemsetAsync(ss.hist, 0, words * 4, c->stream));
+        unsigned long long *dbgBase = c->d_dbg_blocks ? c->d_dbg_blocks + (size_t)levelIdx * kDbgPasses * kDbgBlocks * 4 : nullptr;
+        if (dbgBase) c->dbgGrid[levelIdx] = kDbgBlocks;
+        const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
+        const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
+        const uint32_t nL = (uint32_t)c->nLocal;
+        {
+            const size_t smem = ringBytes + (size_t)nb1 * rep * 4;
+            int occ = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelHist>, kThreads, smem));
+            const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 4));
+            if ((rc = count_event_begin(c))) return rc;
+            k_sel_stream<kSelHist><<<grid, kThreads, smem, c->stream>>>(x, y, z, cand, c->lv, ss, c->d_tile_first, nCells, nL, nTiles, nb1, rep, candCap, dbgBase ? dbgBase : nullptr);
+            if ((rc = count_event_end(c))) return rc;
+        }
+        {
+            const size_t smem = ringBytes + (size_t)kWarps * kSelWarpStage * 4 + (size_t)nb1 * 4;
+            int occ = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelCompact>, kThreads, smem));
+            const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 3));
+            if ((rc = count_event_begin(c))) return rc;
+            k_sel_stream<kSelCompact><<<grid, kThreads, smem, c->stream>>>(x, y, z, cand, c->lv, ss, c->d_tile_first, nCells, nL, nTiles, nb1, 1, candCap, dbgBase ? dbgBase + (size_t)kDbgBlocks * 4 : nullptr);
+            if ((rc = count_event_end(c))) return rc;
+        }
+        {
+            const size_t smem = sel_search_smem_bytes(candCap);
+            const int threads = nCells <= 2u * (uint32_t)c->nSM ? 1024 : search_threads(smem);
+            int occ = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_finish, threads, smem));
+            const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
+            if ((rc = aux_begin(c, "finish", levelIdx))) return rc;
+            k_sel_finish<<<grid, threads, smem, c->stream>>>(cand, c->lv, ss, sc, nCells, nb1, candCap, c->d_err,
+                                                             dbgBase ? dbgBase + (size_t)2 * kDbgBlocks * 4 : nullptr);
+            if ((rc = aux_end(c))) return rc;
+        }
+        c->nCountLaunch += 2;
+        c->nUpdateLaunch += 1;    // the finish kernel takes the place of the per-pass update kernels
+    }
+    CK(cudaGetLastError());
+    // cells the search could not finish: the iterative search, gated on the device by this level's flag count
+    if ((rc = aux_begin(c, "fallback_gate", levelIdx))) return rc;
+    const bool prof = c->profile;
+    c->profile = false;            // its time belongs to the aux group, not to ms_count
+    rc = launch_level_persistent(c, nCells, 3, slotBase, levelIdx, ss.n_flagged, ss.flag);
+    c->profile = prof;
+    if (rc) return rc;
+    return aux_end(c);
 }
 
 // after the loop: cells that hit the iteration cap need one extra count at their final cut
@@ -534,6 +680,7 @@ int reset_pass_ctl(orb_ctx *c) {
     CK(cudaMemsetAsync(c->d_cdone, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots, c->stream));
     CK(cudaMemsetAsync(c->d_lvl_passes, 0, sizeof(int32_t) * kMaxLevels, c->stream));
     CK(cudaMemsetAsync(c->d_lvl_unfound, 0, sizeof(uint32_t) * kMaxLevels, c->stream));
+    CK(cudaMemsetAsync(c->d_sel_nflag, 0, sizeof(uint32_t) * kMaxLevels, c->stream));
     CK(cudaMemsetAsync(c->d_level_iters, 0, sizeof(int32_t) * kMaxLevels, c->stream));
     CK(cudaMemsetAsync(c->d_active_particles, 0, 2 * sizeof(unsigned long long), c->stream));
     // the previous call's speculative passes may still be writing status words: drain first
@@ -640,6 +787,29 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaMemset(c->d_peer_flag, 0, sizeof(uint32_t) * 2 * orb::kMaxPeers * orb::kPeerMaxBlocks));
     CK(cudaMalloc(&c->d_lvl_passes, sizeof(int32_t) * kMaxLevels));
     CK(cudaMalloc(&c->d_lvl_unfound, sizeof(uint32_t) * kMaxLevels));
+    {
+        c->selHistWords = (size_t)n_local / 64 + 2 * (size_t)orb::kSelBinsMax;
+        CK(cudaMalloc(&c->sel.hist, c->selHistWords * 4));
+        CK(cudaMalloc(&c->sel.bfirst, L * 4));
+        CK(cudaMalloc(&c->sel.blast, L * 4));
+        CK(cudaMalloc(&c->sel.base, L * 4));
+        CK(cudaMalloc(&c->sel.ncand, L * 4));
+        CK(cudaMalloc(&c->sel.cursor, L * 4));
+        CK(cudaMalloc(&c->sel.flag, L * 4));
+        CK(cudaMemset(c->sel.flag, 0, L * 4));
+        CK(cudaMemset(c->sel.cursor, 0, L * 4));
+        CK(cudaMalloc(&c->d_sel_nflag, sizeof(uint32_t) * kMaxLevels));
+        CK(cudaMemset(c->d_sel_nflag, 0, sizeof(uint32_t) * kMaxLevels));
+        const int ringBytes = orb::kCountStages * orb::kCountTile * (int)sizeof(float);
+        const int histBytes = ringBytes + orb::kSelBinsMax * 4 /* >= nb1 * rep * 4 for every level */, compBytes = ringBytes + orb::kWarps * orb::kSelWarpStage * 4 + orb::kSelBinsMax * 4;
+        CK(cudaFuncSetAttribute(orb::k_sel_stream<orb::kSelHist>, cudaFuncAttributeMaxDynamicSharedMemorySize, histBytes));
+        CK(cudaFuncSetAttribute(orb::k_sel_stream<orb::kSelCompact>, cudaFuncAttributeMaxDynamicSharedMemorySize, compBytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occSelStream[0], orb::k_sel_stream<orb::kSelHist>, orb::kThreads, histBytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occSelStream[1], orb::k_sel_stream<orb::kSelCompact>, orb::kThreads, compBytes));
+        const int searchBytes = (int)orb::sel_search_smem_bytes(kSelValsCap);
+        CK(cudaFuncSetAttribute(orb::k_sel_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
+        CK(cudaFuncSetAttribute(orb::k_sel_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
+    }
     CK(cudaMalloc(&c->d_misc, 64));
     CK(cudaMalloc(&c->d_active_particles, 16));
     CK(cudaMalloc(&c->d_level_iters, sizeof(int32_t) * kMaxLevels));
@@ -689,6 +859,8 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
             CK(cudaMemset(c->d_dbg_blocks, 0, bytes));
         }
     }
+    const char *se = getenv("ORB_SELECT");
+    if (se) c->select = atoi(se) != 0;
     const char *smt = getenv("ORB_STREAM_MIN_TILES");
     if (smt && atoi(smt) >= 1) c->streamMinTiles = atoi(smt);
     const char *pe = getenv("ORB_PERSIST");
@@ -717,6 +889,8 @@ int orb_destroy(orb_ctx *c) {
     cudaFree(c->lv.compL); cudaFree(c->lv.compR); cudaFree(c->lv.base_l); cudaFree(c->lv.tile_ncand);
     if (c->d_cnt_g_buf) cudaFree(c->d_cnt_g_buf);
     cudaFree(c->d_dbg); cudaFree(c->d_dbg_blocks);
+    cudaFree(c->sel.hist); cudaFree(c->sel.bfirst); cudaFree(c->sel.blast); cudaFree(c->sel.base); cudaFree(c->sel.ncand);
+    cudaFree(c->sel.cursor); cudaFree(c->sel.flag); cudaFree(c->d_sel_nflag);
     for (int r = 0; r < orb::kMaxPeers; ++r)
         if (c->peerIpc[r]) { cudaIpcCloseMemHandle(c->peerCnt[r]); cudaIpcCloseMemHandle(c->peerFlag[r]); }
     cudaFree(c->d_lvl_passes); cudaFree(c->d_lvl_unfound); cudaFree(c->d_cdone); cudaFree(c->d_peer_cnt); cudaFree(c->d_peer_flag);
@@ -1073,6 +1247,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
     int rc = reset_pass_ctl(c);
     if (rc) return rc;
     c->evCountUsed = c->evPartUsed = 0;
+    c->evAuxUsed = 0;
     const uint64_t l0 = c->nCountLaunch, l1 = c->nUpdateLaunch, l2 = c->nPartLaunch, l3 = c->nOtherLaunch;
 
     // root cell: orbit.cpp:45-46,74-76
@@ -1111,7 +1286,11 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         if (rc) return rc;
         int np = 0;
         uint32_t nu = 0;
-        if (level_can_persist(c, nCells, M)) {
+        if (level_can_select(c, nCells, M)) {
+            rc = launch_level_select(c, nCells, slot, l - 1);
+            if (rc) return rc;
+            np = -1;
+        } else if (level_can_persist(c, nCells, M)) {
             // host-free: the whole loop (and the extra count of capped cells) is one cooperative launch;
             // passes / unfound are read back with the other statistics after the build
             rc = launch_level_persistent(c, nCells, M, slot, l - 1);
@@ -1174,6 +1353,30 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             fprintf(stderr, "\n");
         }
         cudaMemset(c->d_dbg, 0, sizeof(unsigned long long) * 64 * kMaxLevels);
+    }
+    if (getenv("ORB_DEBUG_SELECT") && c->profile) {
+        for (size_t i = 0; i < c->evCountUsed; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->evCount[i].first, c->evCount[i].second);
+            fprintf(stderr, "count[%zu] %.1f us\n", i, ms * 1e3);
+        }
+        for (size_t i = 0; i < c->evAuxUsed; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->evAux[i].e0, c->evAux[i].e1);
+            fprintf(stderr, "aux L%d %s %.1f us\n", c->evAux[i].level + 1, c->evAux[i].label, ms * 1e3);
+        }
+        for (size_t i = 0; i < c->evPartUsed; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->evPart[i].first, c->evPart[i].second);
+            fprintf(stderr, "part[%zu] %.1f us\n", i, ms * 1e3);
+        }
+    }
+    if (getenv("ORB_DEBUG_SELECT")) {
+        uint32_t nf[kMaxLevels];
+        cudaMemcpy(nf, c->d_sel_nflag, sizeof(nf), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "select: cells left to the iterative search per level:");
+        for (int l = 0; l < nDone; ++l) fprintf(stderr, " %u", nf[l]);
+        fprintf(stderr, "\n");
     }
     if (c->d_dbg_blocks) {
         // raw dump for offline analysis: per level u32 level, u32 grid, then [kDbgPasses][grid][4] u64 stamps

@@ -907,6 +907,8 @@ struct LevelCtl {
     int compaction;                         // 1: full, compact, then candidate passes
     unsigned long long *dbg;                // optional (ORB_DEBUG_TIMES): globaltimer stamps of block 0, 5 per pass
     unsigned long long *dbg_blocks;         // optional (ORB_DEBUG_TIMES=2): [pass][block][4] start, classified, streamed, flushed
+    const uint32_t *gate;                   // optional: the launch does nothing when *gate == 0 (fallback of the selection search)
+    const uint32_t *only;                   // optional [nCells]: with `gate`, the cells this launch is responsible for
 };
 
 template <int M>
@@ -925,6 +927,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_level_persistent(const float *_
     float4 *ring = reinterpret_cast<float4 *>(count_smem);
     unsigned int gen = 0;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    if (lc.gate && __ldcg(lc.gate) == 0u) return;   // grid-uniform
 
     int pass = 0;
     for (; pass < maxPasses; ++pass) {
@@ -987,6 +990,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_level_persistent(const float *_
     if (pass >= maxPasses) {
         uint32_t need = 0;
         for (uint32_t c = gtid; c < nCells; c += gsize) {
+            if (lc.only && !lc.only[c]) continue;   // finished by the selection search (its capped cells are counted)
             const uint32_t nf = lv.found[c] ? 0u : 1u;
             lv.active[c] = nf;
             if (nf) {
@@ -1011,7 +1015,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_level_persistent(const float *_
                 }
         }
     }
-    if (gtid == 0) *lc.passes_out = pass;
+    if (gtid == 0) atomicAdd(lc.passes_out, pass);
 }
 
 // ---- regime B: cells of at most a few tiles.  One group of G threads per cell (G = 256: block, G = 32: warp);

@@ -1,0 +1,696 @@
+// orb_select.cuh — selection-based cut search (byte-reducing search that keeps the cut sequence).
+//
+// The reference finds each cell's cut with up to 32 bisection steps, every step one count `#{x < cut}` over the cell
+// (orbit.cpp:146-232, countLeft.cpp:9-42).  A step uses the count only through
+//     diff = (int)((float)cnt - (float)n * ratio)          (orbit.cpp:204-205)
+// which is monotone in cnt.  So the whole loop can be replayed without re-reading the particles:
+//   1. HIST     one pass over the cut-axis column bins every particle with a monotone function of its coordinate
+//               (`sel_bin`); the prefix sums bracket `#{x < cut}` for ANY cut by the bin the cut itself falls in;
+//   2. RESOLVE  (inside the COMPACT pass, by every block as it enters a cell) per cell, the bins whose count range can still contain |diff| < 3 or flip the sign of diff are the
+//               candidate bins [first, last] (normally one bin); every cut outside them is decided by the prefix sums;
+//   3. COMPACT  a second pass gathers the particles of the candidate bins into a dense per-cell list (in the idle
+//               ping-pong column);
+//   4. FINISH   one block per cell stages the candidates in shared memory, refines once more with a 2048-bin
+//               histogram, keeps the few still-ambiguous values and replays the reference's float decisions for all
+//               (up to 32) steps with exact counts  base + #{ambiguous < cut}.
+// Cells that fit in shared memory (deep levels) skip 1-3: one block reads the cell once and runs step 4 on it.
+// Result (margins, iterations, foundCut, nLeft) is bit-identical to the literal loop; tests/test_select_model.py
+// restates the algorithm in numpy and checks it against the literal loop, tests/test_gpu_parity.py checks this file
+// against the oracle.  Cells the method cannot finish (candidates beyond shared memory because of massive ties, a
+// capped cell whose final cut leaves the candidate bins) are flagged and left untouched for the iterative path
+// (k_level_persistent / k_count_*), which then runs for them alone.  Single rank only: with several ranks the
+// histograms and candidates would have to be exchanged; the multi-GPU path keeps the iterative search.
+#pragma once
+#include "orb_kernels.cuh"
+
+namespace orb {
+
+constexpr int kSelBinsMin = 512;      // bins per cell of the HIST pass (power of two, chosen per level from the cell size)
+constexpr int kSelBinsMax = 8192;
+constexpr int kSelBins2 = 2048;       // bins of the in-block refinement
+constexpr int kSelAmbCap = 2048;      // ambiguous values kept for the replay
+constexpr int kSelWarpStage = 640;    // COMPACT: staging slots per warp (a tile adds at most 512 per warp)
+constexpr int kSelHist = 0, kSelCompact = 1;
+
+struct SelState {
+    uint32_t *hist;       // [nCells][nb1] bin counts of the HIST pass (zeroed per level)
+    uint32_t *bfirst;     // [nCells] candidate bins [bfirst, blast]; bfirst > blast: nothing to gather
+    uint32_t *blast;
+    uint32_t *base;       // [nCells] particles in bins below bfirst
+    uint32_t *ncand;      // [nCells] particles in the candidate bins
+    uint32_t *cursor;     // [nCells] COMPACT: fill level of the cell's candidate list; FINISH leaves it zero
+    uint32_t *flag;       // [nCells] 1: left to the iterative path
+    uint32_t *n_flagged;  // this level's count of flagged cells (gate of the iterative fallback)
+};
+
+struct SelCtl {           // statistics of the level (same meaning as PassCtl / LevelCtl)
+    unsigned long long *active_particles;
+    int32_t *level_iters;
+    int32_t *passes_out;
+    uint32_t *n_unfound_out;
+};
+
+// scale of the bin function over [L, R): nb / (R - L), or 0 (everything in bin 0) for an empty or non-finite box
+__device__ __forceinline__ float sel_scale(float L, float R, int nb) {
+    const float inf = __int_as_float(0x7f800000);
+    const float w = __fsub_rn(R, L);
+    float s = (w > 0.f && w < inf) ? __fdiv_rn((float)nb, w) : 0.f;
+    if (!(s < inf)) s = 0.f;
+    return s;
+}
+// Bin of a coordinate.  The ONLY property the method needs is that this is monotone non-decreasing in x for every
+// float (sub, mul by a non-negative scale, clamp and truncation all are); NaN products (inf * 0) go to bin 0.
+__device__ __forceinline__ int sel_bin(float x, float lo, float scale, int nb) {
+    float t = __fmul_rn(__fsub_rn(x, lo), scale);
+    t = fminf(fmaxf(t, 0.f), (float)(nb - 1));
+    return __float2int_rz(t);
+}
+
+// the reference's decision value for a count (orbit.cpp:204-205), literal float arithmetic
+struct SelTarget {
+    float prod;
+    __device__ __forceinline__ void init(uint32_t total, int nleaf) {
+        const float ratio = (float)(ceil(nleaf / 2.0) / nleaf);
+        prod = __fmul_rn(__uint2float_rn(total), ratio);
+    }
+    __device__ __forceinline__ int diff(uint32_t cnt) const { return __float2int_rz(__fsub_rn(__uint2float_rn(cnt), prod)); }
+};
+
+// block-wide exclusive scan of one value per thread (any block size up to 1024); total in `total`
+__device__ __forceinline__ uint32_t sel_block_scan(uint32_t v, uint32_t *s_w /*[32]*/, uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = (int)(blockDim.x >> 5);
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    __syncthreads();                       // s_w may still be read from a previous call
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+    for (int w = 0; w < nWarps; ++w) {
+        const uint32_t x = s_w[w];
+        if (w < warp) off += x;
+        tot += x;
+    }
+    total = tot;
+    return off + incl - v;
+}
+
+// append a thread's kept values (bit j of keep <-> v[j]) to its warp's staging region; *wN = fill level of the region
+template <int NV>
+__device__ __forceinline__ void sel_warp_append(const float (&v)[NV], unsigned keep, float *stageWarp, uint32_t *wN) {
+    const int lane = threadIdx.x & 31;
+    const unsigned any = __ballot_sync(0xffffffffu, keep != 0u);
+    if (!any) return;
+    const unsigned mine = __popc(keep);
+    unsigned incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const unsigned wtot = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t start = *wN;
+    float *dst = stageWarp + start + (incl - mine);
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+        if (keep & (1u << j)) dst[__popc(keep & ((1u << j) - 1u))] = v[j];
+    __syncwarp();
+    if (lane == 0) *wN = start + wtot;
+    __syncwarp();
+}
+
+// =====================================================================================
+// RESOLVE of one cell by one block of kThreads threads: prefix sums of the cell's histogram -> candidate bins
+// [first, last] (bins b with NOT(diff(P[b+1]) <= -3) ... diff(P[b]) < 3), base = P[first], ncand = P[last+1] - base.
+// Block-uniform call from the COMPACT pass when a block enters a cell (every block that touches the cell computes the
+// same result; the block holding the cell's first particle publishes it for FINISH).  `hbuf`: nb1 words of shared
+// memory.  Returns the candidate bins (first > last: nothing to gather, the cell is left to the iterative search).
+// =====================================================================================
+struct SelResolveSmem {
+    uint32_t w[32];
+    int first, last;
+    uint32_t base, end;
+};
+__device__ __forceinline__ void sel_resolve_cell(const LevelState &lv, const SelState &ss, uint32_t c, int nb1, uint32_t candCap,
+                                                 bool publish, uint32_t *hbuf, SelResolveSmem &rs, uint32_t &bfOut, uint32_t &blOut) {
+    const int tid = threadIdx.x;
+    const int per = nb1 / kThreads;          // 2 .. 32
+    __syncthreads();
+    if (tid == 0) { rs.first = nb1; rs.last = -1; rs.base = 0u; rs.end = 0u; }
+    SelTarget tg;
+    tg.init(lv.total[c], lv.nleaf[c]);
+    const uint32_t *g = ss.hist + (size_t)c * nb1;
+    for (int i = tid; i < nb1; i += kThreads) hbuf[i] = __ldcg(g + i);      // coalesced, one latency
+    __syncthreads();
+    const uint32_t *h = hbuf + tid * per;
+    uint32_t sum = 0;
+    for (int j = 0; j < per; ++j) sum += h[j];
+    uint32_t total;
+    const uint32_t excl = sel_block_scan(sum, rs.w, total);
+    int myFirst = nb1, myLast = -1;
+    uint32_t p = excl;
+    for (int j = 0; j < per; ++j) {
+        const uint32_t pn = p + h[j];
+        const int b = tid * per + j;
+        if (tg.diff(pn) > -3) myFirst = min(myFirst, b);
+        if (tg.diff(p) < 3) myLast = max(myLast, b);
+        p = pn;
+    }
+    if (myFirst < nb1) atomicMin(&rs.first, myFirst);
+    if (myLast >= 0) atomicMax(&rs.last, myLast);
+    __syncthreads();
+    const int bf = rs.first, bl = rs.last;
+    p = excl;
+    for (int j = 0; j < per; ++j) {
+        const int b = tid * per + j;
+        if (b == bf) rs.base = p;
+        p += h[j];
+        if (b == bl) rs.end = p;
+    }
+    __syncthreads();
+    // bf <= bl always (tests/test_select_model.py::ambiguous_range); guarded anyway.  More candidates than one block
+    // can stage: the cell is left to the iterative search.
+    const bool ok = bf <= bl && bf < nb1 && bl >= 0 && (rs.end - rs.base) <= candCap;
+    bfOut = ok ? (uint32_t)bf : 1u;
+    blOut = ok ? (uint32_t)bl : 0u;
+    if (publish && tid == 0) {
+        ss.bfirst[c] = bfOut; ss.blast[c] = blOut;
+        ss.base[c] = ok ? rs.base : 0u;
+        ss.ncand[c] = ok ? rs.end - rs.base : 0u;
+        ss.flag[c] = ok ? 0u : 1u;
+        if (!ok) atomicAdd(ss.n_flagged, 1u);
+    }
+    __syncthreads();
+}
+
+// =====================================================================================
+// HIST / COMPACT: one streaming pass over the tiles of the level (same tile ownership, classification and cp.async
+// ring as stream_count_pass).  HIST keeps `rep` copies of the block's histogram (copy = lane mod rep) to thin out
+// shared-memory bank conflicts; COMPACT tests bin membership on the un-truncated bin coordinate.
+// =====================================================================================
+struct SelStreamSmem {
+    uint32_t uTile[kMaxUnits], uCell[kMaxUnits];
+    int uAx[kMaxUnits];
+    float uLo[kMaxUnits], uScale[kMaxUnits];
+    uint32_t fTile[kMaxUnits], fCell[kMaxUnits];
+    uint32_t wS[kWarps], wF[kWarps];
+    uint32_t wN[kWarps];                          // COMPACT: staged candidates per warp
+    uint32_t gbase;
+    SelResolveSmem rs;
+};
+
+// bounds on t = max((x - lo) * scale, 0) equivalent to first <= sel_bin(x) <= last (bins are integers <= nb - 1)
+__device__ __forceinline__ void sel_bin_bounds(uint32_t first, uint32_t last, int nb, float &fLo, float &fHi) {
+    fLo = (float)first;
+    fHi = (last + 1u >= (uint32_t)nb) ? __int_as_float(0x7f800000) : (float)(last + 1u);
+    if (first > last) { fLo = 1.f; fHi = 0.f; }     // empty
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, MODE == kSelHist ? 4 : 3)
+k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z, float *__restrict__ cand,
+             LevelState lv, SelState ss, const uint32_t *__restrict__ tile_first, uint32_t nCells, uint32_t nLocal,
+             uint32_t nTiles, int nb1, int rep, uint32_t candCap, unsigned long long *dbg) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    unsigned long long *bs = dbg ? dbg + (size_t)blockIdx.x * 4 : nullptr;      // ORB_DEBUG_TIMES=2: per-block phase stamps
+    if (bs && threadIdx.x == 0) bs[0] = gtimer();
+    // dynamic: ring (kCountStages x 16 KB) | HIST: hist[nb1][rep]  /  COMPACT: stage[kWarps][kSelWarpStage] | hbuf[nb1]
+    float4 *ring = reinterpret_cast<float4 *>(sel_smem);
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(sel_smem + (size_t)kCountStages * kCountTile * sizeof(float));
+    float *s_stage = reinterpret_cast<float *>(s_hist);
+    uint32_t *s_hbuf = s_hist + kWarps * kSelWarpStage;
+    __shared__ SelStreamSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int repSel = lane & (rep - 1);
+
+    if (MODE == kSelHist) for (int i = tid; i < nb1 * rep; i += kThreads) s_hist[i] = 0u;
+    if (MODE == kSelCompact && tid < kWarps) sm.wN[tid] = 0u;
+    __syncthreads();
+
+    // block b owns the contiguous tiles [tb0, tb1)
+    const uint32_t tilesPerBlock = (nTiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t tb0 = min(blockIdx.x * tilesPerBlock, nTiles), tb1 = min(tb0 + tilesPerBlock, nTiles);
+    int cur = -1;
+    float lo = 0.f, scale = 0.f, fLo = 1.f, fHi = 0.f;
+    const float nbm1 = (float)(nb1 - 1);
+
+    // ---- flush of the per-cell block state (block-uniform) ----
+    auto flush = [&]() {
+        if (cur < 0) return;
+        __syncthreads();
+        if (MODE == kSelHist) {
+            for (int b = tid; b < nb1; b += kThreads) {
+                uint32_t v = 0;
+                for (int r = 0; r < rep; ++r) { v += s_hist[b * rep + r]; s_hist[b * rep + r] = 0u; }
+                if (v) atomicAdd(&ss.hist[(size_t)cur * nb1 + b], v);
+            }
+        } else {
+            uint32_t tot = 0, off = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) { const uint32_t n = sm.wN[w]; if (w < warp) off += n; tot += n; }
+            if (tot) {
+                if (tid == 0) sm.gbase = atomicAdd(&ss.cursor[cur], tot);
+                __syncthreads();
+                float *dst = cand + lv.bnd[cur] + sm.gbase + off;
+                const uint32_t n = sm.wN[warp];
+                for (uint32_t i = lane; i < n; i += 32u) dst[i] = s_stage[warp * kSelWarpStage + i];
+            }
+            __syncthreads();
+            if (tid < kWarps) sm.wN[tid] = 0u;
+        }
+        __syncthreads();
+    };
+    // a warp's staging region is nearly full (massive ties): write it out on its own
+    auto warp_spill = [&]() {
+        const uint32_t n = sm.wN[warp];
+        if (n + 512u <= (uint32_t)kSelWarpStage) return;
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(&ss.cursor[cur], n);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        float *dst = cand + lv.bnd[cur] + g;
+        for (uint32_t i = lane; i < n; i += 32u) dst[i] = s_stage[warp * kSelWarpStage + i];
+        __syncwarp();
+        if (lane == 0) sm.wN[warp] = 0u;
+        __syncwarp();
+    };
+    auto enter_cell = [&](uint32_t c, float cLo, float cScale) {   // block-uniform
+        if ((int)c == cur) return;
+        flush();
+        cur = (int)c; lo = cLo; scale = cScale;
+        if (MODE == kSelCompact) {
+            // resolve the cell's candidate bins from its (complete) histogram; the block that holds the cell's first
+            // particle publishes the result for FINISH
+            const uint32_t cb = lv.bnd[c];
+            const bool publish = cb >= tb0 * (uint32_t)kCountTile && cb < tb1 * (uint32_t)kCountTile;
+            uint32_t bf, bl;
+            sel_resolve_cell(lv, ss, c, nb1, candCap, publish, s_hbuf, sm.rs, bf, bl);
+            sel_bin_bounds(bf, bl, nb1, fLo, fHi);
+        }
+    };
+    // bin coordinate: max((x - lo) * scale, 0); NaN (inf * 0) -> 0
+    auto coord = [&](float v) { return fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f); };
+
+
+    for (uint32_t base = tb0; base < tb1; base += (uint32_t)kMaxUnits) {
+        // ---- phase 1: classify up to kMaxUnits tiles ----
+        const uint32_t t = base + (uint32_t)tid;
+        int kind = 0;   // 0 skip, 1 stream, 2 fragmented
+        uint32_t c = 0;
+        if (tid < kMaxUnits && t < tb1) {
+            const uint32_t t0 = t * (uint32_t)kCountTile, t1 = min(t0 + (uint32_t)kCountTile, nLocal);
+            c = tile_first[t * (kCountTile / kMapTile)];
+            const uint32_t cb = lv.bnd[c], ce = lv.bnd[c + 1];
+            if (cb <= t0 && ce >= t1 && (t1 - t0) == (uint32_t)kCountTile) {
+                kind = lv.active[c] ? 1 : 0;
+            } else kind = 2;
+        }
+        const unsigned mS = __ballot_sync(0xffffffffu, kind == 1), mF = __ballot_sync(0xffffffffu, kind == 2);
+        __syncthreads();
+        if (lane == 0) { sm.wS[warp] = __popc(mS); sm.wF[warp] = __popc(mF); }
+        __syncthreads();
+        uint32_t offS = 0, offF = 0, nS = 0, nF = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            if (w < warp) { offS += sm.wS[w]; offF += sm.wF[w]; }
+            nS += sm.wS[w]; nF += sm.wF[w];
+        }
+        const unsigned ltMask = (1u << lane) - 1u;
+        if (kind == 1) {
+            const uint32_t r = offS + __popc(mS & ltMask);
+            sm.uTile[r] = t; sm.uCell[r] = c; sm.uAx[r] = lv.axis[c];
+            const float L = lv.mL[c], R = lv.mR[c];
+            sm.uLo[r] = L; sm.uScale[r] = sel_scale(L, R, nb1);
+        }
+        if (kind == 2) { const uint32_t r = offF + __popc(mF & ltMask); sm.fTile[r] = t; sm.fCell[r] = c; }
+        __syncthreads();
+        if (bs && tid == 0 && base == tb0) bs[1] = gtimer();
+
+        // tiles holding cell boundaries (or the array tail): per cell segment, plain loads.  Processed in tile order
+        // between the streamed tiles, so the block changes cell (and flushes) once per cell it touches.
+        auto process_frag = [&](uint32_t k) {
+            const uint32_t tt = sm.fTile[k];
+            const uint32_t t0 = tt * (uint32_t)kCountTile, t1 = min(t0 + (uint32_t)kCountTile, nLocal);
+            for (uint32_t cc = sm.fCell[k]; cc < nCells; ++cc) {
+                const uint32_t cb = lv.bnd[cc], ce = lv.bnd[cc + 1];
+                if (cb >= t1) break;
+                const uint32_t s0 = max(cb, t0), s1 = min(ce, t1);
+                const bool use = s1 > s0 && lv.active[cc] != 0u;
+                if (use) {
+                    const float L = lv.mL[cc], R = lv.mR[cc];
+                    enter_cell(cc, L, sel_scale(L, R, nb1));
+                    // a segment is at most one tile: every thread loads its (up to) 16 elements before using any
+                    const float *col = pick_col(lv.axis[cc], x, y, z);
+                    float v[16];
+                    unsigned inMask = 0u;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t i = s0 + (uint32_t)tid + (uint32_t)j * kThreads;
+                        const bool in = i < s1;
+                        v[j] = in ? __ldg(col + i) : 0.f;
+                        inMask |= (unsigned)in << j;
+                    }
+                    if (MODE == kSelHist) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (inMask & (1u << j)) atomicAdd(&s_hist[__float2int_rz(fminf(coord(v[j]), nbm1)) * rep + repSel], 1u);
+                    } else {
+                        unsigned keep = 0u;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float tc = coord(v[j]);
+                            keep |= (unsigned)(tc >= fLo && tc < fHi) << j;
+                        }
+                        keep &= inMask;
+                        warp_spill();
+                        sel_warp_append<16>(v, keep, s_stage + warp * kSelWarpStage, &sm.wN[warp]);
+                    }
+                }
+                if (ce >= t1) break;
+            }
+        };
+        uint32_t fi = 0;
+        // ---- phase 2a: whole tiles through the per-thread cp.async ring ----
+        if (nS) {
+            auto issue = [&](uint32_t k) {
+                const float4 *p = reinterpret_cast<const float4 *>(pick_col(sm.uAx[k], x, y, z) + sm.uTile[k] * (uint32_t)kCountTile) + tid;
+                float4 *dst = ring + (k % kCountStages) * (4 * kThreads) + tid;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cp_async16(dst + j * kThreads, p + j * kThreads);
+            };
+#pragma unroll
+            for (int pre = 0; pre < kCountStages - 1; ++pre) {
+                if ((uint32_t)pre < nS) issue(pre);
+                cp_async_commit();
+            }
+            for (uint32_t k = 0; k < nS; ++k) {
+                if (k + kCountStages - 1 < nS) issue(k + kCountStages - 1);
+                cp_async_commit();
+                cp_async_wait<kCountStages - 1>();
+                for (; fi < nF && sm.fTile[fi] < sm.uTile[k]; ++fi) process_frag(fi);
+                enter_cell(sm.uCell[k], sm.uLo[k], sm.uScale[k]);
+                const float4 *src = ring + (k % kCountStages) * (4 * kThreads) + tid;
+                const float4 q0 = src[0], q1 = src[kThreads], q2 = src[2 * kThreads], q3 = src[3 * kThreads];
+                const float v[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+                if (MODE == kSelHist) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int b = __float2int_rz(fminf(coord(v[j]), nbm1));      // == sel_bin(v[j], lo, scale, nb1)
+                        atomicAdd(&s_hist[b * rep + repSel], 1u);
+                    }
+                } else {
+                    unsigned keep = 0u;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float tc = coord(v[j]);
+                        keep |= (unsigned)(tc >= fLo && tc < fHi) << j;
+                    }
+                    warp_spill();
+                    sel_warp_append<16>(v, keep, s_stage + warp * kSelWarpStage, &sm.wN[warp]);
+                }
+            }
+            cp_async_wait<0>();
+        }
+        for (; fi < nF; ++fi) process_frag(fi);
+        __syncthreads();
+    }
+    if (bs && tid == 0) bs[2] = gtimer();
+    flush();
+    if (bs && tid == 0) bs[3] = gtimer();
+}
+
+// =====================================================================================
+// Block-level search on values staged in shared memory (step 4 above).  Block-uniform call, any block size that is a
+// multiple of 32 and divides 2048.
+// vals[K]: the candidates; `base`: particles of the cell known to be smaller than every candidate; `outer*`: the
+// HIST pass' bin function and candidate bins (hasOuter = 0 when vals is the whole cell).
+// Writes the cell's result (margins, iter, found, nleft) or flags it; nothing else is written for a flagged cell.
+// =====================================================================================
+struct SelSearchSmem {
+    float wmin[32], wmax[32];
+    uint32_t w[32];
+    int first, last;
+    uint32_t base2, end2, namb, finalCnt;
+    float lo2, scale2, cutf;
+    int needFinal;
+};
+
+__device__ __forceinline__ void sel_block_search(const float *vals, uint32_t K, uint32_t base, int hasOuter, float lo1,
+                                                 float scale1, int nb1, int bfirst, int blast, uint32_t *hist2, float *amb,
+                                                 const LevelState &lv, const SelState &ss, const SelCtl &sc, uint32_t c,
+                                                 int hbmPasses, SelSearchSmem &sm, unsigned long long *dbg = nullptr) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nThreads = (int)blockDim.x, nWarps = nThreads >> 5;
+    const float inf = __int_as_float(0x7f800000);
+    SelTarget tg;
+    tg.init(lv.total[c], lv.nleaf[c]);
+    const float L0 = lv.mL[c], R0 = lv.mR[c];
+    const int nb2 = K > 4096u ? kSelBins2 : max(256, nThreads);
+    const int per = nb2 / nThreads;          // 1, 2 or 8
+
+    // ---- range of the staged values: the candidate bins' interval when there is an outer histogram, else min / max
+    //      (any range gives a valid monotone bin function; a tight one just resolves better) ----
+    const bool fromBins = hasOuter && scale1 > 0.f;
+    float mn = inf, mx = -inf;
+    if (!fromBins) {
+        for (uint32_t i = tid; i < K; i += nThreads) { const float v = vals[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    }
+    __syncthreads();
+    if (lane == 0) { sm.wmin[warp] = mn; sm.wmax[warp] = mx; }
+    for (int i = tid; i < nb2; i += nThreads) hist2[i] = 0u;
+    __syncthreads();
+    if (tid == 0) {
+        float a = inf, b = -inf;
+        if (fromBins) {
+            a = __fadd_rn(lo1, __fdiv_rn((float)bfirst, scale1));
+            b = __fadd_rn(lo1, __fdiv_rn((float)(blast + 1), scale1));
+        } else {
+            for (int w = 0; w < nWarps; ++w) { a = fminf(a, sm.wmin[w]); b = fmaxf(b, sm.wmax[w]); }
+        }
+        if (K == 0u) { a = 0.f; b = 0.f; }
+        sm.lo2 = a; sm.scale2 = sel_scale(a, b, nb2);
+        sm.first = nb2; sm.last = -1; sm.base2 = 0u; sm.end2 = 0u; sm.namb = 0u; sm.finalCnt = 0u; sm.needFinal = 0; sm.cutf = 0.f;
+    }
+    __syncthreads();
+    const float lo2 = sm.lo2, scale2 = sm.scale2;
+    if (dbg && tid == 0) dbg[2] = gtimer();
+    for (uint32_t i = tid; i < K; i += nThreads) atomicAdd(&hist2[sel_bin(vals[i], lo2, scale2, nb2)], 1u);
+    __syncthreads();
+    if (dbg && tid == 0) dbg[3] = gtimer();
+
+    // ---- prefix sums, ambiguous bins [first, last] ----
+    uint32_t h[8];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { h[j] = (j < per) ? hist2[tid * per + j] : 0u; sum += h[j]; }
+    uint32_t total;
+    const uint32_t excl = sel_block_scan(sum, sm.w, total);
+    int myFirst = nb2, myLast = -1;
+    {
+        uint32_t p = base + excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < per) {
+                const uint32_t pn = p + h[j];
+                const int b = tid * per + j;
+                if (tg.diff(pn) > -3) myFirst = min(myFirst, b);
+                if (tg.diff(p) < 3) myLast = max(myLast, b);
+                p = pn;
+            }
+        }
+    }
+    if (myFirst < nb2) atomicMin(&sm.first, myFirst);
+    if (myLast >= 0) atomicMax(&sm.last, myLast);
+    __syncthreads();
+    const int first = sm.first, last = sm.last;
+    {
+        uint32_t p = base + excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < per) {
+                const int b = tid * per + j;
+                if (b == first) sm.base2 = p;
+                p += h[j];
+                if (b == last) sm.end2 = p;
+            }
+        }
+    }
+    __syncthreads();
+    if (dbg && tid == 0) dbg[4] = gtimer();
+    const uint32_t base2 = sm.base2;
+    const uint32_t K2 = sm.end2 - base2;
+    const bool tooMany = !(first <= last) || K2 > (uint32_t)kSelAmbCap;
+    if (tooMany) {   // massive ties: leave the cell to the iterative path
+        if (tid == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
+        return;
+    }
+    for (uint32_t i = tid; i < K; i += nThreads) {
+        const float v = vals[i];
+        const int b = sel_bin(v, lo2, scale2, nb2);
+        if (b >= first && b <= last) amb[atomicAdd(&sm.namb, 1u)] = v;
+    }
+    __syncthreads();
+
+    if (dbg && tid == 0) dbg[5] = gtimer();
+    // ---- replay of orbit.cpp:149-232 by warp 0 (every lane computes the same scalars) ----
+    float L = L0, R = R0;
+    int it = 0;
+    bool fnd = false;
+    uint32_t nleft = 0;
+    if (warp == 0) {
+        while (it < kMaxIter) {
+            const float cut = mid_cut(L, R);
+            int dec = 0;
+            if (hasOuter) {
+                const int b1 = sel_bin(cut, lo1, scale1, nb1);
+                dec = b1 < bfirst ? -1 : (b1 > blast ? 1 : 0);
+            }
+            if (dec == 0) {
+                const int b2 = sel_bin(cut, lo2, scale2, nb2);
+                dec = b2 < first ? -1 : (b2 > last ? 1 : 0);
+            }
+            ++it;
+            if (dec == 0) {
+                uint32_t n = 0;
+                for (uint32_t i = lane; i < K2; i += 32u) n += (amb[i] < cut) ? 1u : 0u;
+                n = __reduce_add_sync(0xffffffffu, n);
+                const uint32_t cnt = base2 + n;
+                const int d = tg.diff(cnt);
+                if (abs(d) < 3) { fnd = true; nleft = cnt; break; }       // orbit.cpp:208
+                dec = d > 0 ? 1 : -1;
+            }
+            if (dec > 0) R = cut; else L = cut;                            // orbit.cpp:219,227
+        }
+        if (!fnd && lane == 0) {
+            // capped cell: the count at getCut() of the last margins is needed for the partition
+            const float cutf = mid_cut(L, R);
+            int ok = 1;
+            if (hasOuter) { const int b1 = sel_bin(cutf, lo1, scale1, nb1); ok = (b1 >= bfirst && b1 <= blast) ? 1 : 0; }
+            sm.cutf = cutf;
+            sm.needFinal = ok ? 1 : 2;
+        }
+    }
+    __syncthreads();
+    if (dbg && tid == 0) dbg[6] = gtimer();
+    const int needFinal = sm.needFinal;
+    if (needFinal == 2) {   // final cut outside the candidate bins: its exact count is not known here
+        if (tid == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
+        return;
+    }
+    if (needFinal == 1) {
+        const float cutf = sm.cutf;
+        uint32_t n = 0;
+        for (uint32_t i = tid; i < K; i += nThreads) n += (vals[i] < cutf) ? 1u : 0u;
+        n = __reduce_add_sync(0xffffffffu, n);
+        if (lane == 0 && n) atomicAdd(&sm.finalCnt, n);
+        __syncthreads();
+        nleft = base + sm.finalCnt;
+    }
+    if (tid == 0) {
+        lv.mL[c] = L; lv.mR[c] = R; lv.iter[c] = it;
+        lv.found[c] = fnd ? 1u : 0u;
+        lv.active[c] = 0u;
+        lv.nleft_g[c] = nleft;
+        lv.nleft_l[c] = nleft;
+        const unsigned long long np = (unsigned long long)(lv.bnd[c + 1] - lv.bnd[c]);
+        if (np) {
+            atomicAdd(sc.active_particles, np * (unsigned long long)hbmPasses);
+            atomicAdd(sc.active_particles + 1, np * (unsigned long long)it);
+        }
+        atomicMax(sc.level_iters, it);
+        if (!fnd) atomicAdd(sc.n_unfound_out, 1u);
+    }
+}
+
+// dynamic shared memory of the two search kernels: vals[cap + 4] | hist2[kSelBins2] | amb[kSelAmbCap]
+__host__ __device__ inline size_t sel_search_smem_bytes(uint32_t cap) { return ((size_t)cap + 4u + kSelBins2 + kSelAmbCap) * 4u; }
+
+// Stage src[0..K) in shared memory with 16-byte asynchronous copies (every thread keeps all its copies in flight, so
+// one block can pull a whole cell at memory speed).  src is only 4-byte aligned: the staged array starts `mis` floats
+// into sbuf so that shared and global addresses are congruent mod 16; head and tail go through scalar loads.
+// Returns the staged array (vals[i] <-> src[i]).  Ends with a block barrier.
+__device__ __forceinline__ float *sel_stage_vals(float *sbuf, const float *__restrict__ src, uint32_t K) {
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
+    float *vals = sbuf + mis;
+    const uint32_t head = mis ? min(4u - mis, K) : 0u;
+    const uint32_t body4 = (K - head) / 4u;
+    const float4 *g4 = reinterpret_cast<const float4 *>(src + head);
+    float4 *s4 = reinterpret_cast<float4 *>(vals + head);
+    for (uint32_t i = threadIdx.x; i < body4; i += blockDim.x) cp_async16(s4 + i, g4 + i);
+    cp_async_commit();
+    if (threadIdx.x < head) vals[threadIdx.x] = __ldcg(src + threadIdx.x);
+    const uint32_t tail0 = head + body4 * 4u;
+    if (tail0 + threadIdx.x < K) vals[tail0 + threadIdx.x] = __ldcg(src + tail0 + threadIdx.x);
+    cp_async_wait<0>();
+    __syncthreads();
+    return vals;
+}
+
+// FINISH (streaming regime): one block per cell, candidates from the dense list written by COMPACT
+__global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ cand, LevelState lv, SelState ss, SelCtl sc,
+                                                     uint32_t nCells, int nb1, uint32_t cap, int *__restrict__ err,
+                                                     unsigned long long *dbg) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    float *sbuf = reinterpret_cast<float *>(sel_smem);
+    uint32_t *hist2 = reinterpret_cast<uint32_t *>(sbuf + cap + 4);
+    float *amb = reinterpret_cast<float *>(hist2 + kSelBins2);
+    __shared__ SelSearchSmem sm;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(sc.passes_out, 2);
+    unsigned long long *bs = (dbg && blockIdx.x == 0) ? dbg : nullptr;    // ORB_DEBUG_TIMES=2: phases of block 0's first cell
+    if (bs && threadIdx.x == 0) bs[0] = gtimer();
+    for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
+        __syncthreads();
+        // independent loads of the cell's parameters, issued together
+        const uint32_t act = lv.active[c], b0 = lv.bnd[c], b1 = lv.bnd[c + 1];
+        const uint32_t flg = __ldcg(&ss.flag[c]), K = __ldcg(&ss.ncand[c]), cur = __ldcg(&ss.cursor[c]), bs_ = __ldcg(&ss.base[c]);
+        const uint32_t bf = __ldcg(&ss.bfirst[c]), bl = __ldcg(&ss.blast[c]);
+        const float L = lv.mL[c], R = lv.mR[c];
+        if (!act) continue;
+        if (b1 == b0) {     // empty cell: no block ever resolved it; the search on nothing finds the cut at once
+            if (threadIdx.x == 0) ss.flag[c] = 0u;
+            sel_block_search(sbuf, 0u, 0u, 0, 0.f, 0.f, 1, 0, 0, hist2, amb, lv, ss, sc, c, 2, sm);
+            continue;
+        }
+        if (flg) continue;
+        if (cur != K || K > cap) {   // cannot happen: HIST and COMPACT use the same bin function
+            if (threadIdx.x == 0) atomicExch(err, ORB_ERR_STATE);
+            continue;
+        }
+        const float *vals = sel_stage_vals(sbuf, cand + b0, K);
+        if (threadIdx.x == 0) ss.cursor[c] = 0u;      // zero between levels (HIST counts into it)
+        if (bs && threadIdx.x == 0) bs[1] = gtimer();
+        sel_block_search(vals, K, bs_, 1, L, sel_scale(L, R, nb1), nb1, (int)bf, (int)bl, hist2, amb, lv, ss, sc, c, 2, sm,
+                         c == blockIdx.x ? bs : nullptr);
+        if (bs && threadIdx.x == 0 && c == blockIdx.x) bs[7] = gtimer();
+    }
+}
+
+// Cells that fit in shared memory: one block reads the cell once and searches it (no HIST / COMPACT passes)
+__global__ void __launch_bounds__(1024) k_sel_cells(const float *__restrict__ x, const float *__restrict__ y,
+                                                    const float *__restrict__ z, LevelState lv, SelState ss, SelCtl sc,
+                                                    uint32_t nCells, uint32_t cap) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    float *sbuf = reinterpret_cast<float *>(sel_smem);
+    uint32_t *hist2 = reinterpret_cast<uint32_t *>(sbuf + cap + 4);
+    float *amb = reinterpret_cast<float *>(hist2 + kSelBins2);
+    __shared__ SelSearchSmem sm;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(sc.passes_out, 1);
+    for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
+        __syncthreads();
+        const uint32_t act = lv.active[c], b = lv.bnd[c], K = lv.bnd[c + 1] - b;
+        const int ax = lv.axis[c];
+        if (threadIdx.x == 0) ss.flag[c] = 0u;
+        if (!act) continue;
+        if (K > cap) {
+            if (threadIdx.x == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
+            continue;
+        }
+        const float *vals = sel_stage_vals(sbuf, pick_col(ax, x, y, z) + b, K);
+        sel_block_search(vals, K, 0u, 0, 0.f, 0.f, 1, 0, 0, hist2, amb, lv, ss, sc, c, 1, sm);
+    }
+}
+
+}  // namespace orb

@@ -1,0 +1,195 @@
+"""CPU model of the selection-based cut search (CUDA: csrc/orb_select.cuh).
+
+The reference bisects every cell with up to 32 count passes (orbit.cpp:146-232).  Each decision depends on the
+count `#{x < cut}` only through `diff = (int)((float)cnt - (float)n * ratio)`, which is monotone in cnt.  So one
+histogram over a monotone bin function brackets every count, the handful of particles whose bins can still flip a
+decision (the candidates) are gathered once, and the whole 32-step loop is replayed exactly on them: two reads of the
+cut-axis column per level instead of one per (multi-trial) bisection pass.
+
+This file restates that algorithm in numpy float32 and checks it against the literal loop on adversarial inputs
+(ties, clusters, signed zeros, denormals, particles outside the box, degenerate boxes).  The GPU implementation is
+checked against the oracle in tests/test_gpu_parity.py; this model pins the logic without a GPU."""
+import math
+
+import numpy as np
+import pytest
+
+f32 = np.float32
+MAX_ITER = 32
+
+
+def mid_cut(L, R):                      # Cell::getCut, cell.h:74-76
+    return f32(f32(R + L) * f32(0.5))
+
+
+def make_prod(total, nleaf):            # orbit.cpp:204
+    ratio = f32(math.ceil(nleaf / 2.0) / nleaf)
+    return f32(f32(total) * ratio)
+
+
+def diff_of(cnt, prod):                 # orbit.cpp:205: float subtraction, truncation to int
+    return int(np.trunc(f32(f32(cnt) - prod)))
+
+
+def literal_bisection(v, L, R, total, nleaf):
+    """orbit.cpp:149-232 for one cell; returns (L, R, iterations, found, nLeft)."""
+    prod = make_prod(total, nleaf)
+    it, found, nleft = 0, False, None
+    while it < MAX_ITER:
+        cut = mid_cut(L, R)
+        cnt = int(np.count_nonzero(v < cut))
+        d = diff_of(cnt, prod)
+        it += 1
+        if abs(d) < 3:
+            found, nleft = True, cnt
+            break
+        if d > 0:
+            R = cut
+        else:
+            L = cut
+    if not found:
+        nleft = int(np.count_nonzero(v < mid_cut(L, R)))
+    return L, R, it, found, nleft
+
+
+def bin_params(lo, hi, nb):
+    with np.errstate(all="ignore"):
+        w = f32(hi - lo)
+        scale = f32(nb) / w if (w > 0 and np.isfinite(w)) else f32(0)
+    if not np.isfinite(scale):
+        scale = f32(0)
+    return f32(lo), f32(scale)
+
+
+def sel_bin(x, lo, scale, nb):
+    """Monotone non-decreasing in x for every float (the only property the algorithm needs)."""
+    with np.errstate(all="ignore"):
+        t = (np.asarray(x, f32) - lo).astype(f32) * scale
+    t = np.where(np.isnan(t), f32(0), t)
+    t = np.minimum(np.maximum(t, f32(0)), f32(nb - 1))
+    return np.trunc(t).astype(np.int64)
+
+
+def ambiguous_range(prefix, base, prod):
+    """Bins whose count range can still hold |diff| < 3 or flip its sign: [first, last]."""
+    nb = len(prefix) - 1
+    first = next(b for b in range(nb) if diff_of(base + prefix[b + 1], prod) > -3)
+    last = next(b for b in range(nb - 1, -1, -1) if diff_of(base + prefix[b], prod) < 3)
+    assert first <= last
+    return first, last
+
+
+def select_bisection(v, L, R, total, nleaf, nb1=512, nb2=2048, amb_cap=2048, cand_cap=40960):
+    """Histogram -> candidates -> in-block histogram -> replay.  Returns the literal loop's tuple, or None when the
+    cell must fall back to the iterative path (too many candidates, or a final cut outside the candidate bins)."""
+    prod = make_prod(total, nleaf)
+    lo1, s1 = bin_params(L, R, nb1)
+    b = sel_bin(v, lo1, s1, nb1)
+    p1 = np.concatenate([[0], np.cumsum(np.bincount(b, minlength=nb1))])
+    f1, l1 = ambiguous_range(p1, 0, prod)
+    base = int(p1[f1])
+    cand = v[(b >= f1) & (b <= l1)]
+    if cand.size > cand_cap:
+        return None
+    # second histogram over the staged candidates
+    if cand.size:
+        lo2, s2 = bin_params(cand.min(), cand.max(), nb2)
+    else:
+        lo2, s2 = f32(0), f32(0)
+    b2 = sel_bin(cand, lo2, s2, nb2)
+    p2 = np.concatenate([[0], np.cumsum(np.bincount(b2, minlength=nb2))])
+    f2, l2 = ambiguous_range(p2, base, prod)
+    if p2[l2 + 1] - p2[f2] <= amb_cap:
+        amb, base2 = cand[(b2 >= f2) & (b2 <= l2)], base + int(p2[f2])
+    else:
+        amb, base2, f2, l2 = cand, base, 0, nb2 - 1
+    it, found, nleft = 0, False, None
+    while it < MAX_ITER:
+        cut = mid_cut(L, R)
+        c1 = int(sel_bin(cut, lo1, s1, nb1))
+        dec = -1 if c1 < f1 else (1 if c1 > l1 else 0)
+        if dec == 0:
+            c2 = int(sel_bin(cut, lo2, s2, nb2))
+            dec = -1 if c2 < f2 else (1 if c2 > l2 else 0)
+        it += 1
+        if dec == 0:
+            cnt = base2 + int(np.count_nonzero(amb < cut))
+            d = diff_of(cnt, prod)
+            if abs(d) < 3:
+                found, nleft = True, cnt
+                break
+            dec = 1 if d > 0 else -1
+        if dec > 0:
+            R = cut
+        else:
+            L = cut
+    if not found:
+        cut = mid_cut(L, R)
+        c1 = int(sel_bin(cut, lo1, s1, nb1))
+        if c1 < f1 or c1 > l1:
+            return None
+        nleft = base + int(np.count_nonzero(cand < cut))
+    return L, R, it, found, nleft
+
+
+def same(a, b):
+    return (np.float32(a[0]).tobytes(), np.float32(a[1]).tobytes(), a[2:]) == (np.float32(b[0]).tobytes(), np.float32(b[1]).tobytes(), b[2:])
+
+
+def cases():
+    rng = np.random.default_rng(5)
+    out = []
+    for n in (1, 2, 5, 6, 7, 100, 4097, 60_000, 300_000):
+        out.append((f"uniform{n}", (rng.random(n, dtype=f32) - f32(0.5)), f32(-0.5), f32(0.5), 8))
+    v = (rng.normal(0.2, 0.01, 200_000)).clip(-0.5, 0.5).astype(f32)
+    out.append(("cluster", v, f32(-0.5), f32(0.5), 16))
+    out.append(("cluster_odd_leaves", v, f32(-0.5), f32(0.5), 7))
+    t = rng.random(50_000, dtype=f32) - f32(0.5)
+    t[::3] = f32(0.125)                                   # a third of the particles tie on one value
+    out.append(("ties", t, f32(-0.5), f32(0.5), 4))
+    t2 = np.full(30_000, f32(0.25))
+    out.append(("all_equal", t2, f32(-0.5), f32(0.5), 2))
+    z = rng.random(20_000, dtype=f32) - f32(0.5)
+    z[:5000] = f32(0.0)
+    z[5000:9000] = f32(-0.0)
+    z[9000:9100] = f32(1e-42)
+    out.append(("signed_zero_denormal", z, f32(-0.5), f32(0.5), 2))
+    o = (rng.random(10_000, dtype=f32) * f32(3) - f32(1.5))
+    out.append(("outside_box", o, f32(-0.5), f32(0.5), 2))
+    out.append(("degenerate_box", rng.random(3000, dtype=f32), f32(0.3), f32(0.3), 2))
+    out.append(("narrow_box", (f32(0.3) + rng.random(5000, dtype=f32) * f32(1e-6)).astype(f32), f32(0.3), f32(0.3000011), 2))
+    big = rng.random(1 << 22, dtype=f32) - f32(0.5)       # float(cnt) granularity > 3 never happens below 2^24; still big
+    out.append(("big", big, f32(-0.5), f32(0.5), 4096))
+    sub = np.sort(rng.random(100_000, dtype=f32))[20_000:30_000] - f32(0.5)   # cell of a deeper level: narrow box
+    out.append(("deep_cell", sub, sub.min(), f32(np.nextafter(sub.max(), f32(1)))
+                , 3))
+    return out
+
+
+@pytest.mark.parametrize("name,v,L,R,nleaf", cases(), ids=[c[0] for c in cases()])
+def test_select_equals_literal_bisection(name, v, L, R, nleaf):
+    want = literal_bisection(v, L, R, v.size, nleaf)
+    got = select_bisection(v, L, R, v.size, nleaf)
+    if got is None:
+        assert name in ("all_equal", "degenerate_box", "ties", "narrow_box"), "unexpected fallback"
+        return
+    assert same(got, want), (got, want)
+
+
+def test_small_capacities_fall_back_or_agree():
+    """Tiny candidate / ambiguity caps exercise the brute-force and fallback branches."""
+    rng = np.random.default_rng(9)
+    v = rng.random(40_000, dtype=f32) - f32(0.5)
+    v[::7] = f32(-0.2)
+    want = literal_bisection(v, f32(-0.5), f32(0.5), v.size, 2)
+    got = select_bisection(v, f32(-0.5), f32(0.5), v.size, 2, nb1=16, nb2=32, amb_cap=4)
+    assert got is not None and same(got, want)
+    assert select_bisection(v, f32(-0.5), f32(0.5), v.size, 2, nb1=16, cand_cap=100) is None
+
+
+def test_global_total_larger_than_local():
+    """Multi-rank shape: the decision uses the global total, this rank only sees part of the counts.  The model is
+    single-rank (counts are global); here just the monotonicity the algorithm relies on."""
+    prod = make_prod(1 << 27, 2)
+    d = [diff_of(c, prod) for c in range((1 << 26) - 40, (1 << 26) + 40)]
+    assert all(a <= b for a, b in zip(d, d[1:]))
