@@ -64,6 +64,7 @@ class BuildStats(C.Structure):
         ("ms_count", C.c_float),
         ("ms_partition", C.c_float),
         ("ms_total", C.c_float),
+        ("search_fallback_cells", C.c_uint32),
     ]
 
     def as_dict(self):

@@ -1354,6 +1354,8 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         }
         cudaMemset(c->d_dbg, 0, sizeof(unsigned long long) * 64 * kMaxLevels);
     }
+    uint32_t selFlagged[kMaxLevels];
+    CK(cudaMemcpy(selFlagged, c->d_sel_nflag, sizeof(selFlagged), cudaMemcpyDeviceToHost));
     if (getenv("ORB_DEBUG_SELECT") && c->profile) {
         for (size_t i = 0; i < c->evCountUsed; ++i) {
             float ms = 0.f;
@@ -1414,6 +1416,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         float ms = 0.f;
         cudaEventElapsedTime(&ms, evA, evB);
         stats->ms_total = ms;
+        for (int l = 0; l < nDone; ++l) stats->search_fallback_cells += selFlagged[l];
         if (c->profile) {
             stats->ms_count = sum_events(c->evCount, c->evCountUsed);
             stats->ms_partition = sum_events(c->evPart, c->evPartUsed);

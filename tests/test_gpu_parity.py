@@ -1,5 +1,7 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
 inputs.  Integer / index / byte work => the bar is bit-exact everywhere."""
+import os
+
 import numpy as np
 import pytest
 
@@ -148,6 +150,56 @@ def test_signed_zero_coordinates(orb, oracle):
         assert np.array_equal(rng_, ref["ranges"][0])
         for a, b in ((gx, ref["x"]), (gy, ref["y"]), (gz, ref["z"])):
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,d", [(1 << 20, 8), (1 << 16, 32)])
+def test_search_fallback_on_massive_ties(orb, oracle, n, d):
+    """Thousands of particles tie exactly where the cut has to go: the selection-based search cannot isolate the
+    median (more ambiguous values than it keeps), flags those cells and the iterative bisection finishes them.
+    n = 2^20 exercises the streaming passes (HIST / COMPACT / FINISH), n = 2^16 the cell-in-shared-memory kernel."""
+    rng = np.random.default_rng(17)
+    cols = []
+    for a in range(3):
+        v = (rng.random(n, dtype=np.float32) - 0.5).astype(np.float32)
+        tie = rng.random(n) < 0.2                         # a fifth of the particles share one value near the median
+        v[tie] = np.float32(0.01 * (a + 1))
+        cols.append(v)
+    x, y, z = cols
+    ref = oracle.build(x, y, z, d, ties=oracle.TIES_CANONICAL, full_levels=True)
+    with orb.Orb(n, d) as ctx:
+        ctx.upload(x, y, z)
+        heap, st = ctx.build(full_levels=True)
+        gx, gy, gz = ctx.download()
+        rng_ = ctx.ranges()
+    assert st.search_fallback_cells > 0
+    assert list(st.iters[:st.n_levels]) == list(ref["stats"].iters[:st.n_levels])
+    assert list(st.not_found[:st.n_levels]) == list(ref["stats"].not_found[:st.n_levels])
+    assert heap.tobytes() == ref["heap"].tobytes()
+    assert np.array_equal(rng_, ref["ranges"][0])
+    for a, b in ((gx, ref["x"]), (gy, ref["y"]), (gz, ref["z"])):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_search_without_fallback_on_plain_inputs(orb, oracle):
+    """Uniform particles never need the iterative path; ORB_SELECT=0 (iterative search everywhere) gives the same tree."""
+    n, d = 1 << 19, 1 << 7
+    x, y, z = orb.generate_uniform(n)
+    ref = oracle.build(x, y, z, d, ties=oracle.TIES_CANONICAL)
+    with orb.Orb(n, d) as ctx:
+        ctx.upload(x, y, z)
+        heap, st = ctx.build()
+    assert st.search_fallback_cells == 0
+    assert list(st.passes[:st.n_levels]) == [2] * 3 + [1] * 3 or all(p <= 2 for p in st.passes[:st.n_levels])
+    assert heap.tobytes() == ref["heap"].tobytes()
+    os.environ["ORB_SELECT"] = "0"
+    try:
+        with orb.Orb(n, d) as ctx:
+            ctx.upload(x, y, z)
+            heap2, st2 = ctx.build()
+    finally:
+        del os.environ["ORB_SELECT"]
+    assert heap2.tobytes() == ref["heap"].tobytes()
+    assert max(st2.passes[:st2.n_levels]) > 2
 
 
 def test_degenerate_inputs(orb, oracle):
