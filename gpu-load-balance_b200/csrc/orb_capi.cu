@@ -138,6 +138,7 @@ struct orb_ctx {
     uint32_t *d_lvl_unfound = nullptr; // [kMaxLevels]
     // selection-based cut search (orb_select.cuh): single rank, default trial depth
     bool select = true;
+    bool pdl = true;               // programmatic dependent launch between the small kernels of a level
     orb::SelState sel{};
     size_t selHistWords = 0;
     uint32_t *d_sel_nflag = nullptr;   // [kMaxLevels] cells left to the iterative path per level
@@ -172,6 +173,23 @@ namespace {
 
 inline uint32_t ceil_div(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
+// Launch with programmatic dependent launch allowed (see pdl_enter in orb_kernels.cuh): the kernel may begin while
+// the previous kernel of the stream drains.  ORB_PDL=0 launches it as an ordinary kernel.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(const orb_ctx *c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = c->pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 int ensure_scratch(orb_ctx *c, size_t bytes) {
     if (c->h_scratch_bytes >= bytes) return ORB_OK;
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
@@ -195,20 +213,18 @@ int check_device_err(orb_ctx *c) {
 }
 
 // ---- level preparation: SoA state + tile map (ServiceCopyCells' role, copyCells.cu:29-61) ----
-int level_prepare(orb_ctx *c, const orb_cell *d_cells, uint32_t nCells, int nc, uint32_t *n_active0) {
+int level_prepare(orb_ctx *c, const orb_cell *d_cells, uint32_t nCells, int nc, uint32_t *n_active0, uint32_t *zero = nullptr,
+                  size_t nZero = 0) {
     using namespace orb;
     if (nCells == 0 || nCells > c->maxLevelCells) return fail(ORB_ERR_ARG, "n_cells %u out of range (max %u)", nCells, c->maxLevelCells);
     const uint32_t blocks = ceil_div(nCells, 256);
-    k_level_setup<<<blocks, 256, 0, c->stream>>>(d_cells, nCells, c->d_range, c->d_total, c->lv, (uint32_t)c->nLocal, nc, c->d_err);
+    CK(launch_pdl(c, k_level_setup, dim3(blocks), dim3(256), 0, d_cells, nCells, (const uint32_t *)c->d_range, (const uint32_t *)c->d_total, c->lv,
+                  (uint32_t)c->nLocal, nc, c->d_err, n_active0));
     c->nOtherLaunch++;
-    if (n_active0) {
-        // any non-zero value opens the gate of the first pass
-        static const uint32_t one = 1u;
-        CK(cudaMemcpyAsync(n_active0, &one, 4, cudaMemcpyHostToDevice, c->stream));
-    }
     const uint32_t nMap = ceil_div(c->nLocal, kMapTile);
     if (nMap) {
-        k_tile_map<<<ceil_div(nMap, 256), 256, 0, c->stream>>>(c->lv.bnd, nCells, nMap, c->d_tile_first);
+        CK(launch_pdl(c, k_tile_map, dim3(ceil_div(nMap, 256)), dim3(256), 0, (const uint32_t *)c->lv.bnd, nCells, nMap, c->d_tile_first,
+                      zero, nZero));
         c->nOtherLaunch++;
     }
     CK(cudaGetLastError());
@@ -473,6 +489,30 @@ int count_event_end(orb_ctx *c) {
     return ORB_OK;
 }
 
+// Shape of the selection search at a level: cells staged whole in shared memory, or HIST / COMPACT / FINISH with nb1
+// bins (rep copies per block) and room for candCap candidates per cell.
+struct SelPlan {
+    bool cellsInSmem;
+    uint32_t cellCap;     // cellsInSmem: values one block stages
+    int nb1, rep;
+    size_t histWords;     // nCells * nb1 (cleared by k_tile_map during level preparation)
+    uint32_t candCap;
+};
+SelPlan sel_plan(const orb_ctx *c, uint32_t nCells) {
+    SelPlan p{};
+    const uint64_t avg = c->nLocal / nCells;
+    const uint64_t cellCap = avg + avg / 8 + 256;
+    p.cellsInSmem = cellCap <= kSelValsCap;
+    p.cellCap = (uint32_t)std::min<uint64_t>(cellCap, kSelValsCap);
+    p.nb1 = orb::kSelBinsMin;
+    while (p.nb1 < orb::kSelBinsMax && avg / (uint64_t)p.nb1 > 16384) p.nb1 <<= 1;
+    p.rep = p.nb1 <= 512 ? 4 : (p.nb1 <= 1024 ? 2 : 1);
+    p.histWords = p.cellsInSmem ? 0 : (size_t)nCells * (size_t)p.nb1;
+    // candidates one block will stage per cell: a few bins' worth; cells beyond it go to the iterative search
+    p.candCap = (uint32_t)std::min<uint64_t>(kSelValsCap, 4 * (avg / (uint64_t)p.nb1) + 4096);
+    return p;
+}
+
 int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx) {
     using namespace orb;
     const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
@@ -485,31 +525,25 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
     sc.passes_out = c->d_lvl_passes + levelIdx;
     sc.n_unfound_out = c->d_lvl_unfound + levelIdx;
     int rc;
-    const uint64_t avg = c->nLocal / nCells;
-    const uint64_t cellCap = avg + avg / 8 + 256;
+    const SelPlan pl = sel_plan(c, nCells);
     // block size of the per-cell search kernels: big blocks when shared memory allows one block per SM anyway
     auto search_threads = [](size_t smem) { return smem > 112 * 1024 ? 1024 : (smem > 56 * 1024 ? 512 : 256); };
-    if (cellCap <= kSelValsCap) {
+    if (pl.cellsInSmem) {
         // ---- cells fit in shared memory: one read per cell ----
-        const size_t smem = sel_search_smem_bytes((uint32_t)cellCap);
+        const size_t smem = sel_search_smem_bytes(pl.cellCap);
         const int threads = search_threads(smem);
         int occ = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_cells, threads, smem));
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
         if ((rc = count_event_begin(c))) return rc;
-        k_sel_cells<<<grid, threads, smem, c->stream>>>(x, y, z, c->lv, ss, sc, nCells, (uint32_t)cellCap);
+        CK(launch_pdl(c, k_sel_cells, dim3(grid), dim3(threads), smem, x, y, z, c->lv, ss, sc, nCells, pl.cellCap));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     } else {
-        // ---- HIST (+ RESOLVE by the last block of each cell), COMPACT, FINISH ----
-        int nb1 = kSelBinsMin;
-        while (nb1 < kSelBinsMax && avg / (uint64_t)nb1 > 16384) nb1 <<= 1;
-        const int rep = nb1 <= 512 ? 4 : (nb1 <= 1024 ? 2 : 1);
-        const size_t words = (size_t)nCells * (size_t)nb1;
-        if (words > c->selHistWords) return fail(ORB_ERR_STATE, "selection histogram of %zu words exceeds the buffer", words);
-        // candidates one block will stage per cell: a few bins' worth; cells beyond it go to the iterative search
-        const uint32_t candCap = (uint32_t)std::min<uint64_t>(kSelValsCap, 4 * (avg / (uint64_t)nb1) + 4096);
-        CK(cudaMemsetAsync(ss.hist, 0, words * 4, c->stream));
+        // ---- HIST, COMPACT (+ RESOLVE on cell entry), FINISH; the histogram rows were cleared by level_prepare ----
+        const int nb1 = pl.nb1, rep = pl.rep;
+        const uint32_t candCap = pl.candCap;
+        if (pl.histWords > c->selHistWords) return fail(ORB_ERR_STATE, "selection histogram of %zu words exceeds the buffer", pl.histWords);
         unsigned long long *dbgBase = c->d_dbg_blocks ? c->d_dbg_blocks + (size_t)levelIdx * kDbgPasses * kDbgBlocks * 4 : nullptr;
         if (dbgBase) c->dbgGrid[levelIdx] = kDbgBlocks;
         const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
@@ -521,7 +555,8 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelHist>, kThreads, smem));
             const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 4));
             if ((rc = count_event_begin(c))) return rc;
-            k_sel_stream<kSelHist><<<grid, kThreads, smem, c->stream>>>(x, y, z, cand, c->lv, ss, c->d_tile_first, nCells, nL, nTiles, nb1, rep, candCap, dbgBase ? dbgBase : nullptr);
+            CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
+                          nCells, nL, nTiles, nb1, rep, candCap, dbgBase));
             if ((rc = count_event_end(c))) return rc;
         }
         {
@@ -530,7 +565,8 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelCompact>, kThreads, smem));
             const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 3));
             if ((rc = count_event_begin(c))) return rc;
-            k_sel_stream<kSelCompact><<<grid, kThreads, smem, c->stream>>>(x, y, z, cand, c->lv, ss, c->d_tile_first, nCells, nL, nTiles, nb1, 1, candCap, dbgBase ? dbgBase + (size_t)kDbgBlocks * 4 : nullptr);
+            CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
+                          nCells, nL, nTiles, nb1, 1, candCap, dbgBase ? dbgBase + (size_t)kDbgBlocks * 4 : (unsigned long long *)nullptr));
             if ((rc = count_event_end(c))) return rc;
         }
         {
@@ -540,8 +576,8 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_finish, threads, smem));
             const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
             if ((rc = aux_begin(c, "finish", levelIdx))) return rc;
-            k_sel_finish<<<grid, threads, smem, c->stream>>>(cand, c->lv, ss, sc, nCells, nb1, candCap, c->d_err,
-                                                             dbgBase ? dbgBase + (size_t)2 * kDbgBlocks * 4 : nullptr);
+            CK(launch_pdl(c, k_sel_finish, dim3(grid), dim3(threads), smem, (const float *)cand, c->lv, ss, sc, nCells, nb1, candCap, c->d_err,
+                          dbgBase ? dbgBase + (size_t)2 * kDbgBlocks * 4 : (unsigned long long *)nullptr));
             if ((rc = aux_end(c))) return rc;
         }
         c->nCountLaunch += 2;
@@ -859,6 +895,8 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
             CK(cudaMemset(c->d_dbg_blocks, 0, bytes));
         }
     }
+    const char *pd = getenv("ORB_PDL");
+    if (pd) c->pdl = atoi(pd) != 0;
     const char *se = getenv("ORB_SELECT");
     if (se) c->select = atoi(se) != 0;
     const char *smt = getenv("ORB_STREAM_MIN_TILES");
@@ -1282,11 +1320,13 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         const uint32_t first = (1u << (l - 1)) - 1u;   // a = 2^(l-1)-1 (orbit.cpp:104); nCells = 2^(l-1) for d = 2^y
         const uint32_t nCells = 1u << (l - 1);
         const int slot = (l - 1) * kPassSlots;
-        rc = level_prepare(c, c->d_heap + first, nCells, (1 << M) - 1, c->d_nactive + slot);
+        const bool useSelect = level_can_select(c, nCells, M);
+        const size_t histWords = useSelect ? sel_plan(c, nCells).histWords : 0;
+        rc = level_prepare(c, c->d_heap + first, nCells, (1 << M) - 1, c->d_nactive + slot, c->sel.hist, std::min(histWords, c->selHistWords));
         if (rc) return rc;
         int np = 0;
         uint32_t nu = 0;
-        if (level_can_select(c, nCells, M)) {
+        if (useSelect) {
             rc = launch_level_select(c, nCells, slot, l - 1);
             if (rc) return rc;
             np = -1;
@@ -1311,7 +1351,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             rc = launch_partition_hoare(c, nCells);
             if (rc) return rc;
         }
-        k_split<<<ceil_div(nCells, 256), 256, 0, c->stream>>>(c->d_heap, first, nCells, c->lv, c->d_range, c->d_total, c->d_final_cut);
+        CK(launch_pdl(c, k_split, dim3(ceil_div(nCells, 256)), dim3(256), 0, c->d_heap, first, nCells, c->lv, c->d_range, c->d_total, c->d_final_cut));
         c->nOtherLaunch++;
         if (c->tieMode != 1) {
             rc = launch_partition(c, nCells, c->d_tickets + (l - 1));

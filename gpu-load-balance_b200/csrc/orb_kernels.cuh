@@ -81,6 +81,15 @@ __device__ __forceinline__ uint32_t *peer_flag(const PeerSet &ps, int r, int src
     return ps.flag[r] + ((size_t)(ps.seq & 1u) * kMaxPeers + src) * kPeerMaxBlocks + block;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream drains; pdl_wait() blocks until the predecessor has completed and its
+// writes are visible, pdl_trigger() lets the successor start launching.  Both are no-ops for ordinary launches.
+// Every kernel that is launched this way calls pdl_enter() before touching global memory.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // float midpoint exactly as Cell::getCut (cell.h:74-76): float add, halve, round to float.
 // (R+L)/2.0 in double then cast == correctly rounded half of the float sum == __fmul_rn(sum,0.5f).
 __device__ __forceinline__ float mid_cut(float L, float R) { return __fmul_rn(__fadd_rn(R, L), 0.5f); }
@@ -95,8 +104,10 @@ __device__ __forceinline__ const float *pick_col(int a, const float *x, const fl
 // =====================================================================================
 __global__ void k_level_setup(const orb_cell *__restrict__ cells, uint32_t nCells, const uint32_t *__restrict__ range,
                               const uint32_t *__restrict__ total_by_id, LevelState lv, uint32_t nLocal, int nc,
-                              int *__restrict__ err) {
+                              int *__restrict__ err, uint32_t *__restrict__ n_active0) {
+    pdl_enter();
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && n_active0) *n_active0 = 1u;      // any non-zero value opens the gate of the level's first count pass
     if (c >= nCells) return;
     orb_cell cell = cells[c];
     uint32_t b = range[2 * cell.id], e = range[2 * cell.id + 1];
@@ -141,7 +152,10 @@ __global__ void k_level_setup(const orb_cell *__restrict__ cells, uint32_t nCell
 
 // first cell whose range extends beyond the start of each map tile
 __global__ void k_tile_map(const uint32_t *__restrict__ bnd, uint32_t nCells, uint32_t nMapTiles,
-                           uint32_t *__restrict__ tile_first) {
+                           uint32_t *__restrict__ tile_first, uint32_t *__restrict__ zero, size_t nZero) {
+    pdl_enter();
+    // also clears the selection search's histogram rows of the level (saves a memset between two kernels)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nZero; i += (size_t)gridDim.x * blockDim.x) zero[i] = 0u;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nMapTiles) return;
     uint32_t start = t * (uint32_t)kMapTile;
@@ -1269,6 +1283,7 @@ __device__ __forceinline__ void child_axis_margins(orb_cell &ch) {
 
 __global__ void k_split(orb_cell *__restrict__ heap, uint32_t first, uint32_t nCells, LevelState lv,
                         uint32_t *__restrict__ range, uint32_t *__restrict__ total_by_id, float *__restrict__ final_cut) {
+    pdl_enter();
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
     orb_cell p = heap[first + c];

@@ -215,6 +215,7 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
              LevelState lv, SelState ss, const uint32_t *__restrict__ tile_first, uint32_t nCells, uint32_t nLocal,
              uint32_t nTiles, int nb1, int rep, uint32_t candCap, unsigned long long *dbg) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
+    pdl_enter();
     unsigned long long *bs = dbg ? dbg + (size_t)blockIdx.x * 4 : nullptr;      // ORB_DEBUG_TIMES=2: per-block phase stamps
     if (bs && threadIdx.x == 0) bs[0] = gtimer();
     // dynamic: ring (kCountStages x 16 KB) | HIST: hist[nb1][rep]  /  COMPACT: stage[kWarps][kSelWarpStage] | hbuf[nb1]
@@ -638,6 +639,7 @@ __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ c
     uint32_t *hist2 = reinterpret_cast<uint32_t *>(sbuf + cap + 4);
     float *amb = reinterpret_cast<float *>(hist2 + kSelBins2);
     __shared__ SelSearchSmem sm;
+    pdl_enter();
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(sc.passes_out, 2);
     unsigned long long *bs = (dbg && blockIdx.x == 0) ? dbg : nullptr;    // ORB_DEBUG_TIMES=2: phases of block 0's first cell
     if (bs && threadIdx.x == 0) bs[0] = gtimer();
@@ -677,6 +679,7 @@ __global__ void __launch_bounds__(1024) k_sel_cells(const float *__restrict__ x,
     uint32_t *hist2 = reinterpret_cast<uint32_t *>(sbuf + cap + 4);
     float *amb = reinterpret_cast<float *>(hist2 + kSelBins2);
     __shared__ SelSearchSmem sm;
+    pdl_enter();
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(sc.passes_out, 1);
     for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
         __syncthreads();
