@@ -138,6 +138,7 @@ struct orb_ctx {
     uint32_t *d_lvl_unfound = nullptr; // [kMaxLevels]
     // selection-based cut search (orb_select.cuh): single rank, default trial depth
     bool select = true;
+    int selPerCellMinCells = 64;   // levels with at least this many cells: one block searches a whole cell
     bool pdl = true;               // programmatic dependent launch between the small kernels of a level
     orb::SelState sel{};
     size_t selHistWords = 0;
@@ -492,8 +493,9 @@ int count_event_end(orb_ctx *c) {
 // Shape of the selection search at a level: cells staged whole in shared memory, or HIST / COMPACT / FINISH with nb1
 // bins (rep copies per block) and room for candCap candidates per cell.
 struct SelPlan {
-    bool cellsInSmem;
-    uint32_t cellCap;     // cellsInSmem: values one block stages
+    bool cellsInSmem;     // one block per cell (k_sel_percell)
+    uint32_t cellCap;     // candidates a block keeps in shared memory
+    int threads;          // block size of k_sel_percell
     int nb1, rep;
     size_t histWords;     // nCells * nb1 (cleared by k_tile_map during level preparation)
     uint32_t candCap;
@@ -501,9 +503,10 @@ struct SelPlan {
 SelPlan sel_plan(const orb_ctx *c, uint32_t nCells) {
     SelPlan p{};
     const uint64_t avg = c->nLocal / nCells;
-    const uint64_t cellCap = avg + avg / 8 + 256;
-    p.cellsInSmem = cellCap <= kSelValsCap;
-    p.cellCap = (uint32_t)std::min<uint64_t>(cellCap, kSelValsCap);
+    // one block per cell once there are enough cells to fill the GPU; fewer, larger cells are streamed by all blocks
+    p.cellsInSmem = nCells >= (uint32_t)c->selPerCellMinCells && avg <= (1u << 20);
+    p.threads = avg >= 32768 ? 512 : 256;
+    p.cellCap = avg >= 65536 ? 8192u : 4096u;
     p.nb1 = orb::kSelBinsMin;
     while (p.nb1 < orb::kSelBinsMax && avg / (uint64_t)p.nb1 > 16384) p.nb1 <<= 1;
     p.rep = p.nb1 <= 512 ? 4 : (p.nb1 <= 1024 ? 2 : 1);
@@ -529,14 +532,15 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
     // block size of the per-cell search kernels: big blocks when shared memory allows one block per SM anyway
     auto search_threads = [](size_t smem) { return smem > 112 * 1024 ? 1024 : (smem > 56 * 1024 ? 512 : 256); };
     if (pl.cellsInSmem) {
-        // ---- cells fit in shared memory: one read per cell ----
-        const size_t smem = sel_search_smem_bytes(pl.cellCap);
-        const int threads = search_threads(smem);
+        // ---- many cells: one block runs the whole search of a cell ----
+        const size_t smem = sel_percell_smem_bytes(pl.cellCap);
         int occ = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_cells, threads, smem));
+        if (pl.threads == 512) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_percell<512, 3>, 512, smem));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_percell<256, 6>, 256, smem));
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
         if ((rc = count_event_begin(c))) return rc;
-        CK(launch_pdl(c, k_sel_cells, dim3(grid), dim3(threads), smem, x, y, z, c->lv, ss, sc, nCells, pl.cellCap));
+        if (pl.threads == 512) CK(launch_pdl(c, k_sel_percell<512, 3>, dim3(grid), dim3(512), smem, x, y, z, c->lv, ss, sc, nCells, pl.cellCap));
+        else CK(launch_pdl(c, k_sel_percell<256, 6>, dim3(grid), dim3(256), smem, x, y, z, c->lv, ss, sc, nCells, pl.cellCap));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     } else {
@@ -844,7 +848,8 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occSelStream[1], orb::k_sel_stream<orb::kSelCompact>, orb::kThreads, compBytes));
         const int searchBytes = (int)orb::sel_search_smem_bytes(kSelValsCap);
         CK(cudaFuncSetAttribute(orb::k_sel_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
-        CK(cudaFuncSetAttribute(orb::k_sel_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
     }
     CK(cudaMalloc(&c->d_misc, 64));
     CK(cudaMalloc(&c->d_active_particles, 16));
@@ -897,6 +902,8 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     }
     const char *pd = getenv("ORB_PDL");
     if (pd) c->pdl = atoi(pd) != 0;
+    const char *spc = getenv("ORB_SELECT_PERCELL_MIN");
+    if (spc && atoi(spc) >= 1) c->selPerCellMinCells = atoi(spc);
     const char *se = getenv("ORB_SELECT");
     if (se) c->select = atoi(se) != 0;
     const char *smt = getenv("ORB_STREAM_MIN_TILES");

@@ -69,8 +69,13 @@ __device__ __forceinline__ int sel_bin(float x, float lo, float scale, int nb) {
 // the reference's decision value for a count (orbit.cpp:204-205), literal float arithmetic
 struct SelTarget {
     float prod;
+    // ratio = (float)(ceil(nLeafCells / 2.0) / nLeafCells) (orbit.cpp:204: double division, then rounded to float).
+    // Evaluated as ONE correctly rounded float division, which gives the same bits: numerator a = (n+1)/2 and
+    // denominator n are integers below 2^21, so a/n is either exactly a float rounding midpoint or at least
+    // 2^-46 (relative) away from one - the intermediate rounding to double (2^-53) can never move it across.
+    // (Every thread of a block evaluates this; FP64 division would serialise on the narrow FP64 pipe.)
     __device__ __forceinline__ void init(uint32_t total, int nleaf) {
-        const float ratio = (float)(ceil(nleaf / 2.0) / nleaf);
+        const float ratio = __fdiv_rn((float)((nleaf + 1) >> 1), (float)nleaf);
         prod = __fmul_rn(__uint2float_rn(total), ratio);
     }
     __device__ __forceinline__ int diff(uint32_t cnt) const { return __float2int_rz(__fsub_rn(__uint2float_rn(cnt), prod)); }
@@ -670,29 +675,128 @@ __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ c
     }
 }
 
-// Cells that fit in shared memory: one block reads the cell once and searches it (no HIST / COMPACT passes)
-__global__ void __launch_bounds__(1024) k_sel_cells(const float *__restrict__ x, const float *__restrict__ y,
-                                                    const float *__restrict__ z, LevelState lv, SelState ss, SelCtl sc,
-                                                    uint32_t nCells, uint32_t cap) {
+// =====================================================================================
+// Whole search of a cell by ONE block (levels with many cells): HIST of the cell into a shared-memory histogram,
+// RESOLVE, second read of the cell (it is still in L2) that keeps the candidates in shared memory, FINISH.  Nothing
+// but the result goes back to global memory; several blocks per SM overlap each other's memory phases.
+// dynamic shared memory: hist[kSelBins2] (reused as the refinement histogram) | list[candCap] | amb[kSelAmbCap]
+// =====================================================================================
+__host__ __device__ inline size_t sel_percell_smem_bytes(uint32_t candCap) { return ((size_t)kSelBins2 + candCap + kSelAmbCap) * 4u; }
+
+struct SelPerCellSmem {
+    SelSearchSmem search;
+    uint32_t w[32];
+    int first, last;
+    uint32_t base, end, nlist;
+};
+
+// apply f(value) to every element of src[0..K): 16-byte loads where src is aligned, four loads in flight per thread
+template <typename F>
+__device__ __forceinline__ void sel_for_each(const float *__restrict__ src, uint32_t K, F f) {
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
+    const uint32_t head = mis ? min(4u - mis, K) : 0u;
+    const uint32_t body4 = (K - head) / 4u;
+    const float4 *g4 = reinterpret_cast<const float4 *>(src + head);
+    const uint32_t nT = blockDim.x;
+    uint32_t i = threadIdx.x;
+    for (; i + 3u * nT < body4; i += 4u * nT) {
+        const float4 a = __ldg(g4 + i), b = __ldg(g4 + i + nT), c = __ldg(g4 + i + 2u * nT), d = __ldg(g4 + i + 3u * nT);
+        f(a.x); f(a.y); f(a.z); f(a.w); f(b.x); f(b.y); f(b.z); f(b.w);
+        f(c.x); f(c.y); f(c.z); f(c.w); f(d.x); f(d.y); f(d.z); f(d.w);
+    }
+    for (; i < body4; i += nT) { const float4 a = __ldg(g4 + i); f(a.x); f(a.y); f(a.z); f(a.w); }
+    if (threadIdx.x < head) f(__ldg(src + threadIdx.x));
+    const uint32_t tail0 = head + body4 * 4u;
+    if (tail0 + threadIdx.x < K) f(__ldg(src + tail0 + threadIdx.x));
+}
+
+template <int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float *__restrict__ x, const float *__restrict__ y,
+                                                                    const float *__restrict__ z, LevelState lv, SelState ss,
+                                                                    SelCtl sc, uint32_t nCells, uint32_t candCap) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
-    float *sbuf = reinterpret_cast<float *>(sel_smem);
-    uint32_t *hist2 = reinterpret_cast<uint32_t *>(sbuf + cap + 4);
-    float *amb = reinterpret_cast<float *>(hist2 + kSelBins2);
-    __shared__ SelSearchSmem sm;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(sel_smem);
+    float *list = reinterpret_cast<float *>(hist + kSelBins2);
+    float *amb = list + candCap;
+    __shared__ SelPerCellSmem sm;
     pdl_enter();
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(sc.passes_out, 1);
+    const int tid = threadIdx.x, nThreads = (int)blockDim.x;
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(sc.passes_out, 2);
     for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
         __syncthreads();
         const uint32_t act = lv.active[c], b = lv.bnd[c], K = lv.bnd[c + 1] - b;
         const int ax = lv.axis[c];
-        if (threadIdx.x == 0) ss.flag[c] = 0u;
+        const float L = lv.mL[c], R = lv.mR[c];
+        if (tid == 0) ss.flag[c] = 0u;
         if (!act) continue;
-        if (K > cap) {
-            if (threadIdx.x == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
+        const int nb = max(K > 4096u ? kSelBins2 : 256, nThreads);
+        const int per = nb / nThreads;                    // 1, 2 or 8
+        const float lo = L, scale = sel_scale(L, R, nb), nbm1 = (float)(nb - 1);
+        const float *col = pick_col(ax, x, y, z) + b;
+        for (int i = tid; i < nb; i += nThreads) hist[i] = 0u;
+        if (tid == 0) { sm.first = nb; sm.last = -1; sm.base = 0u; sm.end = 0u; sm.nlist = 0u; }
+        __syncthreads();
+        // ---- HIST ----
+        sel_for_each(col, K, [&](float v) {
+            const float t = fminf(fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f), nbm1);      // == sel_bin(v, lo, scale, nb)
+            atomicAdd(&hist[__float2int_rz(t)], 1u);
+        });
+        __syncthreads();
+        // ---- RESOLVE ----
+        SelTarget tg;
+        tg.init(lv.total[c], lv.nleaf[c]);
+        uint32_t h[8];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { h[j] = (j < per) ? hist[tid * per + j] : 0u; sum += h[j]; }
+        uint32_t total;
+        const uint32_t excl = sel_block_scan(sum, sm.w, total);
+        int myFirst = nb, myLast = -1;
+        {
+            uint32_t p = excl;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < per) {
+                    const uint32_t pn = p + h[j];
+                    const int bb = tid * per + j;
+                    if (tg.diff(pn) > -3) myFirst = min(myFirst, bb);
+                    if (tg.diff(p) < 3) myLast = max(myLast, bb);
+                    p = pn;
+                }
+            }
+        }
+        if (myFirst < nb) atomicMin(&sm.first, myFirst);
+        if (myLast >= 0) atomicMax(&sm.last, myLast);
+        __syncthreads();
+        const int first = sm.first, last = sm.last;
+        {
+            uint32_t p = excl;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < per) {
+                    const int bb = tid * per + j;
+                    if (bb == first) sm.base = p;
+                    p += h[j];
+                    if (bb == last) sm.end = p;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t base = sm.base, K2 = sm.end - base;
+        if (!(first <= last) || K2 > candCap) {       // too many candidates for one block: the iterative search takes the cell
+            if (tid == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
             continue;
         }
-        const float *vals = sel_stage_vals(sbuf, pick_col(ax, x, y, z) + b, K);
-        sel_block_search(vals, K, 0u, 0, 0.f, 0.f, 1, 0, 0, hist2, amb, lv, ss, sc, c, 1, sm);
+        // ---- COMPACT: second read (L2), candidates into shared memory ----
+        float fLo, fHi;
+        sel_bin_bounds((uint32_t)first, (uint32_t)last, nb, fLo, fHi);
+        sel_for_each(col, K, [&](float v) {
+            const float t = fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f);
+            if (t >= fLo && t < fHi) list[atomicAdd(&sm.nlist, 1u)] = v;
+        });
+        __syncthreads();
+        // ---- FINISH ----
+        sel_block_search(list, K2, base, 1, lo, scale, nb, first, last, hist, amb, lv, ss, sc, c, 2, sm.search);
     }
 }
 
