@@ -180,6 +180,11 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
+    # stdout carries exactly one JSON line: whatever libraries print while the job runs (NCCL's version banner, ...)
+    # goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -366,7 +371,9 @@ def main():
                 "workload": f"2^{args.x} {args.dist} particles per GPU (reference xorshf96 stream), 2^{args.y} leaf cells, "
                             f"{n_lv} split levels ({'full' if args.full_levels else 'reference-compatible'})",
                 "particles_total": n_local * world, "leaf_cells": d, "parallelism": (f"particle shards x{world}; per-cell counts combined " +
-                                                    ("inside the count kernel over NVLink peer memory" if (world > 1 and use_peers) else "by NCCL allreduce")),
+                                                    ("by the selection search's two exchanges per level (NCCL allreduce of histogram rows, all-gather of candidates)"
+                                                     if (world > 1 and os.environ.get("ORB_SELECT_MR", "1") != "0") else
+                                                     ("inside the count kernel over NVLink peer memory" if (world > 1 and use_peers) else "by NCCL allreduce"))),
                 "l2": "pristine particles restored + 256 MiB buffer written between timed steps (L2 flush)",
                 "trial_depth": args.trial_depth or 3,
             },
@@ -384,7 +391,7 @@ def main():
             "tie_mode": "canonical (stable x<cut; equals the reference whenever no particle sits exactly on a cut)",
             "reference_exact_mode": hoare,
         }
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     ctx.close()
     if dist is not None:
         dist.barrier()

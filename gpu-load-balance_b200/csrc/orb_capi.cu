@@ -50,6 +50,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load() {
         if (lib) return true;
@@ -63,8 +64,9 @@ struct NcclApi {
         CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
         AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && GetErrorString;
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather && GetErrorString;
     }
 } g_nccl;
 
@@ -77,6 +79,8 @@ struct NcclApi {
 
 constexpr int kMaxLevels = 40;
 constexpr uint32_t kSelValsCap = 49152;   // values one block of the selection search stages in shared memory (192 KB)
+constexpr uint32_t kSelMrMaxCells = 2048; // several ranks: levels up to this many cells use the selection search
+constexpr size_t kSelSlotWordsTotal = (size_t)1 << 20;   // candidate slots of one rank and level (4 MB)
 constexpr int kDbgPasses = 12;      // ORB_DEBUG_TIMES=2: passes and blocks recorded per level
 constexpr uint32_t kDbgBlocks = 1024;
 constexpr int kPassSlots = 40;   // >= 32 passes + slack, per level
@@ -139,6 +143,8 @@ struct orb_ctx {
     // selection-based cut search (orb_select.cuh): single rank, default trial depth
     bool select = true;
     int selPerCellMinCells = 64;   // levels with at least this many cells: one block searches a whole cell
+    bool selBigBlocks = true;      // ORB_SELECT_BIG_BLOCKS=0: no 1024 x 1 / 512 x 2 variants of k_sel_percell
+    int selT512MinAvg = 32768;     // ORB_SELECT_T512_MIN: cells of at least this many particles get 512-thread blocks
     bool pdl = true;               // programmatic dependent launch between the small kernels of a level
     orb::SelState sel{};
     size_t selHistWords = 0;
@@ -155,6 +161,14 @@ struct orb_ctx {
     ncclComm_t comm = nullptr;
     bool ownComm = false;
     int rank = 0, nRanks = 1;
+    // selection search over several ranks (k_selmr_* in orb_select.cuh): global histogram rows, candidate slots
+    bool selectMr = true;              // ORB_SELECT_MR=0: iterative search on every multi-rank level
+    uint64_t nLocalMin = 0, nGlobal = 0;   // over ranks; every decision that shapes a collective uses these only
+    uint32_t *d_sel_hist_g = nullptr;  // [selHistWords]
+    uint32_t *d_sel_locbase = nullptr; // [maxLevelCells]
+    float *d_slots_l = nullptr;        // [kSelSlotWordsTotal]
+    float *d_slots_g = nullptr;        // [nRanks][kSelSlotWordsTotal]
+    std::vector<int> extraPasses;      // passes of the iterative fallback per level (host-driven on several ranks)
 
     // fused combine+update over NVLink peer memory (optional; see PeerSet in orb_kernels.cuh)
     bool peerEnabled = false;
@@ -496,6 +510,7 @@ struct SelPlan {
     bool cellsInSmem;     // one block per cell (k_sel_percell)
     uint32_t cellCap;     // candidates a block keeps in shared memory
     int threads;          // block size of k_sel_percell
+    int variant;          // 0: <512,3> / <256,6>, 1: <512,2,8>, 2: <1024,1,8>
     int nb1, rep;
     size_t histWords;     // nCells * nb1 (cleared by k_tile_map during level preparation)
     uint32_t candCap;
@@ -505,7 +520,12 @@ SelPlan sel_plan(const orb_ctx *c, uint32_t nCells) {
     const uint64_t avg = c->nLocal / nCells;
     // one block per cell once there are enough cells to fill the GPU; fewer, larger cells are streamed by all blocks
     p.cellsInSmem = nCells >= (uint32_t)c->selPerCellMinCells && avg <= (1u << 20);
-    p.threads = avg >= 32768 ? 512 : 256;
+    // block shape: few big cells -> a block per SM (or two) with 8 vector loads in flight per thread, so that the
+    // blocks that exist can pull the whole HBM bandwidth; otherwise 3 x 512 or 6 x 256 threads per SM
+    p.threads = avg >= (uint64_t)c->selT512MinAvg ? 512 : 256;
+    p.variant = 0;
+    if (c->selBigBlocks && nCells <= (uint32_t)c->nSM) { p.variant = 2; p.threads = 1024; }
+    else if (c->selBigBlocks && nCells <= 2u * (uint32_t)c->nSM) { p.variant = 1; p.threads = 512; }
     p.cellCap = avg >= 65536 ? 8192u : 4096u;
     p.nb1 = orb::kSelBinsMin;
     while (p.nb1 < orb::kSelBinsMax && avg / (uint64_t)p.nb1 > 16384) p.nb1 <<= 1;
@@ -535,12 +555,12 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
         // ---- many cells: one block runs the whole search of a cell ----
         const size_t smem = sel_percell_smem_bytes(pl.cellCap);
         int occ = 1;
-        if (pl.threads == 512) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_percell<512, 3>, 512, smem));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_percell<256, 6>, 256, smem));
+        auto kern = pl.variant == 2 ? k_sel_percell<1024, 1, 8> : (pl.variant == 1 ? k_sel_percell<512, 2, 8>
+                    : (pl.threads == 512 ? k_sel_percell<512, 3> : k_sel_percell<256, 6>));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, pl.threads, smem));
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
         if ((rc = count_event_begin(c))) return rc;
-        if (pl.threads == 512) CK(launch_pdl(c, k_sel_percell<512, 3>, dim3(grid), dim3(512), smem, x, y, z, c->lv, ss, sc, nCells, pl.cellCap));
-        else CK(launch_pdl(c, k_sel_percell<256, 6>, dim3(grid), dim3(256), smem, x, y, z, c->lv, ss, sc, nCells, pl.cellCap));
+        CK(launch_pdl(c, kern, dim3(grid), dim3(pl.threads), smem, x, y, z, c->lv, ss, sc, nCells, pl.cellCap));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     } else {
@@ -560,7 +580,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
             const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 4));
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                          nCells, nL, nTiles, nb1, rep, candCap, dbgBase));
+                          nCells, nL, nTiles, nb1, rep, candCap, dbgBase, (float *)nullptr, 0u));
             if ((rc = count_event_end(c))) return rc;
         }
         {
@@ -570,7 +590,8 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
             const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 3));
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                          nCells, nL, nTiles, nb1, 1, candCap, dbgBase ? dbgBase + (size_t)kDbgBlocks * 4 : (unsigned long long *)nullptr));
+                          nCells, nL, nTiles, nb1, 1, candCap, dbgBase ? dbgBase + (size_t)kDbgBlocks * 4 : (unsigned long long *)nullptr,
+                          (float *)nullptr, 0u));
             if ((rc = count_event_end(c))) return rc;
         }
         {
@@ -618,6 +639,129 @@ int finalize_unfound(orb_ctx *c, uint32_t nCells, uint32_t *nUnfoundOut) {
         c->nOtherLaunch++;
     }
     CK(cudaGetLastError());
+    return ORB_OK;
+}
+
+// ---- selection search over several ranks: HIST -> allreduce(rows) -> COMPACT into slots -> prep -> all-gather(slots) ->
+//      finish on the candidates of all ranks; cells it flags go to the host-driven iterative loop (run_bisection).
+//      Every number that shapes a collective (nb1, slot size, whether the level qualifies) derives from nCells,
+//      nLocalMin and nGlobal, which are identical on all ranks. ----
+struct SelMrPlan {
+    bool ok;
+    int nb1, rep;
+    uint32_t candCap, slotWords;
+    size_t histWords;
+};
+SelMrPlan sel_plan_mr(const orb_ctx *c, uint32_t nCells, int M) {
+    SelMrPlan p{};
+    p.ok = false;
+    if (!(c->select && c->selectMr && c->nRanks > 1 && c->nRanks <= orb::kMaxPeers && M == 3 && c->d_slots_g && nCells >= 1 &&
+          nCells <= kSelMrMaxCells && c->nLocalMin > 0))
+        return p;
+    const uint64_t gavg = c->nGlobal / nCells, lavg = std::max<uint64_t>(c->nGlobal / c->nRanks, c->nLocalMin) / nCells;
+    p.nb1 = orb::kSelBinsMin;
+    while (p.nb1 < orb::kSelBinsMax && gavg / (uint64_t)p.nb1 > 16384) p.nb1 <<= 1;
+    p.rep = p.nb1 <= 512 ? 4 : (p.nb1 <= 1024 ? 2 : 1);
+    p.histWords = (size_t)nCells * (size_t)p.nb1;
+    p.candCap = (uint32_t)std::min<uint64_t>(kSelValsCap, 4 * (gavg / (uint64_t)p.nb1) + 4096);
+    // slot of one rank and cell: a few bins' worth of its own particles + the count word, a power of two
+    uint64_t want = std::min<uint64_t>(p.candCap, 4 * (lavg / (uint64_t)p.nb1) + 96) + 1;
+    uint32_t sw = 128;
+    while (sw < want) sw <<= 1;
+    while (sw > 32 && (size_t)sw * nCells > kSelSlotWordsTotal) sw >>= 1;
+    p.slotWords = sw;
+    const size_t histFit = (size_t)c->nLocalMin / 16 + 2 * (size_t)orb::kSelBinsMax;   // <= every rank's selHistWords
+    p.ok = p.histWords <= histFit && (size_t)sw * nCells <= kSelSlotWordsTotal;
+    return p;
+}
+
+int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int slotBase, int levelIdx) {
+    using namespace orb;
+    const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
+    float *cand = c->x[c->cur ^ 1];
+    SelState ss = c->sel;                       // hist = this rank's rows
+    ss.n_flagged = c->d_sel_nflag + levelIdx;
+    SelState sg = ss;
+    sg.hist = c->d_sel_hist_g;                  // rows summed over ranks
+    SelCtl sc;
+    sc.active_particles = c->d_active_particles;
+    sc.level_iters = c->d_level_iters + levelIdx;
+    sc.passes_out = c->d_lvl_passes + levelIdx;
+    sc.n_unfound_out = c->d_lvl_unfound + levelIdx;
+    SelMrState mr;
+    mr.hist_l = c->sel.hist;
+    mr.loc_base = c->d_sel_locbase;
+    mr.slots_l = c->d_slots_l;
+    mr.slots_g = c->d_slots_g;
+    mr.slotWords = pl.slotWords;
+    mr.nRanks = c->nRanks;
+    mr.self = c->rank;
+    int rc;
+    const int nb1 = pl.nb1;
+    const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
+    const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
+    const uint32_t nL = (uint32_t)c->nLocal;
+    if (nTiles) {
+        const size_t smem = ringBytes + (size_t)nb1 * pl.rep * 4;
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelHist>, kThreads, smem));
+        const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 4));
+        if ((rc = count_event_begin(c))) return rc;
+        CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
+                      nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u));
+        if ((rc = count_event_end(c))) return rc;
+        c->nCountLaunch++;
+    }
+    NK(g_nccl.AllReduce(c->sel.hist, c->d_sel_hist_g, pl.histWords, ncclUint32, ncclSum, c->comm, c->stream));
+    if (nTiles) {
+        const size_t smem = ringBytes + (size_t)kWarps * kSelWarpStage * 4 + (size_t)nb1 * 4;
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelCompact>, kThreads, smem));
+        const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 3));
+        if ((rc = count_event_begin(c))) return rc;
+        CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, sg, (const uint32_t *)c->d_tile_first,
+                      nCells, nL, nTiles, nb1, 1, pl.candCap, (unsigned long long *)nullptr, c->d_slots_l, pl.slotWords));
+        if ((rc = count_event_end(c))) return rc;
+        c->nCountLaunch++;
+    }
+    {
+        const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * 8u);
+        if ((rc = aux_begin(c, "mr_prep", levelIdx))) return rc;
+        CK(launch_pdl(c, k_selmr_prep, dim3(grid), dim3(kThreads), (size_t)nb1 * 4, c->lv, sg, mr, nCells, nb1, pl.candCap));
+        if ((rc = aux_end(c))) return rc;
+        c->nOtherLaunch++;
+    }
+    NK(g_nccl.AllGather(c->d_slots_l, c->d_slots_g, (size_t)nCells * pl.slotWords, ncclUint32, c->comm, c->stream));
+    {
+        const size_t smem = sel_search_smem_bytes(pl.candCap);
+        const int threads = nCells <= 2u * (uint32_t)c->nSM ? 1024 : (smem > 112 * 1024 ? 1024 : (smem > 56 * 1024 ? 512 : 256));
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_selmr_finish, threads, smem));
+        const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
+        if ((rc = aux_begin(c, "mr_finish", levelIdx))) return rc;
+        CK(launch_pdl(c, k_selmr_finish, dim3(grid), dim3(threads), smem, c->lv, sg, sc, mr, nCells, nb1, pl.candCap, c->d_err));
+        if ((rc = aux_end(c))) return rc;
+        c->nUpdateLaunch++;
+    }
+    CK(cudaGetLastError());
+    // cells the search left over (the same on every rank): read the count, run the iterative loop for them
+    if ((rc = ensure_scratch(c, 64))) return rc;
+    CK(cudaMemcpyAsync(c->h_scratch, c->d_sel_nflag + levelIdx, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->h_scratch[0]) {
+        int np = 0;
+        if ((rc = run_bisection(c, nCells, 3, slotBase, levelIdx, &np))) return rc;
+        if (np >= (kMaxIter + 2) / 3) {
+            uint32_t nu = 0;
+            if ((rc = finalize_unfound(c, nCells, &nu))) return rc;
+            // nu counts every cell of the level without a found cut (also those the selection search itself capped):
+            // it replaces the device-side statistic of the level
+            c->h_scratch[1] = nu;
+            CK(cudaMemcpyAsync(c->d_lvl_unfound + levelIdx, c->h_scratch + 1, 4, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+        if ((size_t)levelIdx < c->extraPasses.size()) c->extraPasses[levelIdx] = np;
+    }
     return ORB_OK;
 }
 
@@ -828,7 +972,7 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaMalloc(&c->d_lvl_passes, sizeof(int32_t) * kMaxLevels));
     CK(cudaMalloc(&c->d_lvl_unfound, sizeof(uint32_t) * kMaxLevels));
     {
-        c->selHistWords = (size_t)n_local / 64 + 2 * (size_t)orb::kSelBinsMax;
+        c->selHistWords = (size_t)n_local / 16 + 2 * (size_t)orb::kSelBinsMax;
         CK(cudaMalloc(&c->sel.hist, c->selHistWords * 4));
         CK(cudaMalloc(&c->sel.bfirst, L * 4));
         CK(cudaMalloc(&c->sel.blast, L * 4));
@@ -848,8 +992,11 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occSelStream[1], orb::k_sel_stream<orb::kSelCompact>, orb::kThreads, compBytes));
         const int searchBytes = (int)orb::sel_search_smem_bytes(kSelValsCap);
         CK(cudaFuncSetAttribute(orb::k_sel_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
+        CK(cudaFuncSetAttribute(orb::k_selmr_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
         CK(cudaFuncSetAttribute(orb::k_sel_percell<512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
         CK(cudaFuncSetAttribute(orb::k_sel_percell<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<512, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<1024, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
     }
     CK(cudaMalloc(&c->d_misc, 64));
     CK(cudaMalloc(&c->d_active_particles, 16));
@@ -904,8 +1051,14 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     if (pd) c->pdl = atoi(pd) != 0;
     const char *spc = getenv("ORB_SELECT_PERCELL_MIN");
     if (spc && atoi(spc) >= 1) c->selPerCellMinCells = atoi(spc);
+    const char *sbb = getenv("ORB_SELECT_BIG_BLOCKS");
+    if (sbb) c->selBigBlocks = atoi(sbb) != 0;
+    const char *st5 = getenv("ORB_SELECT_T512_MIN");
+    if (st5 && atoi(st5) >= 1) c->selT512MinAvg = atoi(st5);
     const char *se = getenv("ORB_SELECT");
     if (se) c->select = atoi(se) != 0;
+    const char *sem = getenv("ORB_SELECT_MR");
+    if (sem) c->selectMr = atoi(sem) != 0;
     const char *smt = getenv("ORB_STREAM_MIN_TILES");
     if (smt && atoi(smt) >= 1) c->streamMinTiles = atoi(smt);
     const char *pe = getenv("ORB_PERSIST");
@@ -936,6 +1089,7 @@ int orb_destroy(orb_ctx *c) {
     cudaFree(c->d_dbg); cudaFree(c->d_dbg_blocks);
     cudaFree(c->sel.hist); cudaFree(c->sel.bfirst); cudaFree(c->sel.blast); cudaFree(c->sel.base); cudaFree(c->sel.ncand);
     cudaFree(c->sel.cursor); cudaFree(c->sel.flag); cudaFree(c->d_sel_nflag);
+    cudaFree(c->d_sel_hist_g); cudaFree(c->d_sel_locbase); cudaFree(c->d_slots_l); cudaFree(c->d_slots_g);
     for (int r = 0; r < orb::kMaxPeers; ++r)
         if (c->peerIpc[r]) { cudaIpcCloseMemHandle(c->peerCnt[r]); cudaIpcCloseMemHandle(c->peerFlag[r]); }
     cudaFree(c->d_lvl_passes); cudaFree(c->d_lvl_unfound); cudaFree(c->d_cdone); cudaFree(c->d_peer_cnt); cudaFree(c->d_peer_flag);
@@ -987,6 +1141,26 @@ static int setup_multi(orb_ctx *c) {
     if (c->nRanks > 1 && !c->d_cnt_g_buf) {
         CK(cudaMalloc(&c->d_cnt_g_buf, (size_t)c->maxLevelCells * orb::kCS * 4));
         c->lv.cnt_g = c->d_cnt_g_buf;
+    }
+    c->nLocalMin = c->nGlobal = c->nLocal;
+    if (c->nRanks > 1) {
+        // shard sizes over ranks (min, sum): whatever shapes a collective must be decided from rank-invariant numbers
+        unsigned long long h[2] = {~(unsigned long long)c->nLocal, (unsigned long long)c->nLocal}, *d = nullptr;
+        CK(cudaMalloc(&d, 16));
+        CK(cudaMemcpyAsync(d, h, 16, cudaMemcpyHostToDevice, c->stream));
+        NK(g_nccl.AllReduce(d, d, 1, ncclUint64, ncclMax, c->comm, c->stream));          // max of ~n = ~min
+        NK(g_nccl.AllReduce(d + 1, d + 1, 1, ncclUint64, ncclSum, c->comm, c->stream));
+        CK(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaFree(d));
+        c->nLocalMin = ~h[0];
+        c->nGlobal = h[1];
+        if (!c->d_sel_hist_g) {
+            CK(cudaMalloc(&c->d_sel_hist_g, c->selHistWords * 4));
+            CK(cudaMalloc(&c->d_sel_locbase, (size_t)c->maxLevelCells * 4));
+            CK(cudaMalloc(&c->d_slots_l, kSelSlotWordsTotal * 4));
+            CK(cudaMalloc(&c->d_slots_g, kSelSlotWordsTotal * 4 * (size_t)c->nRanks));
+        }
     }
     return ORB_OK;
 }
@@ -1320,6 +1494,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
     }
 
     const int M = c->trialDepth;
+    c->extraPasses.assign(kMaxLevels, 0);
     std::vector<int> passes;
     std::vector<uint32_t> unfound;
     int nDone = 0;
@@ -1328,12 +1503,17 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         const uint32_t nCells = 1u << (l - 1);
         const int slot = (l - 1) * kPassSlots;
         const bool useSelect = level_can_select(c, nCells, M);
-        const size_t histWords = useSelect ? sel_plan(c, nCells).histWords : 0;
+        const SelMrPlan mrPlan = sel_plan_mr(c, nCells, M);
+        const size_t histWords = useSelect ? sel_plan(c, nCells).histWords : (mrPlan.ok ? mrPlan.histWords : 0);
         rc = level_prepare(c, c->d_heap + first, nCells, (1 << M) - 1, c->d_nactive + slot, c->sel.hist, std::min(histWords, c->selHistWords));
         if (rc) return rc;
         int np = 0;
         uint32_t nu = 0;
-        if (useSelect) {
+        if (mrPlan.ok) {
+            rc = launch_level_select_mr(c, nCells, mrPlan, slot, l - 1);
+            if (rc) return rc;
+            np = -1;
+        } else if (useSelect) {
             rc = launch_level_select(c, nCells, slot, l - 1);
             if (rc) return rc;
             np = -1;
@@ -1451,7 +1631,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         stats->n_levels = nDone;
         for (int l = 0; l < nDone && l < 64; ++l) {
             stats->iters[l] = iters[l];
-            stats->passes[l] = passes[l] >= 0 ? passes[l] : lvlPasses[l];
+            stats->passes[l] = passes[l] >= 0 ? passes[l] : lvlPasses[l] + c->extraPasses[l];
             stats->not_found[l] = passes[l] >= 0 ? (int32_t)unfound[l] : (int32_t)lvlUnfound[l];
         }
         stats->active_passes = ap[0];

@@ -18,8 +18,8 @@
 // restates the algorithm in numpy and checks it against the literal loop, tests/test_gpu_parity.py checks this file
 // against the oracle.  Cells the method cannot finish (candidates beyond shared memory because of massive ties, a
 // capped cell whose final cut leaves the candidate bins) are flagged and left untouched for the iterative path
-// (k_level_persistent / k_count_*), which then runs for them alone.  Single rank only: with several ranks the
-// histograms and candidates would have to be exchanged; the multi-GPU path keeps the iterative search.
+// (k_level_persistent / k_count_*), which then runs for them alone.  With several ranks the histogram rows are
+// all-reduced and the candidates all-gathered (two exchanges per level, see k_selmr_* at the end of this file).
 #pragma once
 #include "orb_kernels.cuh"
 
@@ -218,7 +218,8 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads, MODE == kSelHist ? 4 : 3)
 k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z, float *__restrict__ cand,
              LevelState lv, SelState ss, const uint32_t *__restrict__ tile_first, uint32_t nCells, uint32_t nLocal,
-             uint32_t nTiles, int nb1, int rep, uint32_t candCap, unsigned long long *dbg) {
+             uint32_t nTiles, int nb1, int rep, uint32_t candCap, unsigned long long *dbg, float *__restrict__ slots,
+             uint32_t slotWords) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     pdl_enter();
     unsigned long long *bs = dbg ? dbg + (size_t)blockIdx.x * 4 : nullptr;      // ORB_DEBUG_TIMES=2: per-block phase stamps
@@ -260,9 +261,14 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
             if (tot) {
                 if (tid == 0) sm.gbase = atomicAdd(&ss.cursor[cur], tot);
                 __syncthreads();
-                float *dst = cand + lv.bnd[cur] + sm.gbase + off;
+                // one rank: the cell's list in the idle column.  Several ranks: the cell's fixed-size slot of the
+                // all-gather buffer (values beyond the slot are dropped; the count word tells every rank)
+                float *dst = slotWords ? slots + (size_t)cur * slotWords : cand + lv.bnd[cur];
+                const uint32_t lim = slotWords ? slotWords - 1u : 0xffffffffu;
+                const uint32_t o0 = sm.gbase + off;
                 const uint32_t n = sm.wN[warp];
-                for (uint32_t i = lane; i < n; i += 32u) dst[i] = s_stage[warp * kSelWarpStage + i];
+                for (uint32_t i = lane; i < n; i += 32u)
+                    if (o0 + i < lim) dst[o0 + i] = s_stage[warp * kSelWarpStage + i];
             }
             __syncthreads();
             if (tid < kWarps) sm.wN[tid] = 0u;
@@ -276,8 +282,10 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
         uint32_t g = 0;
         if (lane == 0) g = atomicAdd(&ss.cursor[cur], n);
         g = __shfl_sync(0xffffffffu, g, 0);
-        float *dst = cand + lv.bnd[cur] + g;
-        for (uint32_t i = lane; i < n; i += 32u) dst[i] = s_stage[warp * kSelWarpStage + i];
+        float *dst = slotWords ? slots + (size_t)cur * slotWords : cand + lv.bnd[cur];
+        const uint32_t lim = slotWords ? slotWords - 1u : 0xffffffffu;
+        for (uint32_t i = lane; i < n; i += 32u)
+            if (g + i < lim) dst[g + i] = s_stage[warp * kSelWarpStage + i];
         __syncwarp();
         if (lane == 0) sm.wN[warp] = 0u;
         __syncwarp();
@@ -290,7 +298,8 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
             // resolve the cell's candidate bins from its (complete) histogram; the block that holds the cell's first
             // particle publishes the result for FINISH
             const uint32_t cb = lv.bnd[c];
-            const bool publish = cb >= tb0 * (uint32_t)kCountTile && cb < tb1 * (uint32_t)kCountTile;
+            // (several ranks: k_selmr_prep resolves and publishes every cell, also those without local particles)
+            const bool publish = slotWords == 0u && cb >= tb0 * (uint32_t)kCountTile && cb < tb1 * (uint32_t)kCountTile;
             uint32_t bf, bl;
             sel_resolve_cell(lv, ss, c, nb1, candCap, publish, s_hbuf, sm.rs, bf, bl);
             sel_bin_bounds(bf, bl, nb1, fLo, fHi);
@@ -432,7 +441,8 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
 // multiple of 32 and divides 2048.
 // vals[K]: the candidates; `base`: particles of the cell known to be smaller than every candidate; `outer*`: the
 // HIST pass' bin function and candidate bins (hasOuter = 0 when vals is the whole cell).
-// Writes the cell's result (margins, iter, found, nleft) or flags it; nothing else is written for a flagged cell.
+// Writes the cell's result (margins, iter, found, nleft) and returns true, or flags it and returns false (block-
+// uniform); nothing else is written for a flagged cell.
 // =====================================================================================
 struct SelSearchSmem {
     float wmin[32], wmax[32];
@@ -443,7 +453,7 @@ struct SelSearchSmem {
     int needFinal;
 };
 
-__device__ __forceinline__ void sel_block_search(const float *vals, uint32_t K, uint32_t base, int hasOuter, float lo1,
+__device__ __forceinline__ bool sel_block_search(const float *vals, uint32_t K, uint32_t base, int hasOuter, float lo1,
                                                  float scale1, int nb1, int bfirst, int blast, uint32_t *hist2, float *amb,
                                                  const LevelState &lv, const SelState &ss, const SelCtl &sc, uint32_t c,
                                                  int hbmPasses, SelSearchSmem &sm, unsigned long long *dbg = nullptr) {
@@ -531,7 +541,7 @@ __device__ __forceinline__ void sel_block_search(const float *vals, uint32_t K, 
     const bool tooMany = !(first <= last) || K2 > (uint32_t)kSelAmbCap;
     if (tooMany) {   // massive ties: leave the cell to the iterative path
         if (tid == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
-        return;
+        return false;
     }
     for (uint32_t i = tid; i < K; i += nThreads) {
         const float v = vals[i];
@@ -584,7 +594,7 @@ __device__ __forceinline__ void sel_block_search(const float *vals, uint32_t K, 
     const int needFinal = sm.needFinal;
     if (needFinal == 2) {   // final cut outside the candidate bins: its exact count is not known here
         if (tid == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
-        return;
+        return false;
     }
     if (needFinal == 1) {
         const float cutf = sm.cutf;
@@ -609,6 +619,7 @@ __device__ __forceinline__ void sel_block_search(const float *vals, uint32_t K, 
         atomicMax(sc.level_iters, it);
         if (!fnd) atomicAdd(sc.n_unfound_out, 1u);
     }
+    return true;
 }
 
 // dynamic shared memory of the two search kernels: vals[cap + 4] | hist2[kSelBins2] | amb[kSelAmbCap]
@@ -690,8 +701,9 @@ struct SelPerCellSmem {
     uint32_t base, end, nlist;
 };
 
-// apply f(value) to every element of src[0..K): 16-byte loads where src is aligned, four loads in flight per thread
-template <typename F>
+// apply f(value) to every element of src[0..K): 16-byte loads where src is aligned, U loads in flight per thread
+// (a block that has an SM to itself needs U = 8 to keep enough bytes in flight for its share of the HBM bandwidth)
+template <int U, typename F>
 __device__ __forceinline__ void sel_for_each(const float *__restrict__ src, uint32_t K, F f) {
     const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
     const uint32_t head = mis ? min(4u - mis, K) : 0u;
@@ -699,10 +711,12 @@ __device__ __forceinline__ void sel_for_each(const float *__restrict__ src, uint
     const float4 *g4 = reinterpret_cast<const float4 *>(src + head);
     const uint32_t nT = blockDim.x;
     uint32_t i = threadIdx.x;
-    for (; i + 3u * nT < body4; i += 4u * nT) {
-        const float4 a = __ldg(g4 + i), b = __ldg(g4 + i + nT), c = __ldg(g4 + i + 2u * nT), d = __ldg(g4 + i + 3u * nT);
-        f(a.x); f(a.y); f(a.z); f(a.w); f(b.x); f(b.y); f(b.z); f(b.w);
-        f(c.x); f(c.y); f(c.z); f(c.w); f(d.x); f(d.y); f(d.z); f(d.w);
+    for (; i + (uint32_t)(U - 1) * nT < body4; i += (uint32_t)U * nT) {
+        float4 q[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) q[u] = __ldg(g4 + i + (uint32_t)u * nT);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { f(q[u].x); f(q[u].y); f(q[u].z); f(q[u].w); }
     }
     for (; i < body4; i += nT) { const float4 a = __ldg(g4 + i); f(a.x); f(a.y); f(a.z); f(a.w); }
     if (threadIdx.x < head) f(__ldg(src + threadIdx.x));
@@ -710,7 +724,7 @@ __device__ __forceinline__ void sel_for_each(const float *__restrict__ src, uint
     if (tail0 + threadIdx.x < K) f(__ldg(src + tail0 + threadIdx.x));
 }
 
-template <int THREADS, int MINBLOCKS>
+template <int THREADS, int MINBLOCKS, int U = 4>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float *__restrict__ x, const float *__restrict__ y,
                                                                     const float *__restrict__ z, LevelState lv, SelState ss,
                                                                     SelCtl sc, uint32_t nCells, uint32_t candCap) {
@@ -737,7 +751,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float 
         if (tid == 0) { sm.first = nb; sm.last = -1; sm.base = 0u; sm.end = 0u; sm.nlist = 0u; }
         __syncthreads();
         // ---- HIST ----
-        sel_for_each(col, K, [&](float v) {
+        sel_for_each<U>(col, K, [&](float v) {
             const float t = fminf(fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f), nbm1);      // == sel_bin(v, lo, scale, nb)
             atomicAdd(&hist[__float2int_rz(t)], 1u);
         });
@@ -790,13 +804,122 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float 
         // ---- COMPACT: second read (L2), candidates into shared memory ----
         float fLo, fHi;
         sel_bin_bounds((uint32_t)first, (uint32_t)last, nb, fLo, fHi);
-        sel_for_each(col, K, [&](float v) {
+        sel_for_each<U>(col, K, [&](float v) {
             const float t = fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f);
             if (t >= fLo && t < fHi) list[atomicAdd(&sm.nlist, 1u)] = v;
         });
         __syncthreads();
         // ---- FINISH ----
         sel_block_search(list, K2, base, 1, lo, scale, nb, first, last, hist, amb, lv, ss, sc, c, 2, sm.search);
+    }
+}
+
+// =====================================================================================
+// Several ranks (particles sharded).  The search needs only two exchanges per level:
+//   HIST (local rows)  ->  allreduce of the histogram rows  ->  COMPACT with the global rows (every rank resolves the
+//   same candidate bins; its own candidates go into the cell's fixed-size slot)  ->  k_selmr_prep (publishes the
+//   resolve result of EVERY cell, also of cells without local particles, the local count below the candidate bins
+//   and the slot's count word)  ->  all-gather of the slots  ->  k_selmr_finish: the same block search as on one rank,
+//   over the candidates of all ranks, so every rank replays the reference's decisions on identical data and ends with
+//   bit-identical margins / iterations / global counts; the local left count (the partition's split offset) is
+//   loc_base + #{own candidates < final cut}.
+// Everything that decides whether a cell is flagged derives from exchanged data, so all ranks flag the same cells.
+// =====================================================================================
+struct SelMrState {
+    const uint32_t *hist_l;   // [nCells][nb1] this rank's histogram rows (the allreduce input)
+    uint32_t *loc_base;       // [nCells] local particles in bins below the candidate bins
+    float *slots_l;           // [nCells][slotWords] own candidates; word slotWords-1 = their count (uint32 bits)
+    const float *slots_g;     // [nRanks][nCells][slotWords] all ranks' slots after the all-gather
+    uint32_t slotWords;
+    int nRanks, self;
+};
+
+__global__ void __launch_bounds__(kThreads) k_selmr_prep(LevelState lv, SelState ss /* hist = global rows */, SelMrState mr,
+                                                          uint32_t nCells, int nb1, uint32_t candCap) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    uint32_t *hbuf = reinterpret_cast<uint32_t *>(sel_smem);
+    __shared__ SelResolveSmem rs;
+    __shared__ uint32_t s_red[kWarps];
+    pdl_enter();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
+        uint32_t *cntWord = reinterpret_cast<uint32_t *>(mr.slots_l + (size_t)c * mr.slotWords + (mr.slotWords - 1u));
+        if (!lv.active[c]) {          // block-uniform
+            if (tid == 0) { ss.flag[c] = 0u; *cntWord = 0u; mr.loc_base[c] = 0u; }
+            continue;
+        }
+        uint32_t bf, bl;
+        sel_resolve_cell(lv, ss, c, nb1, candCap, true, hbuf, rs, bf, bl);
+        uint32_t s = 0;
+        if (bf <= bl) for (uint32_t i = tid; i < bf; i += kThreads) s += __ldcg(mr.hist_l + (size_t)c * nb1 + i);
+        s = __reduce_add_sync(0xffffffffu, s);
+        if (lane == 0) s_red[warp] = s;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) t += s_red[w];
+            mr.loc_base[c] = t;
+            *cntWord = __ldcg(&ss.cursor[c]);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_selmr_finish(LevelState lv, SelState ss, SelCtl sc, SelMrState mr, uint32_t nCells,
+                                                       int nb1, uint32_t cap, int *__restrict__ err) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    float *sbuf = reinterpret_cast<float *>(sel_smem);
+    uint32_t *hist2 = reinterpret_cast<uint32_t *>(sbuf + cap + 4);
+    float *amb = reinterpret_cast<float *>(hist2 + kSelBins2);
+    __shared__ SelSearchSmem sm;
+    __shared__ uint32_t s_cnt[kMaxPeers];
+    __shared__ uint32_t s_nl;
+    pdl_enter();
+    const int tid = threadIdx.x, lane = tid & 31, nThreads = (int)blockDim.x;
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(sc.passes_out, 2);
+    for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
+        __syncthreads();
+        const uint32_t act = lv.active[c];
+        const uint32_t flg = __ldcg(&ss.flag[c]), K = __ldcg(&ss.ncand[c]), base = __ldcg(&ss.base[c]);
+        const uint32_t bf = __ldcg(&ss.bfirst[c]), bl = __ldcg(&ss.blast[c]);
+        const float L = lv.mL[c], R = lv.mR[c];
+        if (tid == 0) { ss.cursor[c] = 0u; s_nl = 0u; }      // the count word was taken by k_selmr_prep
+        if (!act || flg) continue;                          // flagged by the resolve: already counted
+        if (tid < mr.nRanks)
+            s_cnt[tid] = __float_as_uint(__ldcg(mr.slots_g + ((size_t)tid * nCells + c) * mr.slotWords + (mr.slotWords - 1u)));
+        __syncthreads();
+        uint32_t sum = 0;
+        bool over = false;
+        for (int r = 0; r < mr.nRanks; ++r) { over |= s_cnt[r] > mr.slotWords - 1u; sum += s_cnt[r]; }
+        if (over) {        // some rank's candidates did not fit its slot: every rank sees it, the iterative search takes the cell
+            if (tid == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
+            continue;
+        }
+        if (sum != K || K > cap) {   // cannot happen: all ranks bin with the same function and resolve the same rows
+            if (tid == 0) atomicExch(err, ORB_ERR_STATE);
+            continue;
+        }
+        uint32_t off = 0;
+        for (int r = 0; r < mr.nRanks; ++r) {
+            const float *src = mr.slots_g + ((size_t)r * nCells + c) * mr.slotWords;
+            const uint32_t n = s_cnt[r];
+            for (uint32_t i = tid; i < n; i += nThreads) sbuf[off + i] = __ldcg(src + i);
+            off += n;
+        }
+        __syncthreads();
+        const bool done = sel_block_search(sbuf, K, base, 1, L, sel_scale(L, R, nb1), nb1, (int)bf, (int)bl, hist2, amb, lv, ss, sc, c, 2, sm);
+        __syncthreads();
+        if (!done) continue;
+        // local left count at the final cut: getCut() of the final margins is the found cut as well as the capped cell's cut
+        const float cutf = mid_cut(lv.mL[c], lv.mR[c]);
+        const float *mine = mr.slots_g + ((size_t)mr.self * nCells + c) * mr.slotWords;
+        uint32_t n = 0;
+        for (uint32_t i = tid; i < s_cnt[mr.self]; i += nThreads) n += (__ldcg(mine + i) < cutf) ? 1u : 0u;
+        n = __reduce_add_sync(0xffffffffu, n);
+        if (lane == 0 && n) atomicAdd(&s_nl, n);
+        __syncthreads();
+        if (tid == 0) lv.nleft_l[c] = mr.loc_base[c] + s_nl;
     }
 }
 

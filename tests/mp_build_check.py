@@ -44,6 +44,19 @@ def known_answer_summary(out, rank, heap, st, rng, before, after):
     (out / f"known{rank}.json").write_text(json.dumps(rec))
 
 
+def tie_columns(n, seed=17):
+    """A fifth of the particles share one value near the median on every axis (same recipe as
+    tests/test_gpu_parity.py::test_search_fallback_on_massive_ties): the selection search has to flag cells."""
+    rng = np.random.default_rng(seed)
+    cols = []
+    for a in range(3):
+        v = (rng.random(n, dtype=np.float32) - 0.5).astype(np.float32)
+        tie = rng.random(n) < 0.2
+        v[tie] = np.float32(0.01 * (a + 1))
+        cols.append(v)
+    return cols
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -57,7 +70,11 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_local, d = (1 << x_log2) // world, 1 << y_log2
     lo, _ = od.shard_slice(rank, world, n_local)
-    x, y, z = orb.generate_uniform(n_local, skip=lo)
+    ties = len(sys.argv) > 5 and sys.argv[5] == "ties"
+    if ties:
+        x, y, z = (col[lo:lo + n_local].copy() for col in tie_columns(n_local * world))
+    else:
+        x, y, z = orb.generate_uniform(n_local, skip=lo)
     ctx = orb.Orb(n_local, d, device=local)
     od.connect(ctx, rank, world, device="cuda", peers=peers)
     ctx.upload(x, y, z)
@@ -67,7 +84,9 @@ def main():
     if known:
         known_answer_summary(out, rank, heap, st, rng, (x, y, z), (gx, gy, gz))
     else:
-            np.savez(out / f"rank{rank}.npz", heap=heap.view(np.uint8), rng=rng, x=gx, y=gy, z=gz, iters=np.array(st.iters[:st.n_levels]))
+            np.savez(out / f"rank{rank}.npz", heap=heap.view(np.uint8), rng=rng, x=gx, y=gy, z=gz, iters=np.array(st.iters[:st.n_levels]),
+                 not_found=np.array(st.not_found[:st.n_levels]), fallback=np.array([st.search_fallback_cells]),
+                 passes=np.array(st.passes[:st.n_levels]))
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()

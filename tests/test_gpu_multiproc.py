@@ -35,6 +35,39 @@ def test_two_process_build_matches_sharded_oracle(oracle, tmp_path, peers):
         assert list(got["iters"]) == list(ref["stats"].iters[:len(got["iters"])])
 
 
+@pytest.mark.parametrize("x,y,select_mr", [(20, 3, 1), (17, 5, 1), (18, 8, 0)])
+def test_two_process_selection_search(oracle, tmp_path, x, y, select_mr):
+    """Selection search over two ranks (histogram rows all-reduced, candidates all-gathered) on inputs with thousands
+    of particles tied at the median: flagged cells fall back to the iterative loop on every rank alike; and
+    ORB_SELECT_MR=0 (iterative search everywhere) gives the same tree on plain inputs."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import mp_build_check
+
+    R = 2
+    port = 29700 + (os.getpid() % 200) + x
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={R}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "tests" / "mp_build_check.py"), str(tmp_path), str(x), str(y), "1",
+           "ties" if select_mr else "plain"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, ORB_SELECT_MR=str(select_mr)))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    xs, ys, zs = mp_build_check.tie_columns(1 << x) if select_mr else oracle.generate_uniform(1 << x)
+    ref = oracle.build(xs, ys, zs, 1 << y, ties=oracle.TIES_CANONICAL, n_shards=R)
+    per = (1 << x) // R
+    for rank in range(R):
+        got = np.load(tmp_path / f"rank{rank}.npz")
+        L = len(got["iters"])
+        assert list(got["iters"]) == list(ref["stats"].iters[:L])
+        assert list(got["not_found"]) == list(ref["stats"].not_found[:L])
+        assert got["heap"].tobytes() == ref["heap"].tobytes()
+        assert np.array_equal(got["rng"], ref["ranges"][rank])
+        for name in "xyz":
+            assert np.array_equal(got[name].view(np.uint32), ref[name][rank * per:(rank + 1) * per].view(np.uint32))
+        assert (int(got["fallback"][0]) > 0) == bool(select_mr)
+
+
 def _torchrun(nproc, port, *args, timeout=1800):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(ROOT / "tests" / "mp_build_check.py"), *[str(a) for a in args]]
