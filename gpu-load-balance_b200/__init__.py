@@ -101,6 +101,8 @@ class PeerInfo(C.Structure):
         ("pid", C.c_int64),
         ("device", C.c_int32),
         ("reserved_", C.c_int32),
+        ("ipc_xchg", C.c_uint8 * 64),
+        ("ptr_xchg", C.c_uint64),
     ]
 
 

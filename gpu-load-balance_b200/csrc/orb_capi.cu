@@ -144,6 +144,7 @@ struct orb_ctx {
     bool select = true;
     int selPerCellMinCells = 64;   // levels with at least this many cells: one block searches a whole cell
     bool selBigBlocks = true;      // ORB_SELECT_BIG_BLOCKS=0: no 1024 x 1 / 512 x 2 variants of k_sel_percell
+    int selBinAvg = 16384;         // ORB_SELECT_BIN_AVG: HIST bins per cell are doubled (512..8192) until a bin holds at most this many particles on average
     int selT512MinAvg = 32768;     // ORB_SELECT_T512_MIN: cells of at least this many particles get 512-thread blocks
     bool pdl = true;               // programmatic dependent launch between the small kernels of a level
     orb::SelState sel{};
@@ -164,10 +165,15 @@ struct orb_ctx {
     // selection search over several ranks (k_selmr_* in orb_select.cuh): global histogram rows, candidate slots
     bool selectMr = true;              // ORB_SELECT_MR=0: iterative search on every multi-rank level
     uint64_t nLocalMin = 0, nGlobal = 0;   // over ranks; every decision that shapes a collective uses these only
-    uint32_t *d_sel_hist_g = nullptr;  // [selHistWords]
+    uint32_t *d_sel_hist_g = nullptr;  // [selHistWords] NCCL transport: rows summed over ranks
     uint32_t *d_sel_locbase = nullptr; // [maxLevelCells]
-    float *d_slots_l = nullptr;        // [kSelSlotWordsTotal]
-    float *d_slots_g = nullptr;        // [nRanks][kSelSlotWordsTotal]
+    float *d_slots_l = nullptr;        // [kSelSlotWordsTotal] (inside the exchange arena)
+    float *d_slots_g = nullptr;        // [nRanks][kSelSlotWordsTotal] NCCL transport: all-gathered slots
+    // exchange arena mapped by every rank (peer transport): flags[64] | cursor[L] | slots | histogram rows
+    uint32_t *d_xchg = nullptr;
+    uint32_t xOffCursor = 0, xOffSlots = 0, xOffHist = 0;   // word offsets, identical on all ranks
+    uint32_t *peerX[orb::kMaxPeers] = {nullptr};
+    uint32_t xSeq = 0;                 // exchanges issued so far (same on all ranks)
     std::vector<int> extraPasses;      // passes of the iterative fallback per level (host-driven on several ranks)
 
     // fused combine+update over NVLink peer memory (optional; see PeerSet in orb_kernels.cuh)
@@ -528,7 +534,7 @@ SelPlan sel_plan(const orb_ctx *c, uint32_t nCells) {
     else if (c->selBigBlocks && nCells <= 2u * (uint32_t)c->nSM) { p.variant = 1; p.threads = 512; }
     p.cellCap = avg >= 65536 ? 8192u : 4096u;
     p.nb1 = orb::kSelBinsMin;
-    while (p.nb1 < orb::kSelBinsMax && avg / (uint64_t)p.nb1 > 16384) p.nb1 <<= 1;
+    while (p.nb1 < orb::kSelBinsMax && avg / (uint64_t)p.nb1 > (uint64_t)c->selBinAvg) p.nb1 <<= 1;
     p.rep = p.nb1 <= 512 ? 4 : (p.nb1 <= 1024 ? 2 : 1);
     p.histWords = p.cellsInSmem ? 0 : (size_t)nCells * (size_t)p.nb1;
     // candidates one block will stage per cell: a few bins' worth; cells beyond it go to the iterative search
@@ -580,7 +586,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
             const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 4));
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                          nCells, nL, nTiles, nb1, rep, candCap, dbgBase, (float *)nullptr, 0u));
+                          nCells, nL, nTiles, nb1, rep, candCap, dbgBase, (float *)nullptr, 0u, 0));
             if ((rc = count_event_end(c))) return rc;
         }
         {
@@ -591,7 +597,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
                           nCells, nL, nTiles, nb1, 1, candCap, dbgBase ? dbgBase + (size_t)kDbgBlocks * 4 : (unsigned long long *)nullptr,
-                          (float *)nullptr, 0u));
+                          (float *)nullptr, 0u, 0));
             if ((rc = count_event_end(c))) return rc;
         }
         {
@@ -660,7 +666,7 @@ SelMrPlan sel_plan_mr(const orb_ctx *c, uint32_t nCells, int M) {
         return p;
     const uint64_t gavg = c->nGlobal / nCells, lavg = std::max<uint64_t>(c->nGlobal / c->nRanks, c->nLocalMin) / nCells;
     p.nb1 = orb::kSelBinsMin;
-    while (p.nb1 < orb::kSelBinsMax && gavg / (uint64_t)p.nb1 > 16384) p.nb1 <<= 1;
+    while (p.nb1 < orb::kSelBinsMax && gavg / (uint64_t)p.nb1 > (uint64_t)c->selBinAvg) p.nb1 <<= 1;
     p.rep = p.nb1 <= 512 ? 4 : (p.nb1 <= 1024 ? 2 : 1);
     p.histWords = (size_t)nCells * (size_t)p.nb1;
     p.candCap = (uint32_t)std::min<uint64_t>(kSelValsCap, 4 * (gavg / (uint64_t)p.nb1) + 4096);
@@ -675,14 +681,17 @@ SelMrPlan sel_plan_mr(const orb_ctx *c, uint32_t nCells, int M) {
     return p;
 }
 
+// Enqueues the level's search up to the finish kernel; no host synchronisation.  The finish kernel's last block
+// reports 1 + (cells flagged) in h_status[slotBase + kPassSlots - 1] (see select_mr_flagged).
 int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int slotBase, int levelIdx) {
     using namespace orb;
     const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
     float *cand = c->x[c->cur ^ 1];
+    const bool peer = c->peerEnabled && c->peerX[c->rank] != nullptr;
     SelState ss = c->sel;                       // hist = this rank's rows
     ss.n_flagged = c->d_sel_nflag + levelIdx;
     SelState sg = ss;
-    sg.hist = c->d_sel_hist_g;                  // rows summed over ranks
+    sg.hist = c->d_sel_hist_g;                  // NCCL transport: rows summed over ranks
     SelCtl sc;
     sc.active_particles = c->d_active_particles;
     sc.level_iters = c->d_level_iters + levelIdx;
@@ -696,11 +705,22 @@ int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int
     mr.slotWords = pl.slotWords;
     mr.nRanks = c->nRanks;
     mr.self = c->rank;
+    mr.done = c->d_cdone + slotBase + kPassSlots - 1;
+    mr.h_status = (volatile uint32_t *)(c->h_status_dev + slotBase + kPassSlots - 1);
+    SelPeers px;
+    memset(&px, 0, sizeof(px));
+    if (peer) {
+        px.n = c->nRanks;
+        px.self = c->rank;
+        for (int r = 0; r < c->nRanks; ++r) px.arena[r] = c->peerX[r];
+        px.offCursor = c->xOffCursor; px.offSlots = c->xOffSlots; px.offHist = c->xOffHist;
+    }
     int rc;
     const int nb1 = pl.nb1;
     const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
     const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
     const uint32_t nL = (uint32_t)c->nLocal;
+    // ---- HIST: this rank's rows (cleared by level_prepare) ----
     if (nTiles) {
         const size_t smem = ringBytes + (size_t)nb1 * pl.rep * 4;
         int occ = 1;
@@ -708,67 +728,91 @@ int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int
         const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 4));
         if ((rc = count_event_begin(c))) return rc;
         CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                      nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u));
+                      nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u, 0));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     }
-    NK(g_nccl.AllReduce(c->sel.hist, c->d_sel_hist_g, pl.histWords, ncclUint32, ncclSum, c->comm, c->stream));
+    // ---- exchange 1: rows over ranks, resolve ----
+    if (peer) {
+        px.seq = ++c->xSeq;
+        const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * 4u);
+        if ((rc = aux_begin(c, "mr_resolve", levelIdx))) return rc;
+        CK(launch_pdl(c, k_selx_resolve, dim3(grid), dim3(kThreads), (size_t)nb1 * 4, c->lv, ss, mr, px, nCells, nb1, pl.candCap));
+        if ((rc = aux_end(c))) return rc;
+        c->nOtherLaunch++;
+    } else {
+        NK(g_nccl.AllReduce(c->sel.hist, c->d_sel_hist_g, pl.histWords, ncclUint32, ncclSum, c->comm, c->stream));
+    }
+    // ---- COMPACT: own candidates into the cells' slots ----
     if (nTiles) {
         const size_t smem = ringBytes + (size_t)kWarps * kSelWarpStage * 4 + (size_t)nb1 * 4;
         int occ = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelCompact>, kThreads, smem));
         const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 3));
         if ((rc = count_event_begin(c))) return rc;
-        CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, sg, (const uint32_t *)c->d_tile_first,
-                      nCells, nL, nTiles, nb1, 1, pl.candCap, (unsigned long long *)nullptr, c->d_slots_l, pl.slotWords));
+        CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, peer ? ss : sg,
+                      (const uint32_t *)c->d_tile_first, nCells, nL, nTiles, nb1, 1, pl.candCap, (unsigned long long *)nullptr,
+                      c->d_slots_l, pl.slotWords, peer ? 1 : 0));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     }
-    {
+    // ---- exchange 2: candidates over ranks, block search ----
+    if (!peer) {
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * 8u);
         if ((rc = aux_begin(c, "mr_prep", levelIdx))) return rc;
         CK(launch_pdl(c, k_selmr_prep, dim3(grid), dim3(kThreads), (size_t)nb1 * 4, c->lv, sg, mr, nCells, nb1, pl.candCap));
         if ((rc = aux_end(c))) return rc;
         c->nOtherLaunch++;
+        NK(g_nccl.AllGather(c->d_slots_l, c->d_slots_g, (size_t)nCells * pl.slotWords, ncclUint32, c->comm, c->stream));
     }
-    NK(g_nccl.AllGather(c->d_slots_l, c->d_slots_g, (size_t)nCells * pl.slotWords, ncclUint32, c->comm, c->stream));
     {
         const size_t smem = sel_search_smem_bytes(pl.candCap);
         const int threads = nCells <= 2u * (uint32_t)c->nSM ? 1024 : (smem > 112 * 1024 ? 1024 : (smem > 56 * 1024 ? 512 : 256));
+        auto kern = peer ? k_selmr_finish<true> : k_selmr_finish<false>;
         int occ = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_selmr_finish, threads, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
+        if (peer) px.seq = ++c->xSeq;
         if ((rc = aux_begin(c, "mr_finish", levelIdx))) return rc;
-        CK(launch_pdl(c, k_selmr_finish, dim3(grid), dim3(threads), smem, c->lv, sg, sc, mr, nCells, nb1, pl.candCap, c->d_err));
+        CK(launch_pdl(c, kern, dim3(grid), dim3(threads), smem, c->lv, peer ? ss : sg, sc, mr, px, nCells, nb1, pl.candCap, c->d_err));
         if ((rc = aux_end(c))) return rc;
         c->nUpdateLaunch++;
     }
     CK(cudaGetLastError());
-    // cells the search left over (the same on every rank): read the count, run the iterative loop for them
-    if ((rc = ensure_scratch(c, 64))) return rc;
-    CK(cudaMemcpyAsync(c->h_scratch, c->d_sel_nflag + levelIdx, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (c->h_scratch[0]) {
-        int np = 0;
-        if ((rc = run_bisection(c, nCells, 3, slotBase, levelIdx, &np))) return rc;
-        if (np >= (kMaxIter + 2) / 3) {
-            uint32_t nu = 0;
-            if ((rc = finalize_unfound(c, nCells, &nu))) return rc;
-            // nu counts every cell of the level without a found cut (also those the selection search itself capped):
-            // it replaces the device-side statistic of the level
-            c->h_scratch[1] = nu;
-            CK(cudaMemcpyAsync(c->d_lvl_unfound + levelIdx, c->h_scratch + 1, 4, cudaMemcpyHostToDevice, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-        }
-        if ((size_t)levelIdx < c->extraPasses.size()) c->extraPasses[levelIdx] = np;
+    return ORB_OK;
+}
+
+// Cells the multi-rank selection search left over at this level (the same number on every rank).  Spins on the
+// mapped status word the finish kernel's last block writes - no stream synchronisation.
+uint32_t select_mr_flagged(orb_ctx *c, int slotBase) {
+    volatile uint32_t *w = c->h_status + slotBase + kPassSlots - 1;
+    uint32_t s;
+    while ((s = *w) == 0u) cpu_relax();
+    return s - 1u;
+}
+
+// iterative loop for the cells the multi-rank selection search flagged (every rank runs it: the flags agree)
+int select_mr_fallback(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx) {
+    int np = 0, rc;
+    if ((rc = run_bisection(c, nCells, 3, slotBase, levelIdx, &np))) return rc;
+    if (np >= (orb::kMaxIter + 2) / 3) {
+        uint32_t nu = 0;
+        if ((rc = finalize_unfound(c, nCells, &nu))) return rc;
+        // nu counts every cell of the level without a found cut (also those the selection search itself capped):
+        // it replaces the device-side statistic of the level
+        if ((rc = ensure_scratch(c, 64))) return rc;
+        c->h_scratch[1] = nu;
+        CK(cudaMemcpyAsync(c->d_lvl_unfound + levelIdx, c->h_scratch + 1, 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
     }
+    if ((size_t)levelIdx < c->extraPasses.size()) c->extraPasses[levelIdx] = np;
     return ORB_OK;
 }
 
 // Stable split of every cell of the level (canonical tie mode).  Kernel choice by average local cell size:
 // cells of at most 16 tiles (and enough of them to fill the GPU) -> one block per cell with a running carry;
 // otherwise persistent tile streaming with decoupled look-back (cooperative launch: all blocks co-resident).
-int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket) {
+int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket, const uint32_t *gate = nullptr) {
     using namespace orb;
     (void)ticket;
     const uint32_t nTiles = ceil_div(c->nLocal, kPartTile);
@@ -793,13 +837,13 @@ int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket) {
     const size_t smem = sizeof(PartSmem);
     if (avg <= 16ull * kPartTile && nCells >= 2u * (uint32_t)c->nSM) {
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)c->occPartCells);
-        k_partition_cells<<<grid, kThreads, smem, c->stream>>>(x, y, z, x2, y2, z2, c->lv, c->d_final_cut, nCells, (uint32_t)c->nLocal);
+        k_partition_cells<<<grid, kThreads, smem, c->stream>>>(x, y, z, x2, y2, z2, c->lv, c->d_final_cut, nCells, (uint32_t)c->nLocal, gate);
     } else {
         const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)c->occPartStream);
         uint32_t nLocal32 = (uint32_t)c->nLocal, nT = nTiles, nC = nCells;
         void *args[] = {(void *)&x, (void *)&y, (void *)&z, (void *)&x2, (void *)&y2, (void *)&z2, (void *)&c->lv,
                         (void *)&c->d_final_cut, (void *)&c->d_tile_first, (void *)&nC, (void *)&nLocal32, (void *)&nT,
-                        (void *)&c->d_blk_left, (void *)&c->d_blk_restart};
+                        (void *)&c->d_blk_left, (void *)&c->d_blk_restart, (void *)&gate};
         CK(cudaLaunchCooperativeKernel((const void *)k_partition_coop, dim3(grid), dim3(kThreads), args, smem, c->stream));
     }
     if (c->profile) CK(cudaEventRecord(e1, c->stream));
@@ -973,15 +1017,24 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaMalloc(&c->d_lvl_unfound, sizeof(uint32_t) * kMaxLevels));
     {
         c->selHistWords = (size_t)n_local / 16 + 2 * (size_t)orb::kSelBinsMax;
-        CK(cudaMalloc(&c->sel.hist, c->selHistWords * 4));
+        {   // exchange arena: one allocation so that one IPC handle maps all of it; offsets do not depend on n_local
+            const size_t Lr = (L + 63) & ~(size_t)63;
+            c->xOffCursor = 64;
+            c->xOffSlots = (uint32_t)(64 + Lr);
+            c->xOffHist = (uint32_t)(64 + Lr + kSelSlotWordsTotal);
+            const size_t words = (size_t)c->xOffHist + c->selHistWords;
+            CK(cudaMalloc(&c->d_xchg, words * 4));
+            CK(cudaMemset(c->d_xchg, 0, words * 4));
+            c->sel.cursor = c->d_xchg + c->xOffCursor;
+            c->d_slots_l = reinterpret_cast<float *>(c->d_xchg + c->xOffSlots);
+            c->sel.hist = c->d_xchg + c->xOffHist;
+        }
         CK(cudaMalloc(&c->sel.bfirst, L * 4));
         CK(cudaMalloc(&c->sel.blast, L * 4));
         CK(cudaMalloc(&c->sel.base, L * 4));
         CK(cudaMalloc(&c->sel.ncand, L * 4));
-        CK(cudaMalloc(&c->sel.cursor, L * 4));
         CK(cudaMalloc(&c->sel.flag, L * 4));
         CK(cudaMemset(c->sel.flag, 0, L * 4));
-        CK(cudaMemset(c->sel.cursor, 0, L * 4));
         CK(cudaMalloc(&c->d_sel_nflag, sizeof(uint32_t) * kMaxLevels));
         CK(cudaMemset(c->d_sel_nflag, 0, sizeof(uint32_t) * kMaxLevels));
         const int ringBytes = orb::kCountStages * orb::kCountTile * (int)sizeof(float);
@@ -992,7 +1045,8 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occSelStream[1], orb::k_sel_stream<orb::kSelCompact>, orb::kThreads, compBytes));
         const int searchBytes = (int)orb::sel_search_smem_bytes(kSelValsCap);
         CK(cudaFuncSetAttribute(orb::k_sel_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
-        CK(cudaFuncSetAttribute(orb::k_selmr_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
+        CK(cudaFuncSetAttribute(orb::k_selmr_finish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
+        CK(cudaFuncSetAttribute(orb::k_selmr_finish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
         CK(cudaFuncSetAttribute(orb::k_sel_percell<512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
         CK(cudaFuncSetAttribute(orb::k_sel_percell<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
         CK(cudaFuncSetAttribute(orb::k_sel_percell<512, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
@@ -1053,6 +1107,8 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     if (spc && atoi(spc) >= 1) c->selPerCellMinCells = atoi(spc);
     const char *sbb = getenv("ORB_SELECT_BIG_BLOCKS");
     if (sbb) c->selBigBlocks = atoi(sbb) != 0;
+    const char *sba = getenv("ORB_SELECT_BIN_AVG");
+    if (sba && atoi(sba) >= 64) c->selBinAvg = atoi(sba);
     const char *st5 = getenv("ORB_SELECT_T512_MIN");
     if (st5 && atoi(st5) >= 1) c->selT512MinAvg = atoi(st5);
     const char *se = getenv("ORB_SELECT");
@@ -1087,9 +1143,12 @@ int orb_destroy(orb_ctx *c) {
     cudaFree(c->lv.compL); cudaFree(c->lv.compR); cudaFree(c->lv.base_l); cudaFree(c->lv.tile_ncand);
     if (c->d_cnt_g_buf) cudaFree(c->d_cnt_g_buf);
     cudaFree(c->d_dbg); cudaFree(c->d_dbg_blocks);
-    cudaFree(c->sel.hist); cudaFree(c->sel.bfirst); cudaFree(c->sel.blast); cudaFree(c->sel.base); cudaFree(c->sel.ncand);
-    cudaFree(c->sel.cursor); cudaFree(c->sel.flag); cudaFree(c->d_sel_nflag);
-    cudaFree(c->d_sel_hist_g); cudaFree(c->d_sel_locbase); cudaFree(c->d_slots_l); cudaFree(c->d_slots_g);
+    cudaFree(c->sel.bfirst); cudaFree(c->sel.blast); cudaFree(c->sel.base); cudaFree(c->sel.ncand);
+    cudaFree(c->sel.flag); cudaFree(c->d_sel_nflag);
+    cudaFree(c->d_sel_hist_g); cudaFree(c->d_sel_locbase); cudaFree(c->d_slots_g);
+    for (int r = 0; r < orb::kMaxPeers; ++r)
+        if (c->peerIpc[r] && c->peerX[r]) cudaIpcCloseMemHandle(c->peerX[r]);
+    cudaFree(c->d_xchg);
     for (int r = 0; r < orb::kMaxPeers; ++r)
         if (c->peerIpc[r]) { cudaIpcCloseMemHandle(c->peerCnt[r]); cudaIpcCloseMemHandle(c->peerFlag[r]); }
     cudaFree(c->d_lvl_passes); cudaFree(c->d_lvl_unfound); cudaFree(c->d_cdone); cudaFree(c->d_peer_cnt); cudaFree(c->d_peer_flag);
@@ -1158,7 +1217,6 @@ static int setup_multi(orb_ctx *c) {
         if (!c->d_sel_hist_g) {
             CK(cudaMalloc(&c->d_sel_hist_g, c->selHistWords * 4));
             CK(cudaMalloc(&c->d_sel_locbase, (size_t)c->maxLevelCells * 4));
-            CK(cudaMalloc(&c->d_slots_l, kSelSlotWordsTotal * 4));
             CK(cudaMalloc(&c->d_slots_g, kSelSlotWordsTotal * 4 * (size_t)c->nRanks));
         }
     }
@@ -1201,8 +1259,11 @@ int orb_peer_export(orb_ctx *c, orb_peer_info *out) {
     memcpy(out->ipc_cnt, &h, 64);
     CK(cudaIpcGetMemHandle(&h, c->d_peer_flag));
     memcpy(out->ipc_flag, &h, 64);
+    CK(cudaIpcGetMemHandle(&h, c->d_xchg));
+    memcpy(out->ipc_xchg, &h, 64);
     out->ptr_cnt = (uint64_t)(uintptr_t)c->d_peer_cnt;
     out->ptr_flag = (uint64_t)(uintptr_t)c->d_peer_flag;
+    out->ptr_xchg = (uint64_t)(uintptr_t)c->d_xchg;
     out->pid = (int64_t)getpid();
     out->device = c->device;
     return ORB_OK;
@@ -1216,6 +1277,7 @@ int orb_peer_import(orb_ctx *c, const orb_peer_info *all, int n_ranks) {
         if (r == c->rank) {
             c->peerCnt[r] = c->d_peer_cnt;
             c->peerFlag[r] = c->d_peer_flag;
+            c->peerX[r] = c->d_xchg;
         } else if (all[r].pid == (int64_t)getpid()) {
             // same process (thread-per-GPU host): plain pointers + peer access
             int can = 0;
@@ -1226,6 +1288,7 @@ int orb_peer_import(orb_ctx *c, const orb_peer_info *all, int n_ranks) {
             cudaGetLastError();
             c->peerCnt[r] = (uint32_t *)(uintptr_t)all[r].ptr_cnt;
             c->peerFlag[r] = (uint32_t *)(uintptr_t)all[r].ptr_flag;
+            c->peerX[r] = (uint32_t *)(uintptr_t)all[r].ptr_xchg;
         } else {
             cudaIpcMemHandle_t h;
             void *p = nullptr;
@@ -1235,6 +1298,9 @@ int orb_peer_import(orb_ctx *c, const orb_peer_info *all, int n_ranks) {
             memcpy(&h, all[r].ipc_flag, 64);
             CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
             c->peerFlag[r] = (uint32_t *)p;
+            memcpy(&h, all[r].ipc_xchg, 64);
+            CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            c->peerX[r] = (uint32_t *)p;
             c->peerIpc[r] = true;
         }
     }
@@ -1509,10 +1575,16 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         if (rc) return rc;
         int np = 0;
         uint32_t nu = 0;
+        bool speculate = false;     // split + partition enqueued behind the search before its flag count is known
         if (mrPlan.ok) {
             rc = launch_level_select_mr(c, nCells, mrPlan, slot, l - 1);
             if (rc) return rc;
             np = -1;
+            speculate = c->tieMode != 1;
+            if (!speculate && select_mr_flagged(c, slot)) {
+                rc = select_mr_fallback(c, nCells, slot, l - 1);
+                if (rc) return rc;
+            }
         } else if (useSelect) {
             rc = launch_level_select(c, nCells, slot, l - 1);
             if (rc) return rc;
@@ -1538,11 +1610,21 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             rc = launch_partition_hoare(c, nCells);
             if (rc) return rc;
         }
-        CK(launch_pdl(c, k_split, dim3(ceil_div(nCells, 256)), dim3(256), 0, c->d_heap, first, nCells, c->lv, c->d_range, c->d_total, c->d_final_cut));
-        c->nOtherLaunch++;
-        if (c->tieMode != 1) {
-            rc = launch_partition(c, nCells, c->d_tickets + (l - 1));
+        // multi-rank selection search: split and partition go out gated on the level's flag count, the host looks at
+        // the count afterwards; only if cells were flagged it runs the iterative loop and enqueues both again
+        const uint32_t *gate = speculate ? c->d_sel_nflag + (l - 1) : nullptr;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            CK(launch_pdl(c, k_split, dim3(ceil_div(nCells, 256)), dim3(256), 0, c->d_heap, first, nCells, c->lv, c->d_range, c->d_total, c->d_final_cut, gate));
+            c->nOtherLaunch++;
+            if (c->tieMode != 1) {
+                rc = launch_partition(c, nCells, c->d_tickets + (l - 1), gate);
+                if (rc) return rc;
+            }
+            if (!gate || select_mr_flagged(c, slot) == 0u) break;
+            c->cur ^= 1;                  // the gated partition did nothing: undo the ping-pong flip
+            rc = select_mr_fallback(c, nCells, slot, l - 1);
             if (rc) return rc;
+            gate = nullptr;
         }
         if (tight) {   // children boxes from their particles; needs the children's ranges as a level
             const uint32_t cf = (1u << l) - 1u, cn = 1u << l;

@@ -1281,9 +1281,13 @@ __device__ __forceinline__ void child_axis_margins(orb_cell &ch) {
     ch.cutMarginRight = ch.upper[a];
 }
 
+// `gate` (may be null): the kernel was enqueued before the host knew whether the level's search left cells to the
+// iterative loop; a non-zero word means it did, and the launch does nothing (the host enqueues it again afterwards).
 __global__ void k_split(orb_cell *__restrict__ heap, uint32_t first, uint32_t nCells, LevelState lv,
-                        uint32_t *__restrict__ range, uint32_t *__restrict__ total_by_id, float *__restrict__ final_cut) {
+                        uint32_t *__restrict__ range, uint32_t *__restrict__ total_by_id, float *__restrict__ final_cut,
+                        const uint32_t *__restrict__ gate) {
     pdl_enter();
+    if (gate && *((volatile const uint32_t *)gate) != 0u) return;
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
     orb_cell p = heap[first + c];
@@ -1592,9 +1596,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_partition_coop(const float *__r
                                                                LevelState lv, const float *__restrict__ final_cut,
                                                                const uint32_t *__restrict__ tile_first, uint32_t nCells,
                                                                uint32_t nLocal, uint32_t nTiles, uint32_t *blkLeft,
-                                                               uint32_t *blkRestart) {
+                                                               uint32_t *blkRestart, const uint32_t *__restrict__ gate) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PartSmem &sm = *reinterpret_cast<PartSmem *>(smem_raw);
+    if (gate && *((volatile const uint32_t *)gate) != 0u) return;     // see k_split; uniform over the grid
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tilesPerBlock = (nTiles + gridDim.x - 1) / gridDim.x;
@@ -1726,9 +1731,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_partition_cells(const float *__
                                                                 const float *__restrict__ z, float *__restrict__ x2,
                                                                 float *__restrict__ y2, float *__restrict__ z2,
                                                                 LevelState lv, const float *__restrict__ final_cut,
-                                                                uint32_t nCells, uint32_t nLocal) {
+                                                                uint32_t nCells, uint32_t nLocal, const uint32_t *__restrict__ gate) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PartSmem &sm = *reinterpret_cast<PartSmem *>(smem_raw);
+    if (gate && *((volatile const uint32_t *)gate) != 0u) return;     // see k_split
     for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
         const uint32_t b = lv.bnd[c], e = lv.bnd[c + 1];
         if (e <= b) continue;   // block-uniform

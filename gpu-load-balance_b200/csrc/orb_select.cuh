@@ -140,15 +140,18 @@ struct SelResolveSmem {
     uint32_t base, end;
 };
 __device__ __forceinline__ void sel_resolve_cell(const LevelState &lv, const SelState &ss, uint32_t c, int nb1, uint32_t candCap,
-                                                 bool publish, uint32_t *hbuf, SelResolveSmem &rs, uint32_t &bfOut, uint32_t &blOut) {
+                                                 bool publish, uint32_t *hbuf, SelResolveSmem &rs, uint32_t &bfOut, uint32_t &blOut,
+                                                 bool preloaded = false /* hbuf already holds the row (barrier done by the caller) */) {
     const int tid = threadIdx.x;
     const int per = nb1 / kThreads;          // 2 .. 32
-    __syncthreads();
+    if (!preloaded) __syncthreads();
     if (tid == 0) { rs.first = nb1; rs.last = -1; rs.base = 0u; rs.end = 0u; }
     SelTarget tg;
     tg.init(lv.total[c], lv.nleaf[c]);
-    const uint32_t *g = ss.hist + (size_t)c * nb1;
-    for (int i = tid; i < nb1; i += kThreads) hbuf[i] = __ldcg(g + i);      // coalesced, one latency
+    if (!preloaded) {
+        const uint32_t *g = ss.hist + (size_t)c * nb1;
+        for (int i = tid; i < nb1; i += kThreads) hbuf[i] = __ldcg(g + i);      // coalesced, one latency
+    }
     __syncthreads();
     const uint32_t *h = hbuf + tid * per;
     uint32_t sum = 0;
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, MODE == kSelHist ? 4 : 3)
 k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z, float *__restrict__ cand,
              LevelState lv, SelState ss, const uint32_t *__restrict__ tile_first, uint32_t nCells, uint32_t nLocal,
              uint32_t nTiles, int nb1, int rep, uint32_t candCap, unsigned long long *dbg, float *__restrict__ slots,
-             uint32_t slotWords) {
+             uint32_t slotWords, int preResolved) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     pdl_enter();
     unsigned long long *bs = dbg ? dbg + (size_t)blockIdx.x * 4 : nullptr;      // ORB_DEBUG_TIMES=2: per-block phase stamps
@@ -301,7 +304,8 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
             // (several ranks: k_selmr_prep resolves and publishes every cell, also those without local particles)
             const bool publish = slotWords == 0u && cb >= tb0 * (uint32_t)kCountTile && cb < tb1 * (uint32_t)kCountTile;
             uint32_t bf, bl;
-            sel_resolve_cell(lv, ss, c, nb1, candCap, publish, s_hbuf, sm.rs, bf, bl);
+            if (preResolved) { bf = __ldcg(&ss.bfirst[c]); bl = __ldcg(&ss.blast[c]); }     // k_selx_resolve did it for the level
+            else sel_resolve_cell(lv, ss, c, nb1, candCap, publish, s_hbuf, sm.rs, bf, bl);
             sel_bin_bounds(bf, bl, nb1, fLo, fHi);
         }
     };
@@ -815,25 +819,116 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float 
 }
 
 // =====================================================================================
-// Several ranks (particles sharded).  The search needs only two exchanges per level:
-//   HIST (local rows)  ->  allreduce of the histogram rows  ->  COMPACT with the global rows (every rank resolves the
-//   same candidate bins; its own candidates go into the cell's fixed-size slot)  ->  k_selmr_prep (publishes the
-//   resolve result of EVERY cell, also of cells without local particles, the local count below the candidate bins
-//   and the slot's count word)  ->  all-gather of the slots  ->  k_selmr_finish: the same block search as on one rank,
-//   over the candidates of all ranks, so every rank replays the reference's decisions on identical data and ends with
-//   bit-identical margins / iterations / global counts; the local left count (the partition's split offset) is
-//   loc_base + #{own candidates < final cut}.
+// Several ranks (particles sharded).  The search needs only TWO exchanges per level (the iterative
+// search needs one per bisection pass): the histogram rows are summed over ranks, the candidates are gathered, and
+// every rank runs the same block search over the candidates of all ranks - it replays the reference's decisions on
+// identical data and ends with bit-identical margins / iterations / global counts.  The local left count (the
+// partition's split offset) is #{own particles below the candidate bins} + #{own candidates < final cut}.
 // Everything that decides whether a cell is flagged derives from exchanged data, so all ranks flag the same cells.
+//
+// Two transports:
+//  * NVLink peer memory (SelPeers; default when the peer table is imported): no collective call at all.  Every rank
+//    keeps its histogram rows, candidate slots and slot fill levels in an exchange arena that all ranks map.
+//      HIST -> k_selx_resolve [signal + wait: all ranks' HIST done; block per cell sums the rows of all ranks with
+//      remote loads, resolves, publishes] -> COMPACT (reads the published bins, own candidates into the cell's slot)
+//      -> k_selmr_finish<true> [signal + wait: all ranks' COMPACT done; block per cell pulls the candidates of all
+//      ranks straight out of their slots, searches].
+//    The signal is a remote store of the exchange's sequence number into every peer's flag word, issued by the first
+//    block of the kernel that FOLLOWS the producing kernel in the stream (so the producer has completed); the wait
+//    spins on the rank's own flag words.  One buffer of each kind suffices: a rank overwrites rows / slots / fill
+//    levels of level l only after an exchange that every peer reaches after it has finished reading level l.
+//  * NCCL (peer table not imported): HIST -> allreduce(rows) -> COMPACT (+ per-block resolve) -> k_selmr_prep
+//    (publishes every cell's resolve, the slot's count word) -> all-gather(slots) -> k_selmr_finish<false>.
 // =====================================================================================
+struct SelPeers {
+    int n, self;                  // n == 0: NCCL transport
+    uint32_t seq;                 // sequence number of the kernel's exchange (monotone, identical on all ranks)
+    uint32_t *arena[kMaxPeers];   // every rank's exchange arena: flags[kMaxPeers] | ... (word offsets below, rank-invariant)
+    uint32_t offCursor, offSlots, offHist;
+};
 struct SelMrState {
-    const uint32_t *hist_l;   // [nCells][nb1] this rank's histogram rows (the allreduce input)
+    const uint32_t *hist_l;   // [nCells][nb1] this rank's histogram rows
     uint32_t *loc_base;       // [nCells] local particles in bins below the candidate bins
-    float *slots_l;           // [nCells][slotWords] own candidates; word slotWords-1 = their count (uint32 bits)
-    const float *slots_g;     // [nRanks][nCells][slotWords] all ranks' slots after the all-gather
+    float *slots_l;           // [nCells][slotWords] own candidates (NCCL: word slotWords-1 = their count, uint32 bits)
+    const float *slots_g;     // NCCL: [nRanks][nCells][slotWords] all ranks' slots after the all-gather
     uint32_t slotWords;
     int nRanks, self;
+    uint32_t *done;           // finish: blocks-finished counter of the level (zeroed per build)
+    volatile uint32_t *h_status;   // finish: mapped pinned word, receives 1 + cells flagged at this level
 };
 
+__device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_sys_u4(const uint32_t *p) {
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// Cross-rank barrier at the start of a kernel (after pdl_enter: this rank's preceding kernel has completed).
+__device__ __forceinline__ void selx_barrier(const SelPeers &px) {
+    const int t = threadIdx.x;
+    if (blockIdx.x == 0 && t < px.n && t != px.self) {
+        __threadfence_system();
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(px.arena[t] + px.self), "r"(px.seq) : "memory");
+    }
+    if (t < px.n && t != px.self) {
+        const uint32_t *f = px.arena[px.self] + t;
+        while ((int32_t)(ld_sys_u32(f) - px.seq) < 0) {}
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+// peer transport: rows of all ranks -> resolve of every cell of the level
+__global__ void __launch_bounds__(kThreads) k_selx_resolve(LevelState lv, SelState ss, SelMrState mr, SelPeers px, uint32_t nCells,
+                                                            int nb1, uint32_t candCap) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    uint32_t *hbuf = reinterpret_cast<uint32_t *>(sel_smem);
+    __shared__ SelResolveSmem rs;
+    __shared__ uint32_t s_red[kWarps];
+    pdl_enter();
+    selx_barrier(px);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
+        __syncthreads();
+        // every peer is past its finish of the previous level (it has signalled this exchange): the fill level may go
+        if (tid == 0) ss.cursor[c] = 0u;
+        if (!lv.active[c]) {          // block-uniform
+            if (tid == 0) { ss.flag[c] = 0u; mr.loc_base[c] = 0u; }
+            continue;
+        }
+        const uint32_t *own = mr.hist_l + (size_t)c * nb1;
+        for (int i4 = tid; i4 < nb1 / 4; i4 += kThreads) {
+            uint4 a = __ldcg(reinterpret_cast<const uint4 *>(own) + i4);
+            for (int r = 0; r < px.n; ++r) {
+                if (r == px.self) continue;
+                const uint4 b = ld_sys_u4(px.arena[r] + px.offHist + (size_t)c * nb1 + 4 * i4);
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            reinterpret_cast<uint4 *>(hbuf)[i4] = a;
+        }
+        __syncthreads();
+        uint32_t bf, bl;
+        sel_resolve_cell(lv, ss, c, nb1, candCap, true, hbuf, rs, bf, bl, true);
+        uint32_t s = 0;
+        if (bf <= bl) for (uint32_t i = tid; i < bf; i += kThreads) s += __ldcg(own + i);
+        s = __reduce_add_sync(0xffffffffu, s);
+        if (lane == 0) s_red[warp] = s;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) t += s_red[w];
+            mr.loc_base[c] = t;
+        }
+    }
+}
+
+// NCCL transport: after COMPACT (which resolved per block from the all-reduced rows) publish every cell's resolve,
+// also for cells without local particles, and put the fill level into the slot's count word
 __global__ void __launch_bounds__(kThreads) k_selmr_prep(LevelState lv, SelState ss /* hist = global rows */, SelMrState mr,
                                                           uint32_t nCells, int nb1, uint32_t candCap) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
@@ -866,8 +961,11 @@ __global__ void __launch_bounds__(kThreads) k_selmr_prep(LevelState lv, SelState
     }
 }
 
-__global__ void __launch_bounds__(1024) k_selmr_finish(LevelState lv, SelState ss, SelCtl sc, SelMrState mr, uint32_t nCells,
-                                                       int nb1, uint32_t cap, int *__restrict__ err) {
+// block search over the candidates of all ranks.  PEER: pulled from the ranks' slots over NVLink; else from the
+// all-gathered copy.  The last block to finish reports 1 + (cells flagged at this level) to the host.
+template <bool PEER>
+__global__ void __launch_bounds__(1024) k_selmr_finish(LevelState lv, SelState ss, SelCtl sc, SelMrState mr, SelPeers px,
+                                                       uint32_t nCells, int nb1, uint32_t cap, int *__restrict__ err) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     float *sbuf = reinterpret_cast<float *>(sel_smem);
     uint32_t *hist2 = reinterpret_cast<uint32_t *>(sbuf + cap + 4);
@@ -876,6 +974,7 @@ __global__ void __launch_bounds__(1024) k_selmr_finish(LevelState lv, SelState s
     __shared__ uint32_t s_cnt[kMaxPeers];
     __shared__ uint32_t s_nl;
     pdl_enter();
+    if (PEER) selx_barrier(px);
     const int tid = threadIdx.x, lane = tid & 31, nThreads = (int)blockDim.x;
     if (blockIdx.x == 0 && tid == 0) atomicAdd(sc.passes_out, 2);
     for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
@@ -884,10 +983,15 @@ __global__ void __launch_bounds__(1024) k_selmr_finish(LevelState lv, SelState s
         const uint32_t flg = __ldcg(&ss.flag[c]), K = __ldcg(&ss.ncand[c]), base = __ldcg(&ss.base[c]);
         const uint32_t bf = __ldcg(&ss.bfirst[c]), bl = __ldcg(&ss.blast[c]);
         const float L = lv.mL[c], R = lv.mR[c];
-        if (tid == 0) { ss.cursor[c] = 0u; s_nl = 0u; }      // the count word was taken by k_selmr_prep
-        if (!act || flg) continue;                          // flagged by the resolve: already counted
-        if (tid < mr.nRanks)
-            s_cnt[tid] = __float_as_uint(__ldcg(mr.slots_g + ((size_t)tid * nCells + c) * mr.slotWords + (mr.slotWords - 1u)));
+        if (tid == 0) {
+            s_nl = 0u;
+            if (!PEER) ss.cursor[c] = 0u;      // NCCL: the count word was taken by k_selmr_prep.  PEER: peers still read it
+        }
+        if (!act || flg) continue;              // flagged by the resolve: already counted
+        if (tid < mr.nRanks) {
+            if (PEER) s_cnt[tid] = tid == mr.self ? __ldcg(&ss.cursor[c]) : ld_sys_u32(px.arena[tid] + px.offCursor + c);
+            else s_cnt[tid] = __float_as_uint(__ldcg(mr.slots_g + ((size_t)tid * nCells + c) * mr.slotWords + (mr.slotWords - 1u)));
+        }
         __syncthreads();
         uint32_t sum = 0;
         bool over = false;
@@ -900,11 +1004,17 @@ __global__ void __launch_bounds__(1024) k_selmr_finish(LevelState lv, SelState s
             if (tid == 0) atomicExch(err, ORB_ERR_STATE);
             continue;
         }
+        const float *mine = PEER ? mr.slots_l + (size_t)c * mr.slotWords : mr.slots_g + ((size_t)mr.self * nCells + c) * mr.slotWords;
         uint32_t off = 0;
         for (int r = 0; r < mr.nRanks; ++r) {
-            const float *src = mr.slots_g + ((size_t)r * nCells + c) * mr.slotWords;
             const uint32_t n = s_cnt[r];
-            for (uint32_t i = tid; i < n; i += nThreads) sbuf[off + i] = __ldcg(src + i);
+            if (PEER && r != mr.self) {
+                const uint32_t *src = px.arena[r] + px.offSlots + (size_t)c * mr.slotWords;
+                for (uint32_t i = tid; i < n; i += nThreads) sbuf[off + i] = __uint_as_float(ld_sys_u32(src + i));
+            } else {
+                const float *src = PEER ? mine : mr.slots_g + ((size_t)r * nCells + c) * mr.slotWords;
+                for (uint32_t i = tid; i < n; i += nThreads) sbuf[off + i] = __ldcg(src + i);
+            }
             off += n;
         }
         __syncthreads();
@@ -913,13 +1023,20 @@ __global__ void __launch_bounds__(1024) k_selmr_finish(LevelState lv, SelState s
         if (!done) continue;
         // local left count at the final cut: getCut() of the final margins is the found cut as well as the capped cell's cut
         const float cutf = mid_cut(lv.mL[c], lv.mR[c]);
-        const float *mine = mr.slots_g + ((size_t)mr.self * nCells + c) * mr.slotWords;
         uint32_t n = 0;
         for (uint32_t i = tid; i < s_cnt[mr.self]; i += nThreads) n += (__ldcg(mine + i) < cutf) ? 1u : 0u;
         n = __reduce_add_sync(0xffffffffu, n);
         if (lane == 0 && n) atomicAdd(&s_nl, n);
         __syncthreads();
         if (tid == 0) lv.nleft_l[c] = mr.loc_base[c] + s_nl;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(mr.done, 1u) == gridDim.x - 1u) {
+            __threadfence();
+            *mr.h_status = *((volatile uint32_t *)ss.n_flagged) + 1u;
+        }
     }
 }
 

@@ -112,6 +112,8 @@ typedef struct orb_peer_info {
     int64_t pid;
     int32_t device;
     int32_t reserved_;
+    uint8_t ipc_xchg[64];   /* exchange arena of the selection search: flags | slot fill levels | candidate slots | histogram rows */
+    uint64_t ptr_xchg;
 } orb_peer_info;
 int orb_peer_export(orb_ctx *ctx, orb_peer_info *out);
 int orb_peer_import(orb_ctx *ctx, const orb_peer_info *all, int n_ranks);

@@ -35,9 +35,10 @@ def test_two_process_build_matches_sharded_oracle(oracle, tmp_path, peers):
         assert list(got["iters"]) == list(ref["stats"].iters[:len(got["iters"])])
 
 
-@pytest.mark.parametrize("x,y,select_mr", [(20, 3, 1), (17, 5, 1), (18, 8, 0)])
-def test_two_process_selection_search(oracle, tmp_path, x, y, select_mr):
-    """Selection search over two ranks (histogram rows all-reduced, candidates all-gathered) on inputs with thousands
+@pytest.mark.parametrize("x,y,select_mr,peers", [(20, 3, 1, 1), (17, 5, 1, 1), (17, 5, 1, 0), (18, 8, 0, 1)])
+def test_two_process_selection_search(oracle, tmp_path, x, y, select_mr, peers):
+    """Selection search over two ranks (rows summed and candidates gathered over NVLink peer memory, or by NCCL when
+    peers == 0) on inputs with thousands
     of particles tied at the median: flagged cells fall back to the iterative loop on every rank alike; and
     ORB_SELECT_MR=0 (iterative search everywhere) gives the same tree on plain inputs."""
     import torch
@@ -47,9 +48,9 @@ def test_two_process_selection_search(oracle, tmp_path, x, y, select_mr):
     import mp_build_check
 
     R = 2
-    port = 29700 + (os.getpid() % 200) + x
+    port = 29700 + (os.getpid() % 200) + x + 30 * peers
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={R}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), str(ROOT / "tests" / "mp_build_check.py"), str(tmp_path), str(x), str(y), "1",
+           "--master-port", str(port), str(ROOT / "tests" / "mp_build_check.py"), str(tmp_path), str(x), str(y), str(peers),
            "ties" if select_mr else "plain"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, ORB_SELECT_MR=str(select_mr)))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
