@@ -105,6 +105,9 @@ struct orb_ctx {
     uint32_t *d_range = nullptr;      // [nHeap*2]
     uint32_t *d_total = nullptr;      // [nHeap]
     orb::LevelState lv{};
+    orb::LevelState lvAlt{};          // second set of the per-cell arrays: k_split prepares the next level in it while the
+    uint32_t *d_tile_first_alt = nullptr;   // partition still reads this level's (orb_build swaps the two per level)
+    bool fuseNextLevel = true;        // ORB_FUSE_NEXT=0: separate k_level_setup / k_tile_map launches per level
     uint32_t *d_cnt_g_buf = nullptr;  // separate allreduce target (multi-rank only)
     float *d_final_cut = nullptr;     // [maxLevelCells]
     uint32_t *d_tile_first = nullptr; // [nMapTiles]
@@ -144,7 +147,7 @@ struct orb_ctx {
     bool select = true;
     int selPerCellMinCells = 64;   // levels with at least this many cells: one block searches a whole cell
     bool selBigBlocks = true;      // ORB_SELECT_BIG_BLOCKS=0: no 1024 x 1 / 512 x 2 variants of k_sel_percell
-    int selBinAvg = 16384;         // ORB_SELECT_BIN_AVG: HIST bins per cell are doubled (512..8192) until a bin holds at most this many particles on average
+    int selBinAvg = 8192;          // ORB_SELECT_BIN_AVG: HIST bins per cell are doubled (512..8192) until a bin holds at most this many particles on average
     int selT512MinAvg = 32768;     // ORB_SELECT_T512_MIN: cells of at least this many particles get 512-thread blocks
     bool pdl = true;               // programmatic dependent launch between the small kernels of a level
     orb::SelState sel{};
@@ -997,9 +1000,22 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
         CK(cudaMalloc(&c->lv.tile_ncand, nCountTiles * orb::kWarps * 4));
         CK(cudaMemset(c->lv.tile_ncand, 0, nCountTiles * orb::kWarps * 4));
     }
+    c->lvAlt = c->lv;                 // search scratch (cuts, counters, compaction state) is shared
+    CK(cudaMalloc(&c->lvAlt.bnd, (L + 1) * 4));
+    CK(cudaMalloc(&c->lvAlt.axis, L * 4));
+    CK(cudaMalloc(&c->lvAlt.mL, L * 4));
+    CK(cudaMalloc(&c->lvAlt.mR, L * 4));
+    CK(cudaMalloc(&c->lvAlt.total, L * 4));
+    CK(cudaMalloc(&c->lvAlt.nleaf, L * 4));
+    CK(cudaMalloc(&c->lvAlt.active, L * 4));
+    CK(cudaMalloc(&c->lvAlt.found, L * 4));
+    CK(cudaMalloc(&c->lvAlt.iter, L * 4));
+    CK(cudaMalloc(&c->lvAlt.nleft_g, L * 4));
+    CK(cudaMalloc(&c->lvAlt.nleft_l, L * 4));
     CK(cudaMalloc(&c->d_final_cut, L * 4));
     const size_t nMap = ceil_div(n_local, orb::kMapTile) + 1;
     CK(cudaMalloc(&c->d_tile_first, nMap * 4));
+    CK(cudaMalloc(&c->d_tile_first_alt, nMap * 4));
     CK(cudaMalloc(&c->d_blk_left, sizeof(uint32_t) * 64 * (size_t)c->nSM));
     CK(cudaMalloc(&c->d_blk_restart, sizeof(uint32_t) * 64 * (size_t)c->nSM));
     CK(cudaMalloc(&c->d_blk_le, sizeof(uint32_t) * 64 * (size_t)c->nSM));
@@ -1111,6 +1127,8 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     if (sba && atoi(sba) >= 64) c->selBinAvg = atoi(sba);
     const char *st5 = getenv("ORB_SELECT_T512_MIN");
     if (st5 && atoi(st5) >= 1) c->selT512MinAvg = atoi(st5);
+    const char *fnl = getenv("ORB_FUSE_NEXT");
+    if (fnl) c->fuseNextLevel = atoi(fnl) != 0;
     const char *se = getenv("ORB_SELECT");
     if (se) c->select = atoi(se) != 0;
     const char *sem = getenv("ORB_SELECT_MR");
@@ -1141,6 +1159,9 @@ int orb_destroy(orb_ctx *c) {
     cudaFree(c->lv.nleaf); cudaFree(c->lv.active); cudaFree(c->lv.found); cudaFree(c->lv.iter);
     cudaFree(c->lv.nleft_g); cudaFree(c->lv.nleft_l); cudaFree(c->lv.cuts); cudaFree(c->lv.cnt_l);
     cudaFree(c->lv.compL); cudaFree(c->lv.compR); cudaFree(c->lv.base_l); cudaFree(c->lv.tile_ncand);
+    cudaFree(c->lvAlt.bnd); cudaFree(c->lvAlt.axis); cudaFree(c->lvAlt.mL); cudaFree(c->lvAlt.mR); cudaFree(c->lvAlt.total);
+    cudaFree(c->lvAlt.nleaf); cudaFree(c->lvAlt.active); cudaFree(c->lvAlt.found); cudaFree(c->lvAlt.iter);
+    cudaFree(c->lvAlt.nleft_g); cudaFree(c->lvAlt.nleft_l); cudaFree(c->d_tile_first_alt);
     if (c->d_cnt_g_buf) cudaFree(c->d_cnt_g_buf);
     cudaFree(c->d_dbg); cudaFree(c->d_dbg_blocks);
     cudaFree(c->sel.bfirst); cudaFree(c->sel.blast); cudaFree(c->sel.base); cudaFree(c->sel.ncand);
@@ -1200,6 +1221,7 @@ static int setup_multi(orb_ctx *c) {
     if (c->nRanks > 1 && !c->d_cnt_g_buf) {
         CK(cudaMalloc(&c->d_cnt_g_buf, (size_t)c->maxLevelCells * orb::kCS * 4));
         c->lv.cnt_g = c->d_cnt_g_buf;
+        c->lvAlt.cnt_g = c->d_cnt_g_buf;
     }
     c->nLocalMin = c->nGlobal = c->nLocal;
     if (c->nRanks > 1) {
@@ -1564,6 +1586,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
     std::vector<int> passes;
     std::vector<uint32_t> unfound;
     int nDone = 0;
+    bool prepared = false;      // this level's SoA state, tile map and cleared histogram rows came from the previous level's k_split
     for (int l = 1; l < lEnd; ++l) {
         const uint32_t first = (1u << (l - 1)) - 1u;   // a = 2^(l-1)-1 (orbit.cpp:104); nCells = 2^(l-1) for d = 2^y
         const uint32_t nCells = 1u << (l - 1);
@@ -1571,8 +1594,11 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         const bool useSelect = level_can_select(c, nCells, M);
         const SelMrPlan mrPlan = sel_plan_mr(c, nCells, M);
         const size_t histWords = useSelect ? sel_plan(c, nCells).histWords : (mrPlan.ok ? mrPlan.histWords : 0);
-        rc = level_prepare(c, c->d_heap + first, nCells, (1 << M) - 1, c->d_nactive + slot, c->sel.hist, std::min(histWords, c->selHistWords));
-        if (rc) return rc;
+        if (!prepared) {
+            rc = level_prepare(c, c->d_heap + first, nCells, (1 << M) - 1, c->d_nactive + slot, c->sel.hist, std::min(histWords, c->selHistWords));
+            if (rc) return rc;
+        }
+        prepared = false;
         int np = 0;
         uint32_t nu = 0;
         bool speculate = false;     // split + partition enqueued behind the search before its flag count is known
@@ -1613,8 +1639,27 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         // multi-rank selection search: split and partition go out gated on the level's flag count, the host looks at
         // the count afterwards; only if cells were flagged it runs the iterative loop and enqueues both again
         const uint32_t *gate = speculate ? c->d_sel_nflag + (l - 1) : nullptr;
+        // the same launch prepares the next level (not in the modes that build the next level's state elsewhere)
+        NextLevel nx;
+        memset(&nx, 0, sizeof(nx));
+        uint32_t splitBlocks = ceil_div(nCells, 256);
+        if (c->fuseNextLevel && l + 1 < lEnd && !tight && c->tieMode != 1 && 2u * nCells <= c->maxLevelCells && c->nLocal > 0) {
+            const uint32_t nNext = 2u * nCells;
+            const SelMrPlan mrNext = sel_plan_mr(c, nNext, M);
+            const size_t hwNext = level_can_select(c, nNext, M) ? sel_plan(c, nNext).histWords : (mrNext.ok ? mrNext.histWords : 0);
+            nx.enabled = 1;
+            nx.lv = c->lvAlt;
+            nx.nc = (1 << M) - 1;
+            nx.err = c->d_err;
+            nx.n_active0 = c->d_nactive + l * kPassSlots;
+            nx.nMapTiles = ceil_div(c->nLocal, kMapTile);
+            nx.tile_first = c->d_tile_first_alt;
+            nx.zero = c->sel.hist;
+            nx.nZero = std::min(hwNext, c->selHistWords);
+            splitBlocks = std::max(splitBlocks, std::max(ceil_div(nx.nMapTiles, 256), std::min<uint32_t>(ceil_div(nx.nZero, 2048), 4u * (uint32_t)c->nSM)));
+        }
         for (int attempt = 0; attempt < 2; ++attempt) {
-            CK(launch_pdl(c, k_split, dim3(ceil_div(nCells, 256)), dim3(256), 0, c->d_heap, first, nCells, c->lv, c->d_range, c->d_total, c->d_final_cut, gate));
+            CK(launch_pdl(c, k_split, dim3(splitBlocks), dim3(256), 0, c->d_heap, first, nCells, c->lv, c->d_range, c->d_total, c->d_final_cut, gate, nx));
             c->nOtherLaunch++;
             if (c->tieMode != 1) {
                 rc = launch_partition(c, nCells, c->d_tickets + (l - 1), gate);
@@ -1625,6 +1670,11 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             rc = select_mr_fallback(c, nCells, slot, l - 1);
             if (rc) return rc;
             gate = nullptr;
+        }
+        if (nx.enabled) {       // the partition has been enqueued with this level's state: switch to the prepared one
+            std::swap(c->lv, c->lvAlt);
+            std::swap(c->d_tile_first, c->d_tile_first_alt);
+            prepared = true;
         }
         if (tight) {   // children boxes from their particles; needs the children's ranges as a level
             const uint32_t cf = (1u << l) - 1u, cn = 1u << l;

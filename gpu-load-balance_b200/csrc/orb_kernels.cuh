@@ -102,6 +102,23 @@ __device__ __forceinline__ const float *pick_col(int a, const float *x, const fl
 // Level setup: flatten Cell[] (the reference's wire format) into the SoA level state.
 // Mirrors what ServiceCopyCells prepares per level (copyCells.cu:29-61) without block descriptors.
 // =====================================================================================
+// trial cuts of a cell's first pass: the implicit bisection tree below (L,R), heap order; counters cleared
+__device__ __forceinline__ void init_first_cuts(const LevelState &lv, uint32_t c, float L, float R, int nc) {
+    float cv[kCS];
+    float lo[kCS], hi[kCS];
+    lo[0] = L; hi[0] = R;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        if (k < nc) {
+            cv[k] = mid_cut(lo[k], hi[k]);
+            if (2 * k + 2 < 7) { lo[2 * k + 1] = lo[k]; hi[2 * k + 1] = cv[k]; lo[2 * k + 2] = cv[k]; hi[2 * k + 2] = hi[k]; }
+        } else cv[k] = 0.f;
+    }
+    cv[7] = 0.f;
+#pragma unroll
+    for (int k = 0; k < kCS; ++k) { lv.cuts[c * kCS + k] = cv[k]; lv.cnt_l[c * kCS + k] = 0u; }
+}
+
 __global__ void k_level_setup(const orb_cell *__restrict__ cells, uint32_t nCells, const uint32_t *__restrict__ range,
                               const uint32_t *__restrict__ total_by_id, LevelState lv, uint32_t nLocal, int nc,
                               int *__restrict__ err, uint32_t *__restrict__ n_active0) {
@@ -134,20 +151,7 @@ __global__ void k_level_setup(const orb_cell *__restrict__ cells, uint32_t nCell
     lv.iter[c] = 0;
     lv.nleft_g[c] = 0;
     lv.nleft_l[c] = 0;
-    // trial cuts of the first pass: the implicit bisection tree below (L,R), heap order
-    float cv[kCS];
-    float lo[kCS], hi[kCS];
-    lo[0] = L; hi[0] = R;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        if (k < nc) {
-            cv[k] = mid_cut(lo[k], hi[k]);
-            if (2 * k + 2 < 7) { lo[2 * k + 1] = lo[k]; hi[2 * k + 1] = cv[k]; lo[2 * k + 2] = cv[k]; hi[2 * k + 2] = hi[k]; }
-        } else cv[k] = 0.f;
-    }
-    cv[7] = 0.f;
-#pragma unroll
-    for (int k = 0; k < kCS; ++k) { lv.cuts[c * kCS + k] = cv[k]; lv.cnt_l[c * kCS + k] = 0u; }
+    init_first_cuts(lv, c, L, R, nc);
 }
 
 // first cell whose range extends beyond the start of each map tile
@@ -1283,12 +1287,57 @@ __device__ __forceinline__ void child_axis_margins(orb_cell &ch) {
 
 // `gate` (may be null): the kernel was enqueued before the host knew whether the level's search left cells to the
 // iterative loop; a non-zero word means it did, and the launch does nothing (the host enqueues it again afterwards).
+// `nx.enabled`: the same launch also prepares the NEXT level - what k_level_setup and k_tile_map would do from the
+// children it has just made: their SoA level state (in the other LevelState buffer, the partition that follows still
+// reads this level's), the tile -> first-cell map of the children's ranges, cleared histogram rows.  Saves two launches
+// per level.
+struct NextLevel {
+    int enabled;
+    LevelState lv;                // the other buffer
+    int nc;                       // trial cuts per pass of the iterative search
+    int *err;
+    uint32_t *n_active0;          // gate of the next level's first count pass
+    uint32_t nMapTiles;
+    uint32_t *tile_first;         // the other buffer
+    uint32_t *zero;               // histogram rows of the next level
+    size_t nZero;
+};
+__device__ __forceinline__ void setup_child(const NextLevel &nx, uint32_t idx, const orb_cell &ch, uint32_t begin, uint32_t total) {
+    nx.lv.bnd[idx] = begin;
+    if (ch.cutAxis < 0 || ch.cutAxis > 2) atomicExch(nx.err, ORB_ERR_ARG);
+    nx.lv.axis[idx] = ch.cutAxis < 0 ? 0 : (ch.cutAxis > 2 ? 2 : ch.cutAxis);
+    nx.lv.mL[idx] = ch.cutMarginLeft;
+    nx.lv.mR[idx] = ch.cutMarginRight;
+    nx.lv.total[idx] = total;
+    nx.lv.nleaf[idx] = ch.nLeafCells;
+    nx.lv.found[idx] = 0u;
+    nx.lv.active[idx] = 1u;
+    nx.lv.iter[idx] = 0;
+    nx.lv.nleft_g[idx] = 0u;
+    nx.lv.nleft_l[idx] = 0u;
+    init_first_cuts(nx.lv, idx, ch.cutMarginLeft, ch.cutMarginRight, nx.nc);
+}
 __global__ void k_split(orb_cell *__restrict__ heap, uint32_t first, uint32_t nCells, LevelState lv,
                         uint32_t *__restrict__ range, uint32_t *__restrict__ total_by_id, float *__restrict__ final_cut,
-                        const uint32_t *__restrict__ gate) {
+                        const uint32_t *__restrict__ gate, NextLevel nx) {
     pdl_enter();
     if (gate && *((volatile const uint32_t *)gate) != 0u) return;
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nx.enabled) {
+        for (size_t i = c; i < nx.nZero; i += (size_t)gridDim.x * blockDim.x) nx.zero[i] = 0u;
+        if (c == 0 && nx.n_active0) *nx.n_active0 = 1u;
+        if (c < nx.nMapTiles) {
+            // smallest child whose range extends beyond the tile's first particle: the parent by binary search on
+            // this level's boundaries, then left or right of its split position
+            const uint32_t start = c * (uint32_t)kMapTile;
+            uint32_t lo = 0, hi = nCells - 1;
+            while (lo < hi) {
+                const uint32_t m = (lo + hi) >> 1;
+                if (lv.bnd[m + 1] > start) hi = m; else lo = m + 1;
+            }
+            nx.tile_first[c] = 2u * lo + ((lv.bnd[lo] + lv.nleft_l[lo] > start) ? 0u : 1u);
+        }
+    }
     if (c >= nCells) return;
     orb_cell p = heap[first + c];
     p.cutMarginLeft = lv.mL[c];
@@ -1318,6 +1367,11 @@ __global__ void k_split(orb_cell *__restrict__ heap, uint32_t first, uint32_t nC
     range[2 * r.id] = m; range[2 * r.id + 1] = e;
     total_by_id[l.id] = lv.nleft_g[c];
     total_by_id[r.id] = lv.total[c] - lv.nleft_g[c];
+    if (nx.enabled) {
+        setup_child(nx, 2u * c, l, b, lv.nleft_g[c]);
+        setup_child(nx, 2u * c + 1u, r, m, lv.total[c] - lv.nleft_g[c]);
+        if (c + 1u == nCells) nx.lv.bnd[2u * nCells] = e;
+    }
 }
 
 // service-granular partition: only ranges + final cut (the host owns the Cell heap)

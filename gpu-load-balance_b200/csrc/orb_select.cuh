@@ -862,11 +862,6 @@ __device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t *p) {
     asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ uint4 ld_sys_u4(const uint32_t *p) {
-    uint4 v;
-    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
 // Cross-rank barrier at the start of a kernel (after pdl_enter: this rank's preceding kernel has completed).
 __device__ __forceinline__ void selx_barrier(const SelPeers &px) {
     const int t = threadIdx.x;
@@ -901,13 +896,21 @@ __global__ void __launch_bounds__(kThreads) k_selx_resolve(LevelState lv, SelSta
             continue;
         }
         const uint32_t *own = mr.hist_l + (size_t)c * nb1;
+        // (peer memory is not cached by this GPU's L2, .cg skips its L1: plain loads the compiler may batch - all
+        //  ranks' rows of a chunk are in flight together, one NVLink round trip per chunk instead of one per rank)
         for (int i4 = tid; i4 < nb1 / 4; i4 += kThreads) {
-            uint4 a = __ldcg(reinterpret_cast<const uint4 *>(own) + i4);
-            for (int r = 0; r < px.n; ++r) {
-                if (r == px.self) continue;
-                const uint4 b = ld_sys_u4(px.arena[r] + px.offHist + (size_t)c * nb1 + 4 * i4);
-                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            uint4 b[kMaxPeers];
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r) {
+                b[r] = make_uint4(0u, 0u, 0u, 0u);
+                if (r < px.n) {
+                    const uint32_t *row = (r == px.self) ? own : px.arena[r] + px.offHist + (size_t)c * nb1;
+                    b[r] = __ldcg(reinterpret_cast<const uint4 *>(row) + i4);
+                }
             }
+            uint4 a = b[0];
+#pragma unroll
+            for (int r = 1; r < kMaxPeers; ++r) { a.x += b[r].x; a.y += b[r].y; a.z += b[r].z; a.w += b[r].w; }
             reinterpret_cast<uint4 *>(hbuf)[i4] = a;
         }
         __syncthreads();
@@ -1005,16 +1008,29 @@ __global__ void __launch_bounds__(1024) k_selmr_finish(LevelState lv, SelState s
             continue;
         }
         const float *mine = PEER ? mr.slots_l + (size_t)c * mr.slotWords : mr.slots_g + ((size_t)mr.self * nCells + c) * mr.slotWords;
+        // slots are 128-byte aligned: 16-byte loads, four in flight per thread and rank (remote ones cross NVLink)
         uint32_t off = 0;
         for (int r = 0; r < mr.nRanks; ++r) {
             const uint32_t n = s_cnt[r];
-            if (PEER && r != mr.self) {
-                const uint32_t *src = px.arena[r] + px.offSlots + (size_t)c * mr.slotWords;
-                for (uint32_t i = tid; i < n; i += nThreads) sbuf[off + i] = __uint_as_float(ld_sys_u32(src + i));
-            } else {
-                const float *src = PEER ? mine : mr.slots_g + ((size_t)r * nCells + c) * mr.slotWords;
-                for (uint32_t i = tid; i < n; i += nThreads) sbuf[off + i] = __ldcg(src + i);
+            const float *src = PEER ? (r == mr.self ? mine : reinterpret_cast<const float *>(px.arena[r] + px.offSlots) + (size_t)c * mr.slotWords)
+                                    : mr.slots_g + ((size_t)r * nCells + c) * mr.slotWords;
+            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+            const uint32_t n4 = n >> 2;
+            uint32_t i = tid;
+            for (; i + 3u * nThreads < n4; i += 4u * nThreads) {
+                const float4 q0 = __ldcg(s4 + i), q1 = __ldcg(s4 + i + nThreads), q2 = __ldcg(s4 + i + 2u * nThreads), q3 = __ldcg(s4 + i + 3u * nThreads);
+                float *d = sbuf + off + 4u * i;
+                d[0] = q0.x; d[1] = q0.y; d[2] = q0.z; d[3] = q0.w;
+                d += 4u * nThreads; d[0] = q1.x; d[1] = q1.y; d[2] = q1.z; d[3] = q1.w;
+                d += 4u * nThreads; d[0] = q2.x; d[1] = q2.y; d[2] = q2.z; d[3] = q2.w;
+                d += 4u * nThreads; d[0] = q3.x; d[1] = q3.y; d[2] = q3.z; d[3] = q3.w;
             }
+            for (; i < n4; i += nThreads) {
+                const float4 q = __ldcg(s4 + i);
+                float *d = sbuf + off + 4u * i;
+                d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+            }
+            if (4u * n4 + tid < n) sbuf[off + 4u * n4 + tid] = __ldcg(src + 4u * n4 + tid);
             off += n;
         }
         __syncthreads();
