@@ -108,6 +108,7 @@ struct orb_ctx {
     orb::LevelState lvAlt{};          // second set of the per-cell arrays: k_split prepares the next level in it while the
     uint32_t *d_tile_first_alt = nullptr;   // partition still reads this level's (orb_build swaps the two per level)
     bool fuseNextLevel = true;        // ORB_FUSE_NEXT=0: separate k_level_setup / k_tile_map launches per level
+    bool prefuseHist = true;          // ORB_PREFUSE=0: the partition does not build the next level's histogram rows
     uint32_t *d_cnt_g_buf = nullptr;  // separate allreduce target (multi-rank only)
     float *d_final_cut = nullptr;     // [maxLevelCells]
     uint32_t *d_tile_first = nullptr; // [nMapTiles]
@@ -524,7 +525,7 @@ struct SelPlan {
     size_t histWords;     // nCells * nb1 (cleared by k_tile_map during level preparation)
     uint32_t candCap;
 };
-SelPlan sel_plan(const orb_ctx *c, uint32_t nCells) {
+SelPlan sel_plan(const orb_ctx *c, uint32_t nCells, int forcedNb = 0 /* rows already built by the partition with this many bins */) {
     SelPlan p{};
     const uint64_t avg = c->nLocal / nCells;
     // one block per cell once there are enough cells to fill the GPU; fewer, larger cells are streamed by all blocks
@@ -538,14 +539,15 @@ SelPlan sel_plan(const orb_ctx *c, uint32_t nCells) {
     p.cellCap = avg >= 65536 ? 8192u : 4096u;
     p.nb1 = orb::kSelBinsMin;
     while (p.nb1 < orb::kSelBinsMax && avg / (uint64_t)p.nb1 > (uint64_t)c->selBinAvg) p.nb1 <<= 1;
+    if (forcedNb) p.nb1 = forcedNb;
     p.rep = p.nb1 <= 512 ? 4 : (p.nb1 <= 1024 ? 2 : 1);
-    p.histWords = p.cellsInSmem ? 0 : (size_t)nCells * (size_t)p.nb1;
+    p.histWords = (p.cellsInSmem && !forcedNb) ? 0 : (size_t)nCells * (size_t)p.nb1;
     // candidates one block will stage per cell: a few bins' worth; cells beyond it go to the iterative search
     p.candCap = (uint32_t)std::min<uint64_t>(kSelValsCap, 4 * (avg / (uint64_t)p.nb1) + 4096);
     return p;
 }
 
-int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx) {
+int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx, int preNb = 0) {
     using namespace orb;
     const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
     float *cand = c->x[c->cur ^ 1];
@@ -557,7 +559,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
     sc.passes_out = c->d_lvl_passes + levelIdx;
     sc.n_unfound_out = c->d_lvl_unfound + levelIdx;
     int rc;
-    const SelPlan pl = sel_plan(c, nCells);
+    const SelPlan pl = sel_plan(c, nCells, preNb);
     // block size of the per-cell search kernels: big blocks when shared memory allows one block per SM anyway
     auto search_threads = [](size_t smem) { return smem > 112 * 1024 ? 1024 : (smem > 56 * 1024 ? 512 : 256); };
     if (pl.cellsInSmem) {
@@ -569,7 +571,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, pl.threads, smem));
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
         if ((rc = count_event_begin(c))) return rc;
-        CK(launch_pdl(c, kern, dim3(grid), dim3(pl.threads), smem, x, y, z, c->lv, ss, sc, nCells, pl.cellCap));
+        CK(launch_pdl(c, kern, dim3(grid), dim3(pl.threads), smem, x, y, z, c->lv, ss, sc, nCells, pl.cellCap, preNb));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     } else {
@@ -582,7 +584,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
         const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
         const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
         const uint32_t nL = (uint32_t)c->nLocal;
-        {
+        if (!preNb) {      // (preNb: the rows were built by the previous level's partition)
             const size_t smem = ringBytes + (size_t)nb1 * rep * 4;
             int occ = 1;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelHist>, kThreads, smem));
@@ -591,6 +593,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
             CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
                           nCells, nL, nTiles, nb1, rep, candCap, dbgBase, (float *)nullptr, 0u, 0));
             if ((rc = count_event_end(c))) return rc;
+            c->nCountLaunch++;
         }
         {
             const size_t smem = ringBytes + (size_t)kWarps * kSelWarpStage * 4 + (size_t)nb1 * 4;
@@ -614,7 +617,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx)
                           dbgBase ? dbgBase + (size_t)2 * kDbgBlocks * 4 : (unsigned long long *)nullptr));
             if ((rc = aux_end(c))) return rc;
         }
-        c->nCountLaunch += 2;
+        c->nCountLaunch += 1;
         c->nUpdateLaunch += 1;    // the finish kernel takes the place of the per-pass update kernels
     }
     CK(cudaGetLastError());
@@ -661,7 +664,7 @@ struct SelMrPlan {
     uint32_t candCap, slotWords;
     size_t histWords;
 };
-SelMrPlan sel_plan_mr(const orb_ctx *c, uint32_t nCells, int M) {
+SelMrPlan sel_plan_mr(const orb_ctx *c, uint32_t nCells, int M, int forcedNb = 0) {
     SelMrPlan p{};
     p.ok = false;
     if (!(c->select && c->selectMr && c->nRanks > 1 && c->nRanks <= orb::kMaxPeers && M == 3 && c->d_slots_g && nCells >= 1 &&
@@ -670,6 +673,7 @@ SelMrPlan sel_plan_mr(const orb_ctx *c, uint32_t nCells, int M) {
     const uint64_t gavg = c->nGlobal / nCells, lavg = std::max<uint64_t>(c->nGlobal / c->nRanks, c->nLocalMin) / nCells;
     p.nb1 = orb::kSelBinsMin;
     while (p.nb1 < orb::kSelBinsMax && gavg / (uint64_t)p.nb1 > (uint64_t)c->selBinAvg) p.nb1 <<= 1;
+    if (forcedNb) p.nb1 = forcedNb;
     p.rep = p.nb1 <= 512 ? 4 : (p.nb1 <= 1024 ? 2 : 1);
     p.histWords = (size_t)nCells * (size_t)p.nb1;
     p.candCap = (uint32_t)std::min<uint64_t>(kSelValsCap, 4 * (gavg / (uint64_t)p.nb1) + 4096);
@@ -684,9 +688,31 @@ SelMrPlan sel_plan_mr(const orb_ctx *c, uint32_t nCells, int M) {
     return p;
 }
 
+// Bins of the histogram rows the partition of the previous level builds for a level of nNext cells (NextHist), or 0:
+// the level must use the selection search, a bin must not hold more candidates than one block stages, the rows must
+// fit.  Decided from rank-invariant numbers only (it shapes the multi-rank exchanges).
+int prefuse_nb(const orb_ctx *c, uint32_t nNext, int M) {
+    if (!c->prefuseHist) return 0;
+    // The partition's block histogram holds at most 1024 bins per child.  Where the level streams (HIST / COMPACT /
+    // FINISH) the rows must have the bins the level would choose itself - coarser rows mean more candidates per bin
+    // and, on clustered inputs, cells that overflow the finish kernel's staging; where one block searches a whole
+    // cell it can zoom on its own (k_sel_percell), so coarser rows only cost that cell another read.
+    if (c->nRanks > 1) {
+        const SelMrPlan p = sel_plan_mr(c, nNext, M);
+        if (!p.ok || p.nb1 > 1024) return 0;
+        return p.nb1;
+    }
+    if (!level_can_select(c, nNext, M)) return 0;
+    const SelPlan p = sel_plan(c, nNext);
+    if (!p.cellsInSmem && p.nb1 > 1024) return 0;
+    const int nb = std::min(p.nb1, 1024);
+    if ((size_t)nNext * (size_t)nb > c->selHistWords) return 0;
+    return nb;
+}
+
 // Enqueues the level's search up to the finish kernel; no host synchronisation.  The finish kernel's last block
 // reports 1 + (cells flagged) in h_status[slotBase + kPassSlots - 1] (see select_mr_flagged).
-int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int slotBase, int levelIdx) {
+int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int slotBase, int levelIdx, int preNb = 0) {
     using namespace orb;
     const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
     float *cand = c->x[c->cur ^ 1];
@@ -723,8 +749,8 @@ int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int
     const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
     const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
     const uint32_t nL = (uint32_t)c->nLocal;
-    // ---- HIST: this rank's rows (cleared by level_prepare) ----
-    if (nTiles) {
+    // ---- HIST: this rank's rows (cleared by level_prepare); not needed when the previous level's partition built them ----
+    if (nTiles && !preNb) {
         const size_t smem = ringBytes + (size_t)nb1 * pl.rep * 4;
         int occ = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelHist>, kThreads, smem));
@@ -815,7 +841,13 @@ int select_mr_fallback(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx) 
 // Stable split of every cell of the level (canonical tie mode).  Kernel choice by average local cell size:
 // cells of at most 16 tiles (and enough of them to fill the GPU) -> one block per cell with a running carry;
 // otherwise persistent tile streaming with decoupled look-back (cooperative launch: all blocks co-resident).
-int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket, const uint32_t *gate = nullptr) {
+orb::NextHist no_next_hist() {
+    orb::NextHist nh;
+    memset(&nh, 0, sizeof(nh));
+    return nh;
+}
+
+int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket, const uint32_t *gate = nullptr, orb::NextHist nh = no_next_hist()) {
     using namespace orb;
     (void)ticket;
     const uint32_t nTiles = ceil_div(c->nLocal, kPartTile);
@@ -840,13 +872,13 @@ int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket, const uint32
     const size_t smem = sizeof(PartSmem);
     if (avg <= 16ull * kPartTile && nCells >= 2u * (uint32_t)c->nSM) {
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)c->occPartCells);
-        k_partition_cells<<<grid, kThreads, smem, c->stream>>>(x, y, z, x2, y2, z2, c->lv, c->d_final_cut, nCells, (uint32_t)c->nLocal, gate);
+        k_partition_cells<<<grid, kThreads, smem, c->stream>>>(x, y, z, x2, y2, z2, c->lv, c->d_final_cut, nCells, (uint32_t)c->nLocal, gate, nh);
     } else {
         const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)c->occPartStream);
         uint32_t nLocal32 = (uint32_t)c->nLocal, nT = nTiles, nC = nCells;
         void *args[] = {(void *)&x, (void *)&y, (void *)&z, (void *)&x2, (void *)&y2, (void *)&z2, (void *)&c->lv,
                         (void *)&c->d_final_cut, (void *)&c->d_tile_first, (void *)&nC, (void *)&nLocal32, (void *)&nT,
-                        (void *)&c->d_blk_left, (void *)&c->d_blk_restart, (void *)&gate};
+                        (void *)&c->d_blk_left, (void *)&c->d_blk_restart, (void *)&gate, (void *)&nh};
         CK(cudaLaunchCooperativeKernel((const void *)k_partition_coop, dim3(grid), dim3(kThreads), args, smem, c->stream));
     }
     if (c->profile) CK(cudaEventRecord(e1, c->stream));
@@ -1127,6 +1159,8 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     if (sba && atoi(sba) >= 64) c->selBinAvg = atoi(sba);
     const char *st5 = getenv("ORB_SELECT_T512_MIN");
     if (st5 && atoi(st5) >= 1) c->selT512MinAvg = atoi(st5);
+    const char *pfh = getenv("ORB_PREFUSE");
+    if (pfh) c->prefuseHist = atoi(pfh) != 0;
     const char *fnl = getenv("ORB_FUSE_NEXT");
     if (fnl) c->fuseNextLevel = atoi(fnl) != 0;
     const char *se = getenv("ORB_SELECT");
@@ -1587,13 +1621,14 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
     std::vector<uint32_t> unfound;
     int nDone = 0;
     bool prepared = false;      // this level's SoA state, tile map and cleared histogram rows came from the previous level's k_split
+    int preNb = 0;              // != 0: the previous level's partition built this level's histogram rows with this many bins
     for (int l = 1; l < lEnd; ++l) {
         const uint32_t first = (1u << (l - 1)) - 1u;   // a = 2^(l-1)-1 (orbit.cpp:104); nCells = 2^(l-1) for d = 2^y
         const uint32_t nCells = 1u << (l - 1);
         const int slot = (l - 1) * kPassSlots;
         const bool useSelect = level_can_select(c, nCells, M);
-        const SelMrPlan mrPlan = sel_plan_mr(c, nCells, M);
-        const size_t histWords = useSelect ? sel_plan(c, nCells).histWords : (mrPlan.ok ? mrPlan.histWords : 0);
+        const SelMrPlan mrPlan = sel_plan_mr(c, nCells, M, preNb);
+        const size_t histWords = useSelect ? sel_plan(c, nCells, preNb).histWords : (mrPlan.ok ? mrPlan.histWords : 0);
         if (!prepared) {
             rc = level_prepare(c, c->d_heap + first, nCells, (1 << M) - 1, c->d_nactive + slot, c->sel.hist, std::min(histWords, c->selHistWords));
             if (rc) return rc;
@@ -1603,7 +1638,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         uint32_t nu = 0;
         bool speculate = false;     // split + partition enqueued behind the search before its flag count is known
         if (mrPlan.ok) {
-            rc = launch_level_select_mr(c, nCells, mrPlan, slot, l - 1);
+            rc = launch_level_select_mr(c, nCells, mrPlan, slot, l - 1, preNb);
             if (rc) return rc;
             np = -1;
             speculate = c->tieMode != 1;
@@ -1612,7 +1647,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
                 if (rc) return rc;
             }
         } else if (useSelect) {
-            rc = launch_level_select(c, nCells, slot, l - 1);
+            rc = launch_level_select(c, nCells, slot, l - 1, preNb);
             if (rc) return rc;
             np = -1;
         } else if (level_can_persist(c, nCells, M)) {
@@ -1642,11 +1677,20 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         // the same launch prepares the next level (not in the modes that build the next level's state elsewhere)
         NextLevel nx;
         memset(&nx, 0, sizeof(nx));
+        NextHist nh = no_next_hist();
+        int preNext = 0;
         uint32_t splitBlocks = ceil_div(nCells, 256);
         if (c->fuseNextLevel && l + 1 < lEnd && !tight && c->tieMode != 1 && 2u * nCells <= c->maxLevelCells && c->nLocal > 0) {
             const uint32_t nNext = 2u * nCells;
-            const SelMrPlan mrNext = sel_plan_mr(c, nNext, M);
-            const size_t hwNext = level_can_select(c, nNext, M) ? sel_plan(c, nNext).histWords : (mrNext.ok ? mrNext.histWords : 0);
+            preNext = prefuse_nb(c, nNext, M);
+            const SelMrPlan mrNext = sel_plan_mr(c, nNext, M, preNext);
+            const size_t hwNext = level_can_select(c, nNext, M) ? sel_plan(c, nNext, preNext).histWords : (mrNext.ok ? mrNext.histWords : 0);
+            if (preNext) {
+                nh.enabled = 1;
+                nh.hist = c->sel.hist;
+                nh.nb = preNext;
+                nh.mL = c->lvAlt.mL; nh.mR = c->lvAlt.mR; nh.axis = c->lvAlt.axis;
+            }
             nx.enabled = 1;
             nx.lv = c->lvAlt;
             nx.nc = (1 << M) - 1;
@@ -1662,7 +1706,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             CK(launch_pdl(c, k_split, dim3(splitBlocks), dim3(256), 0, c->d_heap, first, nCells, c->lv, c->d_range, c->d_total, c->d_final_cut, gate, nx));
             c->nOtherLaunch++;
             if (c->tieMode != 1) {
-                rc = launch_partition(c, nCells, c->d_tickets + (l - 1), gate);
+                rc = launch_partition(c, nCells, c->d_tickets + (l - 1), gate, nh);
                 if (rc) return rc;
             }
             if (!gate || select_mr_flagged(c, slot) == 0u) break;
@@ -1676,6 +1720,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             std::swap(c->d_tile_first, c->d_tile_first_alt);
             prepared = true;
         }
+        preNb = preNext;
         if (tight) {   // children boxes from their particles; needs the children's ranges as a level
             const uint32_t cf = (1u << l) - 1u, cn = 1u << l;
             if (cn <= c->maxLevelCells) {

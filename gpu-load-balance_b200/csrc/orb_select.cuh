@@ -50,21 +50,7 @@ struct SelCtl {           // statistics of the level (same meaning as PassCtl / 
     uint32_t *n_unfound_out;
 };
 
-// scale of the bin function over [L, R): nb / (R - L), or 0 (everything in bin 0) for an empty or non-finite box
-__device__ __forceinline__ float sel_scale(float L, float R, int nb) {
-    const float inf = __int_as_float(0x7f800000);
-    const float w = __fsub_rn(R, L);
-    float s = (w > 0.f && w < inf) ? __fdiv_rn((float)nb, w) : 0.f;
-    if (!(s < inf)) s = 0.f;
-    return s;
-}
-// Bin of a coordinate.  The ONLY property the method needs is that this is monotone non-decreasing in x for every
-// float (sub, mul by a non-negative scale, clamp and truncation all are); NaN products (inf * 0) go to bin 0.
-__device__ __forceinline__ int sel_bin(float x, float lo, float scale, int nb) {
-    float t = __fmul_rn(__fsub_rn(x, lo), scale);
-    t = fminf(fmaxf(t, 0.f), (float)(nb - 1));
-    return __float2int_rz(t);
-}
+// (sel_scale / sel_bin, the bin function, live in orb_kernels.cuh: the partition bins with them as well)
 
 // the reference's decision value for a count (orbit.cpp:204-205), literal float arithmetic
 struct SelTarget {
@@ -731,7 +717,7 @@ __device__ __forceinline__ void sel_for_each(const float *__restrict__ src, uint
 template <int THREADS, int MINBLOCKS, int U = 4>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float *__restrict__ x, const float *__restrict__ y,
                                                                     const float *__restrict__ z, LevelState lv, SelState ss,
-                                                                    SelCtl sc, uint32_t nCells, uint32_t candCap) {
+                                                                    SelCtl sc, uint32_t nCells, uint32_t candCap, int preNb) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     uint32_t *hist = reinterpret_cast<uint32_t *>(sel_smem);
     float *list = reinterpret_cast<float *>(hist + kSelBins2);
@@ -747,65 +733,94 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float 
         const float L = lv.mL[c], R = lv.mR[c];
         if (tid == 0) ss.flag[c] = 0u;
         if (!act) continue;
-        const int nb = max(K > 4096u ? kSelBins2 : 256, nThreads);
-        const int per = nb / nThreads;                    // 1, 2 or 8
-        const float lo = L, scale = sel_scale(L, R, nb), nbm1 = (float)(nb - 1);
+        // Rounds: HIST (bins over [lo, lo + nb/scale)), RESOLVE; if the candidate bins hold more particles than the
+        // block stages (a dense clump inside a wide cell), zoom the bin function onto them and go again - any monotone
+        // bin function over the whole cell is valid, so a round needs nothing from the previous one but the interval.
+        // Round 0 with preNb != 0: the cell's row (preNb bins over the margins) was built by the partition of the
+        // previous level (NextHist) and is loaded instead of read from the particles.  The scan runs over
+        // nbScan >= nb bins; bins beyond nb are empty (an empty trailing bin never becomes the first candidate bin;
+        // as the last one it only means "up to the end", which sel_bin_bounds and the search treat the same way).
         const float *col = pick_col(ax, x, y, z) + b;
-        for (int i = tid; i < nb; i += nThreads) hist[i] = 0u;
-        if (tid == 0) { sm.first = nb; sm.last = -1; sm.base = 0u; sm.end = 0u; sm.nlist = 0u; }
-        __syncthreads();
-        // ---- HIST ----
-        sel_for_each<U>(col, K, [&](float v) {
-            const float t = fminf(fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f), nbm1);      // == sel_bin(v, lo, scale, nb)
-            atomicAdd(&hist[__float2int_rz(t)], 1u);
-        });
-        __syncthreads();
-        // ---- RESOLVE ----
-        SelTarget tg;
-        tg.init(lv.total[c], lv.nleaf[c]);
-        uint32_t h[8];
-        uint32_t sum = 0;
+        int nb = preNb ? preNb : max(K > 4096u ? kSelBins2 : 256, nThreads);
+        float lo = L, scale = sel_scale(L, R, nb);
+        int first = 0, last = -1;
+        uint32_t base = 0, K2 = 0;
+        bool ok = false;
+        for (int round = 0; round < 3; ++round) {
+            const int nbScan = max(nb, nThreads);
+            const int per = nbScan / nThreads;                // 1, 2 or 8
+            const float nbm1 = (float)(nb - 1);
+            __syncthreads();
+            if (preNb && round == 0) for (int i = tid; i < nbScan; i += nThreads) hist[i] = i < nb ? __ldcg(ss.hist + (size_t)c * nb + i) : 0u;
+            else for (int i = tid; i < nbScan; i += nThreads) hist[i] = 0u;
+            if (tid == 0) { sm.first = nbScan; sm.last = -1; sm.base = 0u; sm.end = 0u; sm.nlist = 0u; }
+            __syncthreads();
+            // ---- HIST ----
+            if (!(preNb && round == 0)) {
+                sel_for_each<U>(col, K, [&](float v) {
+                    const float t = fminf(fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f), nbm1);      // == sel_bin(v, lo, scale, nb)
+                    atomicAdd(&hist[__float2int_rz(t)], 1u);
+                });
+                __syncthreads();
+            }
+            // ---- RESOLVE ----
+            SelTarget tg;
+            tg.init(lv.total[c], lv.nleaf[c]);
+            uint32_t h[8];
+            uint32_t sum = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { h[j] = (j < per) ? hist[tid * per + j] : 0u; sum += h[j]; }
-        uint32_t total;
-        const uint32_t excl = sel_block_scan(sum, sm.w, total);
-        int myFirst = nb, myLast = -1;
-        {
-            uint32_t p = excl;
+            for (int j = 0; j < 8; ++j) { h[j] = (j < per) ? hist[tid * per + j] : 0u; sum += h[j]; }
+            uint32_t total;
+            const uint32_t excl = sel_block_scan(sum, sm.w, total);
+            int myFirst = nbScan, myLast = -1;
+            {
+                uint32_t p = excl;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < per) {
-                    const uint32_t pn = p + h[j];
-                    const int bb = tid * per + j;
-                    if (tg.diff(pn) > -3) myFirst = min(myFirst, bb);
-                    if (tg.diff(p) < 3) myLast = max(myLast, bb);
-                    p = pn;
+                for (int j = 0; j < 8; ++j) {
+                    if (j < per) {
+                        const uint32_t pn = p + h[j];
+                        const int bb = tid * per + j;
+                        if (tg.diff(pn) > -3) myFirst = min(myFirst, bb);
+                        if (tg.diff(p) < 3) myLast = max(myLast, bb);
+                        p = pn;
+                    }
                 }
             }
-        }
-        if (myFirst < nb) atomicMin(&sm.first, myFirst);
-        if (myLast >= 0) atomicMax(&sm.last, myLast);
-        __syncthreads();
-        const int first = sm.first, last = sm.last;
-        {
-            uint32_t p = excl;
+            if (myFirst < nbScan) atomicMin(&sm.first, myFirst);
+            if (myLast >= 0) atomicMax(&sm.last, myLast);
+            __syncthreads();
+            first = sm.first; last = sm.last;
+            {
+                uint32_t p = excl;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < per) {
-                    const int bb = tid * per + j;
-                    if (bb == first) sm.base = p;
-                    p += h[j];
-                    if (bb == last) sm.end = p;
+                for (int j = 0; j < 8; ++j) {
+                    if (j < per) {
+                        const int bb = tid * per + j;
+                        if (bb == first) sm.base = p;
+                        p += h[j];
+                        if (bb == last) sm.end = p;
+                    }
                 }
             }
+            __syncthreads();
+            base = sm.base; K2 = sm.end - base;
+            if (!(first <= last)) break;                    // cannot happen (tests/test_select_model.py::ambiguous_range)
+            if (K2 <= candCap) { ok = true; break; }
+            // ---- zoom onto the candidate bins (widened by 1/16 of their width on either side) ----
+            const float a = __fadd_rn(lo, __fdiv_rn((float)first, scale));
+            const float e = __fadd_rn(lo, __fdiv_rn((float)min(last + 1, nb), scale));
+            const float w = __fsub_rn(e, a);
+            const int nbNew = max(kSelBins2, nThreads);
+            const float loNew = __fsub_rn(a, w * 0.0625f);
+            const float scNew = sel_scale(loNew, __fadd_rn(e, w * 0.0625f), nbNew);
+            if (!(scale > 0.f) || !(w > 0.f) || !(scNew > scale)) break;     // degenerate box / no resolution left: ties
+            lo = loNew; scale = scNew; nb = nbNew;
         }
-        __syncthreads();
-        const uint32_t base = sm.base, K2 = sm.end - base;
-        if (!(first <= last) || K2 > candCap) {       // too many candidates for one block: the iterative search takes the cell
+        if (!ok) {       // too many candidates for one block even after zooming (massive ties): the iterative search takes the cell
             if (tid == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
             continue;
         }
-        // ---- COMPACT: second read (L2), candidates into shared memory ----
+        // ---- COMPACT: another read (L2), candidates into shared memory ----
         float fLo, fHi;
         sel_bin_bounds((uint32_t)first, (uint32_t)last, nb, fLo, fHi);
         sel_for_each<U>(col, K, [&](float v) {

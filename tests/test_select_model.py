@@ -79,11 +79,12 @@ def ambiguous_range(prefix, base, prod):
     return first, last
 
 
-def select_bisection(v, L, R, total, nleaf, nb1=512, nb2=2048, amb_cap=2048, cand_cap=40960):
+def select_bisection(v, L, R, total, nleaf, nb1=512, nb2=2048, amb_cap=2048, cand_cap=40960, bins=None):
     """Histogram -> candidates -> in-block histogram -> replay.  Returns the literal loop's tuple, or None when the
-    cell must fall back to the iterative path (too many candidates, or a final cut outside the candidate bins)."""
+    cell must fall back to the iterative path (too many candidates, or a final cut outside the candidate bins).
+    `bins` = (lo, hi): range of the bin function when it is not the cell's margins (zoom rounds of k_sel_percell)."""
     prod = make_prod(total, nleaf)
-    lo1, s1 = bin_params(L, R, nb1)
+    lo1, s1 = bin_params(*(bins if bins is not None else (L, R)), nb1)
     b = sel_bin(v, lo1, s1, nb1)
     p1 = np.concatenate([[0], np.cumsum(np.bincount(b, minlength=nb1))])
     f1, l1 = ambiguous_range(p1, 0, prod)
@@ -193,3 +194,63 @@ def test_global_total_larger_than_local():
     prod = make_prod(1 << 27, 2)
     d = [diff_of(c, prod) for c in range((1 << 26) - 40, (1 << 26) + 40)]
     assert all(a <= b for a, b in zip(d, d[1:]))
+
+
+def zoom_range(v, lo, hi, nb, total, nleaf):
+    """One zoom step of k_sel_percell: the interval of the candidate bins, widened by 1/16 of its width on each side."""
+    prod = make_prod(total, nleaf)
+    lo1, s1 = bin_params(lo, hi, nb)
+    b = sel_bin(v, lo1, s1, nb)
+    p1 = np.concatenate([[0], np.cumsum(np.bincount(b, minlength=nb))])
+    f1, l1 = ambiguous_range(p1, 0, prod)
+    a = f32(lo1 + f32(f32(f1) / s1))
+    e = f32(lo1 + f32(f32(l1 + 1) / s1))
+    w = f32(e - a)
+    return f32(a - w * f32(0.0625)), f32(e + w * f32(0.0625)), int(p1[l1 + 1] - p1[f1])
+
+
+def test_zoomed_bin_function_gives_the_same_result():
+    """A dense clump inside a wide cell: the first histogram leaves too many candidates; zooming the bin function onto
+    the candidate bins (any monotone bin function over the whole cell is valid) isolates the median."""
+    rng = np.random.default_rng(21)
+    v = np.concatenate([rng.normal(0.31, 0.0004, 180_000), rng.random(20_000) - 0.5]).clip(-0.5, 0.5).astype(f32)
+    L, R = f32(-0.5), f32(0.5)
+    for nleaf in (2, 5, 64):
+        want = literal_bisection(v, L, R, v.size, nleaf)
+        assert select_bisection(v, L, R, v.size, nleaf, nb1=512, cand_cap=8192) is None      # too dense for one round
+        lo, hi, ncand = L, R, v.size
+        for _ in range(2):
+            lo, hi, ncand = zoom_range(v, lo, hi, 512 if (lo, hi) == (L, R) else 2048, v.size, nleaf)
+            got = select_bisection(v, L, R, v.size, nleaf, nb1=2048, cand_cap=8192, bins=(lo, hi))
+            if got is not None:
+                break
+        assert got is not None and same(got, want), (got, want)
+
+
+def test_sharded_histograms_and_local_left_count():
+    """Several ranks: the histogram rows add up to the global row, the candidates of all ranks are the global
+    candidates, and a rank's left count at the final cut is #{own particles below the candidate bins} +
+    #{own candidates < cut} (k_selx_resolve / k_selmr_finish)."""
+    rng = np.random.default_rng(33)
+    v = rng.random(200_000, dtype=f32) - f32(0.5)
+    v[::11] = f32(0.003)
+    L, R, nleaf, nb1 = f32(-0.5), f32(0.5), 6, 512
+    want = literal_bisection(v, L, R, v.size, nleaf)
+    got = select_bisection(v, L, R, v.size, nleaf, nb1=nb1)
+    assert got is not None and same(got, want)
+    cutf = mid_cut(got[0], got[1])
+    prod = make_prod(v.size, nleaf)
+    lo1, s1 = bin_params(L, R, nb1)
+    shards = np.array_split(v, 3)
+    rows = [np.bincount(sel_bin(sh, lo1, s1, nb1), minlength=nb1) for sh in shards]
+    glob = np.sum(rows, axis=0)
+    assert np.array_equal(glob, np.bincount(sel_bin(v, lo1, s1, nb1), minlength=nb1))
+    f1, l1 = ambiguous_range(np.concatenate([[0], np.cumsum(glob)]), 0, prod)
+    tot = 0
+    for sh, row in zip(shards, rows):
+        b = sel_bin(sh, lo1, s1, nb1)
+        own = sh[(b >= f1) & (b <= l1)]
+        nleft_l = int(row[:f1].sum()) + int(np.count_nonzero(own < cutf))
+        assert nleft_l == int(np.count_nonzero(sh < cutf))
+        tot += nleft_l
+    assert tot == want[4]
