@@ -108,7 +108,7 @@ struct orb_ctx {
     orb::LevelState lvAlt{};          // second set of the per-cell arrays: k_split prepares the next level in it while the
     uint32_t *d_tile_first_alt = nullptr;   // partition still reads this level's (orb_build swaps the two per level)
     bool fuseNextLevel = true;        // ORB_FUSE_NEXT=0: separate k_level_setup / k_tile_map launches per level
-    bool prefuseHist = true;          // ORB_PREFUSE=0: the partition does not build the next level's histogram rows
+    int prefuseHist = -1;             // ORB_PREFUSE: 1 the partition builds the next level's histogram rows, 0 never, unset: where it pays
     uint32_t *d_cnt_g_buf = nullptr;  // separate allreduce target (multi-rank only)
     float *d_final_cut = nullptr;     // [maxLevelCells]
     uint32_t *d_tile_first = nullptr; // [nMapTiles]
@@ -614,7 +614,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
             const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
             if ((rc = aux_begin(c, "finish", levelIdx))) return rc;
             CK(launch_pdl(c, k_sel_finish, dim3(grid), dim3(threads), smem, (const float *)cand, c->lv, ss, sc, nCells, nb1, candCap, c->d_err,
-                          dbgBase ? dbgBase + (size_t)2 * kDbgBlocks * 4 : (unsigned long long *)nullptr));
+                          dbgBase ? dbgBase + (size_t)2 * kDbgBlocks * 4 : (unsigned long long *)nullptr, preNb ? 1 : 2));
             if ((rc = aux_end(c))) return rc;
         }
         c->nCountLaunch += 1;
@@ -692,7 +692,11 @@ SelMrPlan sel_plan_mr(const orb_ctx *c, uint32_t nCells, int M, int forcedNb = 0
 // the level must use the selection search, a bin must not hold more candidates than one block stages, the rows must
 // fit.  Decided from rank-invariant numbers only (it shapes the multi-rank exchanges).
 int prefuse_nb(const orb_ctx *c, uint32_t nNext, int M) {
-    if (!c->prefuseHist) return 0;
+    if (c->prefuseHist == 0) return 0;
+    // Measured (profiles/r01x_*, r01z_*): binning in the partition costs ~10 us per level at 2^24 particles - as much as
+    // the HIST pass it replaces, whose column is still half in L2 at that size - but pays from ~2^25 particles per GPU
+    // (HIST is then a full HBM pass: -9 % build time at 2^27) and whenever ranks have to agree on the rows anyway.
+    if (c->prefuseHist < 0 && c->nRanks == 1 && c->nLocal < (1ull << 25)) return 0;
     // The partition's block histogram holds at most 1024 bins per child.  Where the level streams (HIST / COMPACT /
     // FINISH) the rows must have the bins the level would choose itself - coarser rows mean more candidates per bin
     // and, on clustered inputs, cells that overflow the finish kernel's staging; where one block searches a whole
@@ -803,7 +807,7 @@ int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
         if (peer) px.seq = ++c->xSeq;
         if ((rc = aux_begin(c, "mr_finish", levelIdx))) return rc;
-        CK(launch_pdl(c, kern, dim3(grid), dim3(threads), smem, c->lv, peer ? ss : sg, sc, mr, px, nCells, nb1, pl.candCap, c->d_err));
+        CK(launch_pdl(c, kern, dim3(grid), dim3(threads), smem, c->lv, peer ? ss : sg, sc, mr, px, nCells, nb1, pl.candCap, c->d_err, preNb ? 1 : 2));
         if ((rc = aux_end(c))) return rc;
         c->nUpdateLaunch++;
     }
@@ -1160,7 +1164,7 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     const char *st5 = getenv("ORB_SELECT_T512_MIN");
     if (st5 && atoi(st5) >= 1) c->selT512MinAvg = atoi(st5);
     const char *pfh = getenv("ORB_PREFUSE");
-    if (pfh) c->prefuseHist = atoi(pfh) != 0;
+    if (pfh) c->prefuseHist = atoi(pfh) != 0 ? 1 : 0;
     const char *fnl = getenv("ORB_FUSE_NEXT");
     if (fnl) c->fuseNextLevel = atoi(fnl) != 0;
     const char *se = getenv("ORB_SELECT");

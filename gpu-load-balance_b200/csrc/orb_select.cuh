@@ -639,14 +639,14 @@ __device__ __forceinline__ float *sel_stage_vals(float *sbuf, const float *__res
 // FINISH (streaming regime): one block per cell, candidates from the dense list written by COMPACT
 __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ cand, LevelState lv, SelState ss, SelCtl sc,
                                                      uint32_t nCells, int nb1, uint32_t cap, int *__restrict__ err,
-                                                     unsigned long long *dbg) {
+                                                     unsigned long long *dbg, int hbmPasses /* reads of the column: 2, or 1 when the partition built the rows */) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     float *sbuf = reinterpret_cast<float *>(sel_smem);
     uint32_t *hist2 = reinterpret_cast<uint32_t *>(sbuf + cap + 4);
     float *amb = reinterpret_cast<float *>(hist2 + kSelBins2);
     __shared__ SelSearchSmem sm;
     pdl_enter();
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(sc.passes_out, 2);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(sc.passes_out, hbmPasses);
     unsigned long long *bs = (dbg && blockIdx.x == 0) ? dbg : nullptr;    // ORB_DEBUG_TIMES=2: phases of block 0's first cell
     if (bs && threadIdx.x == 0) bs[0] = gtimer();
     for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ c
         if (!act) continue;
         if (b1 == b0) {     // empty cell: no block ever resolved it; the search on nothing finds the cut at once
             if (threadIdx.x == 0) ss.flag[c] = 0u;
-            sel_block_search(sbuf, 0u, 0u, 0, 0.f, 0.f, 1, 0, 0, hist2, amb, lv, ss, sc, c, 2, sm);
+            sel_block_search(sbuf, 0u, 0u, 0, 0.f, 0.f, 1, 0, 0, hist2, amb, lv, ss, sc, c, hbmPasses, sm);
             continue;
         }
         if (flg) continue;
@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ c
         const float *vals = sel_stage_vals(sbuf, cand + b0, K);
         if (threadIdx.x == 0) ss.cursor[c] = 0u;      // zero between levels (HIST counts into it)
         if (bs && threadIdx.x == 0) bs[1] = gtimer();
-        sel_block_search(vals, K, bs_, 1, L, sel_scale(L, R, nb1), nb1, (int)bf, (int)bl, hist2, amb, lv, ss, sc, c, 2, sm,
+        sel_block_search(vals, K, bs_, 1, L, sel_scale(L, R, nb1), nb1, (int)bf, (int)bl, hist2, amb, lv, ss, sc, c, hbmPasses, sm,
                          c == blockIdx.x ? bs : nullptr);
         if (bs && threadIdx.x == 0 && c == blockIdx.x) bs[7] = gtimer();
     }
@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float 
     __shared__ SelPerCellSmem sm;
     pdl_enter();
     const int tid = threadIdx.x, nThreads = (int)blockDim.x;
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(sc.passes_out, 2);
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(sc.passes_out, preNb ? 1 : 2);
     for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
         __syncthreads();
         const uint32_t act = lv.active[c], b = lv.bnd[c], K = lv.bnd[c + 1] - b;
@@ -746,6 +746,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float 
         int first = 0, last = -1;
         uint32_t base = 0, K2 = 0;
         bool ok = false;
+        int reads = 1;                                        // of the cell: HIST rounds + COMPACT
         for (int round = 0; round < 3; ++round) {
             const int nbScan = max(nb, nThreads);
             const int per = nbScan / nThreads;                // 1, 2 or 8
@@ -757,6 +758,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float 
             __syncthreads();
             // ---- HIST ----
             if (!(preNb && round == 0)) {
+                ++reads;
                 sel_for_each<U>(col, K, [&](float v) {
                     const float t = fminf(fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f), nbm1);      // == sel_bin(v, lo, scale, nb)
                     atomicAdd(&hist[__float2int_rz(t)], 1u);
@@ -829,7 +831,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float 
         });
         __syncthreads();
         // ---- FINISH ----
-        sel_block_search(list, K2, base, 1, lo, scale, nb, first, last, hist, amb, lv, ss, sc, c, 2, sm.search);
+        sel_block_search(list, K2, base, 1, lo, scale, nb, first, last, hist, amb, lv, ss, sc, c, reads, sm.search);
     }
 }
 
@@ -983,7 +985,7 @@ __global__ void __launch_bounds__(kThreads) k_selmr_prep(LevelState lv, SelState
 // all-gathered copy.  The last block to finish reports 1 + (cells flagged at this level) to the host.
 template <bool PEER>
 __global__ void __launch_bounds__(1024) k_selmr_finish(LevelState lv, SelState ss, SelCtl sc, SelMrState mr, SelPeers px,
-                                                       uint32_t nCells, int nb1, uint32_t cap, int *__restrict__ err) {
+                                                       uint32_t nCells, int nb1, uint32_t cap, int *__restrict__ err, int hbmPasses) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     float *sbuf = reinterpret_cast<float *>(sel_smem);
     uint32_t *hist2 = reinterpret_cast<uint32_t *>(sbuf + cap + 4);
@@ -994,7 +996,7 @@ __global__ void __launch_bounds__(1024) k_selmr_finish(LevelState lv, SelState s
     pdl_enter();
     if (PEER) selx_barrier(px);
     const int tid = threadIdx.x, lane = tid & 31, nThreads = (int)blockDim.x;
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(sc.passes_out, 2);
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(sc.passes_out, hbmPasses);
     for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
         __syncthreads();
         const uint32_t act = lv.active[c];
@@ -1049,7 +1051,7 @@ __global__ void __launch_bounds__(1024) k_selmr_finish(LevelState lv, SelState s
             off += n;
         }
         __syncthreads();
-        const bool done = sel_block_search(sbuf, K, base, 1, L, sel_scale(L, R, nb1), nb1, (int)bf, (int)bl, hist2, amb, lv, ss, sc, c, 2, sm);
+        const bool done = sel_block_search(sbuf, K, base, 1, L, sel_scale(L, R, nb1), nb1, (int)bf, (int)bl, hist2, amb, lv, ss, sc, c, hbmPasses, sm);
         __syncthreads();
         if (!done) continue;
         // local left count at the final cut: getCut() of the final margins is the found cut as well as the capped cell's cut

@@ -108,12 +108,38 @@ def test_build_bit_exact_vs_oracle(orb, oracle, n, d, m):
     assert st.active_passes > 0
 
 
+@pytest.mark.parametrize("n,d", [(1 << 16, 1 << 8), (1 << 18, 1 << 10), (100_003, 32), (3000, 1 << 10), (1 << 21, 1 << 6)])
+def test_build_bit_exact_with_partition_built_rows(orb, oracle, n, d, monkeypatch):
+    """ORB_PREFUSE=1: from level 2 on the selection search takes its histogram rows from the previous level's
+    partition (NextHist) - lean tiles, boundary tiles, one-block-per-cell levels, ragged tail."""
+    monkeypatch.setenv("ORB_PREFUSE", "1")
+    x, y, z = orb.generate_uniform(n)
+    ref = oracle.build(x, y, z, d, ties=oracle.TIES_CANONICAL)
+    with orb.Orb(n, d) as ctx:
+        ctx.upload(x, y, z)
+        heap, st = ctx.build()
+        gx, gy, gz = ctx.download()
+        rng = ctx.ranges()
+    assert list(st.iters[:st.n_levels]) == list(ref["stats"].iters[:st.n_levels])
+    assert st.search_fallback_cells == 0
+    # one read of the cut-axis column at the levels whose rows fit the histogram buffer, two elsewhere
+    assert st.passes[0] == 2 and st.passes[1] == 1 and all(p <= 2 for p in st.passes[:st.n_levels]), list(st.passes[:st.n_levels])
+    assert heap.tobytes() == ref["heap"].tobytes()
+    assert np.array_equal(rng, ref["ranges"][0])
+    for a, b in ((gx, ref["x"]), (gy, ref["y"]), (gz, ref["z"])):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 @pytest.mark.parametrize("gen", ["gaussian", "plummer"])
 @pytest.mark.parametrize("full", [False, True])
-def test_build_clustered_and_full_levels(orb, oracle, gen, full):
+def test_build_clustered_and_full_levels(orb, oracle, gen, full, monkeypatch):
+    """Also forces the partition-built histogram rows (ORB_PREFUSE=1; by default they are only used from 2^25 particles
+    per GPU or with several ranks) in the full-levels runs."""
     n, d = 1 << 17, 1 << 9
     x, y, z = orb.generate_clustered(n, gen)
     ref = oracle.build(x, y, z, d, ties=oracle.TIES_CANONICAL, full_levels=full)
+    if full:
+        monkeypatch.setenv("ORB_PREFUSE", "1")
     with orb.Orb(n, d) as ctx:
         ctx.upload(x, y, z)
         heap, st = ctx.build(full_levels=full)
@@ -178,6 +204,41 @@ def test_search_fallback_on_massive_ties(orb, oracle, n, d):
     assert np.array_equal(rng_, ref["ranges"][0])
     for a, b in ((gx, ref["x"]), (gy, ref["y"]), (gz, ref["z"])):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_search_zooms_on_dense_clumps(orb, oracle):
+    """Many tight clumps in a sparse background: at the levels where one block searches a whole cell (>= 64 cells), a
+    cell is much wider than the clump its median falls in, so the first histogram (the row the partition built, or the
+    block's own) leaves more candidates than the block stages; k_sel_percell then zooms its bin function onto the
+    candidate bins instead of leaving the cell to the iterative search.  Tree, ranges and particle order stay exact,
+    with the partition-built rows (default) and without (ORB_PREFUSE=0)."""
+    n, d = 1 << 22, 1 << 8
+    rng = np.random.default_rng(41)
+    centres = rng.uniform(-0.45, 0.45, (256, 3))
+    which = rng.integers(0, 256, n)
+    pos = centres[which] + rng.normal(0.0, 2e-5, (n, 3))
+    bg = rng.random(n) < 0.3
+    pos[bg] = rng.uniform(-0.5, 0.5, (int(bg.sum()), 3))
+    x, y, z = (np.ascontiguousarray(pos[:, a].clip(-0.5, 0.5).astype(np.float32)) for a in range(3))
+    ref = oracle.build(x, y, z, d, ties=oracle.TIES_CANONICAL)
+    for prefuse in ("1", "0"):
+        os.environ["ORB_PREFUSE"] = prefuse
+        try:
+            with orb.Orb(n, d) as ctx:
+                ctx.upload(x, y, z)
+                heap, st = ctx.build()
+                gx, gy, gz = ctx.download()
+                rng_ = ctx.ranges()
+        finally:
+            del os.environ["ORB_PREFUSE"]
+        assert list(st.iters[:st.n_levels]) == list(ref["stats"].iters[:st.n_levels])
+        assert list(st.not_found[:st.n_levels]) == list(ref["stats"].not_found[:st.n_levels])
+        assert heap.tobytes() == ref["heap"].tobytes()
+        assert np.array_equal(rng_, ref["ranges"][0])
+        for a, b in ((gx, ref["x"]), (gy, ref["y"]), (gz, ref["z"])):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        print(f"prefuse={prefuse}: passes {list(st.passes[:st.n_levels])} not_found {list(st.not_found[:st.n_levels])} "
+              f"fallback cells {st.search_fallback_cells}")
 
 
 def test_search_without_fallback_on_plain_inputs(orb, oracle):
