@@ -144,7 +144,7 @@ struct orb_ctx {
     unsigned long long *d_dbg_blocks = nullptr;   // ORB_DEBUG_TIMES=2: [kMaxLevels][kDbgPasses][kDbgBlocks][4] per-block stamps
     uint32_t dbgGrid[kMaxLevels] = {};
     uint32_t *d_lvl_unfound = nullptr; // [kMaxLevels]
-    // selection-based cut search (orb_select.cuh): single rank, default trial depth
+    // selection-based cut search (orb_select.cuh), default trial depth; several ranks: see selectMr below
     bool select = true;
     int selPerCellMinCells = 64;   // levels with at least this many cells: one block searches a whole cell
     bool selBigBlocks = true;      // ORB_SELECT_BIG_BLOCKS=0: no 1024 x 1 / 512 x 2 variants of k_sel_percell
@@ -490,7 +490,7 @@ int aux_end(orb_ctx *c) {
 
 // Selection-based cut search of a level (orb_select.cuh): two streaming passes + a per-cell finish where cells are
 // large, one read per cell where they fit in shared memory; then the iterative search (gated on the device, no host
-// round trip) for the cells it flagged.  Single rank, default trial depth.
+// round trip) for the cells it flagged.  This is the single-rank flow (launch_level_select_mr: several ranks).
 bool level_can_select(const orb_ctx *c, uint32_t nCells, int M) {
     return c->select && c->nRanks == 1 && c->nLocal > 0 && M == 3 && c->persist && c->occPersist[3] >= 1 && nCells >= 1;
 }
@@ -844,7 +844,8 @@ int select_mr_fallback(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx) 
 
 // Stable split of every cell of the level (canonical tie mode).  Kernel choice by average local cell size:
 // cells of at most 16 tiles (and enough of them to fill the GPU) -> one block per cell with a running carry;
-// otherwise persistent tile streaming with decoupled look-back (cooperative launch: all blocks co-resident).
+// otherwise cooperative reduce-then-scan over contiguous tile ranges (k_partition_coop: all blocks co-resident).
+// `nh`: also build the next level's histogram rows (NextHist).
 orb::NextHist no_next_hist() {
     orb::NextHist nh;
     memset(&nh, 0, sizeof(nh));

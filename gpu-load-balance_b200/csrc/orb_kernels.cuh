@@ -1407,11 +1407,10 @@ __global__ void k_ranges_from_level(const orb_cell *__restrict__ cells, uint32_t
 // =====================================================================================
 // Partition: replaces partition<256>+permute<256> (partitionGPU.cu:58-280) and the CPU Hoare loop
 // (partition.cpp:30-60) with a STABLE split by `x < cut` (canonical tie mode).
-// One launch for all cells.  Tiles of kPartTile particles; tile ids come from an atomic ticket so
-// look-back only ever waits on tiles that already run.  A tile needs a carry-in (number of left
-// particles of its first cell in earlier tiles) only if that cell began before the tile; tiles that
-// contain a cell boundary publish an inclusive prefix at once, so look-back chains restart at every
-// cell boundary.
+// One launch for all cells.  Tiles of kPartTile particles, staged in shared memory and written out in destination
+// order; a tile needs a carry-in (number of left particles of its first cell in earlier tiles) only if that cell began
+// before the tile.  k_partition_coop gets the carries by reduce-then-scan over contiguous per-block tile ranges,
+// k_partition_cells (small cells) walks each cell with one block.
 // =====================================================================================
 // Histogram rows of the NEXT level's selection search, produced while the particles pass through the partition
 // anyway: every particle is binned on its child's cut axis with the child's bin function (sel_bin over the child's

@@ -68,7 +68,7 @@ typedef struct orb_build_stats {
     float ms_partition;
     float ms_total;              /* CUDA-event time of the whole build on the context's stream */
     uint32_t search_fallback_cells; /* cells the selection-based cut search left to the iterative bisection (massive
-                                       ties, candidates beyond shared memory); 0 on multi-rank builds, which always iterate */
+                                       ties, candidates beyond shared memory); the same number on every rank */
 } orb_build_stats;
 
 /* ---- lifetime (replaces ServiceInit / ServiceFinalize allocation: init.cu:85-141, finalize.cu:15-45) ---- */
