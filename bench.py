@@ -9,8 +9,11 @@ per-cell count vectors cross NVLink (NCCL allreduce inside the library).
 
 value      = reference-equivalent particle-passes per second, whole job, particles resident in HBM:
              sum over bisection iterations of particles in still-unfound cells (what orbit.cpp's
-             loop streams; identical for the reference and for this build because the cut sequence
-             is bit-identical) / build time.
+             loop streams; for the same particles identical for the reference and for this build,
+             because the cut sequence is bit-identical) / build time.  (The reference arm counts its
+             own passes: run on several threads the unmodified reference draws a different, partly
+             duplicated particle set - its generator state is shared by its threads, init.cu:11-25 -
+             so its numerator differs by some percent; each arm divides its own work by its own time.)
 ms_per_step= ORB build time (CUDA events on the library's stream, max over ranks).
 e2e        = same metric through the public API with HOST buffers: pinned host x,y,z -> device,
              build, device -> host x,y,z + cell heap + ranges, inside the timed region.
@@ -36,6 +39,12 @@ sys.path.insert(0, str(ROOT / "tests"))
 X_LOG2, Y_LOG2 = 24, 12          # BASELINE config[1]
 METRIC = "orb_particle_passes_per_s"
 UNIT = "particle-passes/s"
+
+
+def workload_name(x_log2: int, y_log2: int, dist: str, n_levels: int, full: bool) -> str:
+    """config.workload, shared by both arms so that the two JSON lines name the same workload"""
+    return (f"2^{x_log2} {dist} particles per GPU (reference xorshf96 stream), 2^{y_log2} leaf cells, "
+            f"{n_levels} split levels ({'full' if full else 'reference-compatible'})")
 
 
 def host_cores() -> int:
@@ -92,7 +101,9 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"orbit {X_LOG2} {Y_LOG2} 0: 2^{X_LOG2} uniform particles, 2^{Y_LOG2} leaf cells, reference CPU-only mode",
+        "config": {"workload": workload_name(X_LOG2, Y_LOG2, "uniform", Y_LOG2 - 1, False),
+                   "particles_total": (1 << X_LOG2) * args.gpus, "leaf_cells": 1 << Y_LOG2,
+                   "reference_run": f"orbit {X_LOG2} {Y_LOG2} 0 (CPU-only mode of the unmodified reference), one build of the per-GPU workload per step",
                    "levels": Y_LOG2 - 1, "threads": cores},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"full workload (orbit {X_LOG2} {Y_LOG2} 0), {args.steps} run(s)", "reference_stdout": lines},
@@ -368,8 +379,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"2^{args.x} {args.dist} particles per GPU (reference xorshf96 stream), 2^{args.y} leaf cells, "
-                            f"{n_lv} split levels ({'full' if args.full_levels else 'reference-compatible'})",
+                "workload": workload_name(args.x, args.y, args.dist, n_lv, args.full_levels),
                 "particles_total": n_local * world, "leaf_cells": d, "parallelism": (f"particle shards x{world}; per-cell counts combined " +
                                                     ("by the selection search's two exchanges per level (NCCL allreduce of histogram rows, all-gather of candidates)"
                                                      if (world > 1 and os.environ.get("ORB_SELECT_MR", "1") != "0") else
