@@ -1,44 +1,32 @@
-// TraversePST.cpp — PST walk (reference: src/services/TraversePST.cpp:3-57).  The sibling's reply is
-// received into a heap buffer (the reference uses alloca(nOut), which cannot hold the count vectors of
-// 2^20-cell levels).
+// TraversePST.cpp — the walk over the rank tree (see TraversePST.h).
+// The replies of the upper halves are received into one heap buffer of maxOutBytes (the reference receives each
+// into alloca(nOut), which cannot hold the per-cell vectors of levels with 2^20 cells).
 #include "TraversePST.h"
 
+#include <algorithm>
 #include <vector>
 
-int TraversePST::operator()(int nIn, void *pIn, void *pOut) { return Traverse(node_pst, pIn, nIn, pOut, getMaxBytesOut()); }
+int TraversePST::operator()(int nIn, void *pIn, void *pOut) {
+    auto *rt = static_cast<mdl::mdlClass *>(tree_->mdl);
+    const int capacity = getMaxBytesOut();
 
-int TraversePST::Traverse(PST pst, void *vin, int nIn, void *vout, int nOut) {
-    if (pst->AmCore()) return Service(pst, vin, nIn, vout, nOut);
-    if (pst->OffNode()) return OffNode(pst, vin, nIn, vout, nOut);
-    if (pst->AmNode()) return AtNode(pst, vin, nIn, vout, nOut);
-    return Recurse(pst, vin, nIn, vout, nOut);
-}
+    // down: leave the request with the first rank of every upper half, keep to the lower halves
+    std::vector<int> outstanding;
+    PST node = tree_;
+    while (node->NotCore()) {
+        outstanding.push_back(rt->ReqService(node->idUpper, getServiceID(), pIn, nIn));
+        node = node->pstLower;
+    }
 
-// run another service over the same subtree
-int TraversePST::Traverse(unsigned sid, PST pst, void *vin, int nIn, void *vout, int nOut) {
-    auto *m = static_cast<mdl::mdlClass *>(pst->mdl);
-    auto *svc = dynamic_cast<TraversePST *>(m->GetService(sid));
-    mdlassert(pst->mdl, svc != nullptr);
-    return svc->Traverse(pst, vin, nIn, vout, nOut);
-}
+    // bottom: this rank's own work
+    int nOut = Service(node, pIn, nIn, pOut, capacity);
 
-int TraversePST::Recurse(PST pst, void *vin, int nIn, void *vout, int nOut) {
-    auto *m = static_cast<mdl::mdlClass *>(pst->mdl);
-    const int request = m->ReqService(pst->idUpper, getServiceID(), vin, nIn);
-    Traverse(pst->pstLower, vin, nIn, vout, nOut);
-    return m->GetReply(request, vout);
-}
-
-int TraverseCombinePST::Recurse(PST pst, void *vin, int nIn, void *vout, int nOut) {
-    auto *m = static_cast<mdl::mdlClass *>(pst->mdl);
-    const int request = m->ReqService(pst->idUpper, getServiceID(), vin, nIn);
-    Traverse(pst->pstLower, vin, nIn, vout, nOut);
-    std::vector<char> sibling((size_t)(nOut > 0 ? nOut : 1));
-    const int nOut2 = m->GetReply(request, sibling.data());
-    return Combine(vout, sibling.data(), nIn, nOut, nOut2);
-}
-
-int TraverseCountN::Combine(void *vout, void *vout2, int, int, int) {
-    *static_cast<output *>(vout) += *static_cast<output *>(vout2);
-    return sizeof(output);
+    // up: the most recently asked upper half is the sibling of the node we just finished
+    std::vector<char> theirs((size_t)std::max(capacity, 1));
+    while (!outstanding.empty()) {
+        const int nTheirs = rt->GetReply(outstanding.back(), theirs.data());
+        outstanding.pop_back();
+        nOut = Combine(pOut, theirs.data(), nIn, capacity, nTheirs);
+    }
+    return nOut;
 }

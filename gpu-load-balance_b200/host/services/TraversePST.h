@@ -1,57 +1,47 @@
-// TraversePST.h — service base classes (reference: src/services/TraversePST.h:11-60).
-// A service is called on thread 0; it walks the PST (binary tree over ranks): send the request to the
-// upper half, recurse into the lower half, fetch the reply, fold it with Combine.  At a leaf (one rank)
-// Service() runs.  Same class names and virtual signatures as the reference so service code ports 1:1.
-#ifndef ORB_HOST_TRAVERSEPST_H
-#define ORB_HOST_TRAVERSEPST_H
-#include <cstdint>
-
+// TraversePST.h — how one service call spreads over the rank threads.
+//
+// Replaces src/services/TraversePST.{h,cpp} of the reference.  What service code sees is unchanged — it derives
+// from TraverseCombinePST(pst, id, maxInBytes, maxOutBytes, name) and overrides Service() and Combine() with the
+// reference's signatures (TraversePST.h:37-46 there) — but the machinery underneath is a single loop rather than the
+// reference's mutually recursive Traverse / Recurse / OffNode / AtNode hooks: this host is one process with one
+// thread per GPU, so a node of the rank tree (pst.h) is either a leaf or it is not.
+#pragma once
 #include "pst.h"
 
+// Entry point the mdl runtime calls on the rank that received the request.  The call walks this rank's chain of
+// lower halves; on the way down every upper half gets the same request, at the bottom Service() does this rank's
+// work, on the way back up the upper halves' replies are folded in, innermost first.
 class TraversePST : public mdl::BasicService {
-    PST node_pst;
 public:
-    explicit TraversePST(PST pst, int service_id, int nInBytes, int nOutBytes, const char *service_name = "")
-        : BasicService(service_id, nInBytes, nOutBytes, service_name), node_pst(pst) {}
-    explicit TraversePST(PST pst, int service_id, int nInBytes, const char *service_name = "")
-        : BasicService(service_id, nInBytes, 0, service_name), node_pst(pst) {}
-    explicit TraversePST(PST pst, int service_id, const char *service_name = "")
-        : BasicService(service_id, 0, 0, service_name), node_pst(pst) {}
-    virtual ~TraversePST() = default;
+    TraversePST(PST pst, int service_id, int nInBytes = 0, int nOutBytes = 0, const char *service_name = "")
+        : BasicService(service_id, nInBytes, nOutBytes, service_name), tree_(pst) {}
+    ~TraversePST() override = default;
 
 protected:
-    virtual int operator()(int nIn, void *pIn, void *pOut) final;
-    virtual int Traverse(PST pst, void *vin, int nIn, void *vout, int nOut);
-    virtual int OffNode(PST pst, void *vin, int nIn, void *vout, int nOut) { return Recurse(pst, vin, nIn, vout, nOut); }
-    virtual int AtNode(PST pst, void *vin, int nIn, void *vout, int nOut) { return Recurse(pst, vin, nIn, vout, nOut); }
-    virtual int Recurse(PST pst, void *vin, int nIn, void *vout, int nOut);
+    int operator()(int nIn, void *pIn, void *pOut) final;
+
+    // this rank's share; returns the bytes written to vout (capacity nOut = the service's maxOutBytes)
     virtual int Service(PST pst, void *vin, int nIn, void *vout, int nOut) = 0;
-    static int Traverse(unsigned sid, PST pst, void *vin, int nIn, void *vout, int nOut);
+
+    // fold the reply of an upper half (nOut2 bytes at vout2) into vout (capacity nOut1); returns the size of the result.
+    // Default: the replies only signal completion.
+    virtual int Combine(void *vout, void *vout2, int nIn, int nOut1, int nOut2) {
+        (void)vout; (void)vout2; (void)nIn; (void)nOut2;
+        return nOut1;
+    }
+
+    PST tree() const { return tree_; }
+
+private:
+    PST tree_;     // this rank's root of the rank tree (ServiceSetAdd hangs the lower halves below it)
 };
 
-// Same input on every rank, fixed-size outputs folded pairwise by Combine().
+// Same input on every rank, fixed-size outputs folded pairwise: the only kind of service the ORB path has.
 class TraverseCombinePST : public TraversePST {
 public:
     explicit TraverseCombinePST(PST pst, int service_id, int nInBytes = 0, int nOutBytes = 0, const char *service_name = "")
         : TraversePST(pst, service_id, nInBytes, nOutBytes, service_name) {}
-    virtual ~TraverseCombinePST() = default;
 
 protected:
-    virtual int Recurse(PST pst, void *vin, int nIn, void *vout, int nOut) final;
-    virtual int Combine(void *vout, void *vout2, int nIn, int nOut1, int nOut2) = 0;
+    int Combine(void *vout, void *vout2, int nIn, int nOut1, int nOut2) override = 0;
 };
-
-// Services that return one 64-bit count, summed over ranks.
-class TraverseCountN : public TraverseCombinePST {
-public:
-    typedef uint64_t output;
-    explicit TraverseCountN(PST pst, int service_id, int nInBytes, const char *service_name = "")
-        : TraverseCombinePST(pst, service_id, nInBytes, sizeof(output), service_name) {}
-    explicit TraverseCountN(PST pst, int service_id, const char *service_name = "")
-        : TraverseCombinePST(pst, service_id, 0, sizeof(output), service_name) {}
-
-protected:
-    virtual int Combine(void *vout, void *vout2, int nIn, int nOut1, int nOut2) final;
-    virtual int Service(PST pst, void *vin, int nIn, void *vout, int nOut) override = 0;
-};
-#endif

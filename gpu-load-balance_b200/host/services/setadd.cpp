@@ -1,31 +1,36 @@
-// setadd.cpp — split the rank interval [idLower, idUpper) in halves until every PST leaf is one rank.
-// Single process, so no "keep a process together" adjustment is needed (reference setadd.cpp:24-30).
+// setadd.cpp — halve the rank interval until this rank is alone.
+// Every halving hands the upper half to its first rank (a request for this same service, so that rank organises its
+// own subtree concurrently) and hangs a new node for the lower half below the current one.  One process, so the
+// reference's adjustment that keeps a process's threads in one subtree (setadd.cpp:24-30 there) has nothing to do.
 #include "setadd.h"
 
 #include <type_traits>
-static_assert(std::is_trivial<ServiceSetAdd::input>(), "service inputs travel by memcpy");
+#include <vector>
+
+static_assert(std::is_trivial<ServiceSetAdd::input>::value, "service inputs travel by memcpy");
 
 int ServiceSetAdd::operator()(int nIn, void *pIn, void *) {
-    mdlassert(node_pst->mdl, nIn == (int)sizeof(input));
-    SetAdd(node_pst, static_cast<input *>(pIn));
-    return 0;
-}
+    MDL mdl = root_->mdl;
+    mdlassert(mdl, nIn == (int)sizeof(input));
+    const input all = *static_cast<const input *>(pIn);
+    mdlassert(mdl, all.idLower == mdlSelf(mdl));
 
-void ServiceSetAdd::SetAdd(PST pst, input *in) {
-    mdlassert(pst->mdl, pst->nLeaves == 1);
-    mdlassert(pst->mdl, in->idLower == mdlSelf(pst->mdl));
-    const int span = in->idUpper - in->idLower;
-    if (span <= 1) return;
-    const int middle = (in->idUpper + in->idLower) / 2;
-    pst->nLeaves += span - 1;
-    pst->nLower = middle - in->idLower;
-    pst->nUpper = in->idUpper - middle;
-    pst->idUpper = middle;
-    input upper(middle, in->idUpper);          // the upper half builds its own subtree ...
-    const int request = mdlReqService(pst->mdl, pst->idUpper, getServiceID(), &upper, sizeof(upper));
-    input lower(mdlSelf(pst->mdl), middle);    // ... while this thread descends into the lower half
-    pst->pstLower = new pstNode(pst->mdl);
-    pst->pstLower->lcl = pst->lcl;
-    SetAdd(pst->pstLower, &lower);
-    mdlGetReply(pst->mdl, request, nullptr, nullptr);
+    std::vector<int> outstanding;
+    PST node = root_;
+    for (int first = all.idLower, end = all.idUpper; end - first > 1;) {
+        mdlassert(mdl, node->nLeaves == 1);               // not organised yet
+        const int middle = (first + end) / 2;
+        node->nLeaves = end - first;
+        node->nLower = middle - first;
+        node->nUpper = end - middle;
+        node->idUpper = middle;
+        input upperHalf(middle, end);
+        outstanding.push_back(mdlReqService(mdl, middle, getServiceID(), &upperHalf, sizeof(upperHalf)));
+        node->pstLower = new pstNode(mdl);
+        node->pstLower->lcl = node->lcl;
+        node = node->pstLower;
+        end = middle;
+    }
+    for (auto it = outstanding.rbegin(); it != outstanding.rend(); ++it) mdlGetReply(mdl, *it, nullptr, nullptr);
+    return 0;
 }
