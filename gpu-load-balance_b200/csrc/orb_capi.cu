@@ -148,6 +148,8 @@ struct orb_ctx {
     bool select = true;
     int selPerCellMinCells = 64;   // levels with at least this many cells: one block searches a whole cell
     bool selBigBlocks = true;      // ORB_SELECT_BIG_BLOCKS=0: no 1024 x 1 / 512 x 2 variants of k_sel_percell
+    bool selBigFinish = false;     // ORB_SELECT_BIG_FINISH=1 (experimental, unmeasured): streaming levels gather any number of
+                                   // candidates and the finish kernel searches an over-full list in global memory
     int selBinAvg = 8192;          // ORB_SELECT_BIN_AVG: HIST bins per cell are doubled (512..8192) until a bin holds at most this many particles on average
     int selT512MinAvg = 32768;     // ORB_SELECT_T512_MIN: cells of at least this many particles get 512-thread blocks
     bool pdl = true;               // programmatic dependent launch between the small kernels of a level
@@ -602,7 +604,8 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
             const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 3));
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                          nCells, nL, nTiles, nb1, 1, candCap, dbgBase ? dbgBase + (size_t)kDbgBlocks * 4 : (unsigned long long *)nullptr,
+                          nCells, nL, nTiles, nb1, 1, c->selBigFinish ? 0x7fffffffu : candCap,
+                          dbgBase ? dbgBase + (size_t)kDbgBlocks * 4 : (unsigned long long *)nullptr,
                           (float *)nullptr, 0u, 0));
             if ((rc = count_event_end(c))) return rc;
         }
@@ -614,7 +617,8 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
             const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
             if ((rc = aux_begin(c, "finish", levelIdx))) return rc;
             CK(launch_pdl(c, k_sel_finish, dim3(grid), dim3(threads), smem, (const float *)cand, c->lv, ss, sc, nCells, nb1, candCap, c->d_err,
-                          dbgBase ? dbgBase + (size_t)2 * kDbgBlocks * 4 : (unsigned long long *)nullptr, preNb ? 1 : 2));
+                          dbgBase ? dbgBase + (size_t)2 * kDbgBlocks * 4 : (unsigned long long *)nullptr, preNb ? 1 : 2,
+                          c->selBigFinish ? 1 : 0));
             if ((rc = aux_end(c))) return rc;
         }
         c->nCountLaunch += 1;
@@ -1160,6 +1164,8 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     if (spc && atoi(spc) >= 1) c->selPerCellMinCells = atoi(spc);
     const char *sbb = getenv("ORB_SELECT_BIG_BLOCKS");
     if (sbb) c->selBigBlocks = atoi(sbb) != 0;
+    const char *sbf = getenv("ORB_SELECT_BIG_FINISH");
+    if (sbf) c->selBigFinish = atoi(sbf) != 0;
     const char *sba = getenv("ORB_SELECT_BIN_AVG");
     if (sba && atoi(sba) >= 64) c->selBinAvg = atoi(sba);
     const char *st5 = getenv("ORB_SELECT_T512_MIN");

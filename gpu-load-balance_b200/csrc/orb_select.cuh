@@ -639,7 +639,8 @@ __device__ __forceinline__ float *sel_stage_vals(float *sbuf, const float *__res
 // FINISH (streaming regime): one block per cell, candidates from the dense list written by COMPACT
 __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ cand, LevelState lv, SelState ss, SelCtl sc,
                                                      uint32_t nCells, int nb1, uint32_t cap, int *__restrict__ err,
-                                                     unsigned long long *dbg, int hbmPasses /* reads of the column: 2, or 1 when the partition built the rows */) {
+                                                     unsigned long long *dbg, int hbmPasses /* reads of the column: 2, or 1 when the partition built the rows */,
+                                                     int allowGlobal /* more candidates than `cap`: search them where they lie instead of failing */) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     float *sbuf = reinterpret_cast<float *>(sel_smem);
     uint32_t *hist2 = reinterpret_cast<uint32_t *>(sbuf + cap + 4);
@@ -663,11 +664,14 @@ __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ c
             continue;
         }
         if (flg) continue;
-        if (cur != K || K > cap) {   // cannot happen: HIST and COMPACT use the same bin function
+        if (cur != K || (K > cap && !allowGlobal)) {   // cannot happen: HIST and COMPACT use the same bin function
             if (threadIdx.x == 0) atomicExch(err, ORB_ERR_STATE);
             continue;
         }
-        const float *vals = sel_stage_vals(sbuf, cand + b0, K);
+        // Normally the candidates are staged in shared memory.  With allowGlobal (experimental, ORB_SELECT_BIG_FINISH=1)
+        // COMPACT gathers any number of them (the list has room for the whole cell) and a dense bin's candidates are
+        // searched in place: the block search only needs a pointer it can read a few times.
+        const float *vals = K <= cap ? sel_stage_vals(sbuf, cand + b0, K) : cand + b0;
         if (threadIdx.x == 0) ss.cursor[c] = 0u;      // zero between levels (HIST counts into it)
         if (bs && threadIdx.x == 0) bs[1] = gtimer();
         sel_block_search(vals, K, bs_, 1, L, sel_scale(L, R, nb1), nb1, (int)bf, (int)bl, hist2, amb, lv, ss, sc, c, hbmPasses, sm,
