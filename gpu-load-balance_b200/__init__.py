@@ -109,6 +109,20 @@ class PeerInfo(C.Structure):
 PEER_INFO_BYTES = C.sizeof(PeerInfo)
 
 
+class LevelPlan(C.Structure):
+    """orb_level_plan: how a level would be searched (include/orb_b200.h, orb_plan_level)."""
+
+    _fields_ = [
+        ("search", C.c_int32),
+        ("hist_bins", C.c_int32),
+        ("cand_cap", C.c_uint32),
+        ("slot_words", C.c_uint32),
+        ("hist_words", C.c_uint64),
+        ("prefuse_bins", C.c_int32),
+        ("reserved_", C.c_int32),
+    ]
+
+
 class OrbError(RuntimeError):
     pass
 
@@ -146,6 +160,7 @@ def lib() -> C.CDLL:
         "orb_version": ([], C.c_int),
         "orb_set_trial_depth": ([P, C.c_int], C.c_int),
         "orb_set_profile": ([P, C.c_int], C.c_int),
+        "orb_plan_level": ([C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(LevelPlan)], C.c_int),
         "orb_set_tie_mode": ([P, C.c_int], C.c_int),
         "orb_comm_unique_id": ([P], C.c_int),
         "orb_comm_init": ([P, P, C.c_int, C.c_int], C.c_int),
@@ -186,6 +201,16 @@ def _f32(a) -> np.ndarray:
 
 def _ptr(a: np.ndarray):
     return C.c_void_p(a.ctypes.data)
+
+
+def plan_level(n_local: int, n_cells: int, n_leaf_cells: int, n_ranks: int = 1, n_global: int | None = None,
+               n_local_min: int | None = None, prefuse: int = -1) -> LevelPlan:
+    """orb_plan_level: pure host arithmetic, works without a GPU."""
+    out = LevelPlan()
+    _check(lib().orb_plan_level(n_local, n_global if n_global is not None else n_local * n_ranks,
+                                n_local_min if n_local_min is not None else n_local, n_ranks, n_leaf_cells, n_cells, prefuse,
+                                C.byref(out)), "orb_plan_level")
+    return out
 
 
 # ----------------------------------------------------------------------------- inputs

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <memory>
 #include <vector>
 
 #if defined(__x86_64__)
@@ -1242,6 +1243,43 @@ int orb_set_tie_mode(orb_ctx *c, int mode) {
     if (!c) return fail(ORB_ERR_ARG, "null ctx");
     if (mode != 0 && mode != 1) return fail(ORB_ERR_ARG, "tie mode must be 0 (canonical) or 1 (hoare)");
     c->tieMode = mode;
+    return ORB_OK;
+}
+
+int orb_plan_level(uint64_t n_local, uint64_t n_global, uint64_t n_local_min, int n_ranks, uint32_t n_leaf_cells,
+                   uint32_t n_cells, int prefuse_mode, orb_level_plan *out) {
+    if (!out || n_cells == 0 || n_ranks < 1) return fail(ORB_ERR_ARG, "bad plan arguments");
+    // a context that never touches a device: only the fields the planning functions read
+    std::unique_ptr<orb_ctx> c(new orb_ctx());
+    c->nLocal = n_local;
+    c->nGlobal = n_ranks > 1 ? n_global : n_local;
+    c->nLocalMin = n_ranks > 1 ? n_local_min : n_local;
+    c->nRanks = n_ranks;
+    c->d = n_leaf_cells;
+    c->maxLevelCells = std::max<uint32_t>(1u, n_leaf_cells);
+    c->selHistWords = (size_t)n_local / 16 + 2 * (size_t)orb::kSelBinsMax;
+    c->occPersist[3] = 1;
+    c->prefuseHist = prefuse_mode < 0 ? -1 : (prefuse_mode ? 1 : 0);
+    c->d_slots_g = reinterpret_cast<float *>(uintptr_t(16));     // "allocated" (sel_plan_mr only tests the pointer)
+    memset(out, 0, sizeof(*out));
+    const int M = 3;
+    const int pre = n_cells >= 2 ? prefuse_nb(c.get(), n_cells, M) : 0;
+    out->prefuse_bins = pre;
+    const SelMrPlan mr = sel_plan_mr(c.get(), n_cells, M, pre);
+    if (mr.ok) {
+        out->search = 3;
+        out->hist_bins = mr.nb1;
+        out->cand_cap = mr.candCap;
+        out->slot_words = mr.slotWords;
+        out->hist_words = mr.histWords;
+    } else if (level_can_select(c.get(), n_cells, M)) {
+        const SelPlan p = sel_plan(c.get(), n_cells, pre);
+        out->search = p.cellsInSmem ? 2 : 1;
+        out->hist_bins = (p.cellsInSmem && !pre) ? 0 : p.nb1;
+        out->cand_cap = p.cellsInSmem ? p.cellCap : p.candCap;
+        out->hist_words = p.histWords;
+    }
+    c->d_slots_g = nullptr;
     return ORB_OK;
 }
 

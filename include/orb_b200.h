@@ -90,6 +90,24 @@ int orb_set_tie_mode(orb_ctx *ctx, int mode);
  * stream and orb_build_stats.ms_count / ms_partition are filled (also enabled by env ORB_PROFILE=1) */
 int orb_set_profile(orb_ctx *ctx, int on);
 
+/* ---- diagnostic: how a level would be searched (pure host arithmetic, needs no device) ----
+ * A context of n_local particles on one of n_ranks ranks (n_global particles in all, smallest shard n_local_min), level
+ * of n_cells cells, prev_cells_prefuse = whether the previous level's partition may build this level's histogram rows
+ * (ORB_PREFUSE semantics: -1 automatic, 0 never, 1 always).  Everything that shapes a multi-rank exchange depends on
+ * (n_cells, n_global, n_local_min, n_ranks) only - never on n_local - so that all ranks take the same branch. */
+typedef struct orb_level_plan {
+    int32_t search;        /* 0 iterative count kernels, 1 selection: streaming passes, 2 selection: one block per cell,
+                              3 selection over several ranks (two exchanges) */
+    int32_t hist_bins;     /* bins per cell of the histogram rows (0: none) */
+    uint32_t cand_cap;     /* candidates one finish block stages */
+    uint32_t slot_words;   /* several ranks: words of one rank's candidate slot per cell (last word = count) */
+    uint64_t hist_words;   /* words of histogram rows the level needs in global memory */
+    int32_t prefuse_bins;  /* != 0: the previous level's partition builds this level's rows with this many bins */
+    int32_t reserved_;
+} orb_level_plan;
+int orb_plan_level(uint64_t n_local, uint64_t n_global, uint64_t n_local_min, int n_ranks, uint32_t n_leaf_cells,
+                   uint32_t n_cells, int prefuse_mode, orb_level_plan *out);
+
 /* ---- multi-GPU (replaces the mdl2 reduce tree, TraversePST.cpp:28-44 + Combine in countLeft.cpp:44-53) ----
  * One rank per GPU.  Either let the library own the communicator (rank 0 makes an id, the caller
  * broadcasts the 128 bytes by any means, every rank calls orb_comm_init), or attach an existing

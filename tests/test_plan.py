@@ -1,0 +1,71 @@
+"""CPU tests of the host-side planning of a level's cut search (orb_plan_level: pure host arithmetic, the same functions
+orb_build uses).  What matters most: with several ranks every quantity that shapes an exchange (bins, slot size, which
+search a level uses, whether the partition pre-builds the rows) depends only on numbers all ranks share - a rank that
+took a different branch would leave its peers waiting in a cross-rank barrier or a collective."""
+import pytest
+
+POW2 = {1 << k for k in range(5, 21)}
+
+
+def fields(p):
+    return (p.search, p.hist_bins, p.cand_cap, p.slot_words, p.hist_words, p.prefuse_bins)
+
+
+@pytest.mark.parametrize("ranks", [2, 4, 8])
+@pytest.mark.parametrize("x_min", [14, 20, 24, 27])
+def test_multi_rank_plan_depends_on_shared_numbers_only(orb, ranks, x_min):
+    n_min = (1 << x_min) + 12345
+    shards = [n_min, n_min + n_min // 3, 2 * n_min][:ranks] + [n_min + 7] * max(0, ranks - 3)
+    n_global = sum(shards)
+    for y in (4, 12, 16, 20):
+        for level in range(1, y + 1):
+            n_cells = 1 << (level - 1)
+            plans = [fields(orb.plan_level(n, n_cells, 1 << y, n_ranks=ranks, n_global=n_global, n_local_min=n_min)) for n in shards]
+            assert all(p == plans[0] for p in plans), (ranks, x_min, y, level, plans)
+            search, bins, cand_cap, slot_words, hist_words, pre = plans[0]
+            assert search in (0, 3)
+            if search == 3:
+                assert n_cells <= 2048
+                assert bins in (512, 1024, 2048, 4096, 8192) and hist_words == n_cells * bins
+                assert hist_words <= n_min // 16 + 2 * 8192              # fits every rank's buffer, also the smallest shard's
+                assert 4096 < cand_cap <= 49152
+                assert slot_words in POW2 and slot_words * n_cells <= 1 << 20
+                assert pre in (0, 512, 1024) and (pre == 0 or pre == bins)
+            else:
+                assert (bins, cand_cap, slot_words, hist_words, pre) == (0, 0, 0, 0, 0)
+
+
+@pytest.mark.parametrize("x", [10, 16, 20, 24, 26, 27, 30])
+def test_single_rank_plan_bounds(orb, x):
+    n = 1 << x
+    for y in (3, 12, 16, 20):
+        for level in range(1, y + 1):
+            n_cells = 1 << (level - 1)
+            for mode in (-1, 0, 1):
+                p = orb.plan_level(n, n_cells, 1 << y, prefuse=mode)
+                assert p.search in (1, 2) and p.slot_words == 0
+                assert p.hist_words <= n // 16 + 2 * 8192
+                assert p.cand_cap <= 49152
+                assert p.prefuse_bins in (0, 512, 1024)
+                if mode == 0 or level == 1:
+                    assert p.prefuse_bins == 0
+                if p.prefuse_bins:
+                    assert p.hist_bins == p.prefuse_bins and p.hist_words == n_cells * p.prefuse_bins
+                if p.search == 1:
+                    assert p.hist_bins in (512, 1024, 2048, 4096, 8192) and p.hist_words == n_cells * p.hist_bins
+                    # a bin of the streaming levels holds at most 16384 particles on average: one block can stage a few bins
+                    assert (n // n_cells) // p.hist_bins <= 16384 or p.hist_bins == 8192
+                if p.search == 2:
+                    assert n_cells >= 64 and n // n_cells <= 1 << 20
+
+
+def test_automatic_prefuse_policy(orb):
+    """One rank: the partition pre-builds the next level's rows from 2^25 particles on; several ranks: always."""
+    small = [orb.plan_level(1 << 24, 1 << l, 1 << 12).prefuse_bins for l in range(1, 11)]
+    big = [orb.plan_level(1 << 27, 1 << l, 1 << 16).prefuse_bins for l in range(1, 15)]
+    forced = [orb.plan_level(1 << 24, 1 << l, 1 << 12, prefuse=1).prefuse_bins for l in range(1, 11)]
+    multi = [orb.plan_level(1 << 24, 1 << l, 1 << 12, n_ranks=2).prefuse_bins for l in range(1, 11)]
+    assert not any(small)
+    assert big[:2] == [0, 0] and all(big[3:])          # 2^26 / 2^25-particle cells want more than 1024 bins: separate pass
+    assert all(forced)
+    assert multi[0] == 0 and all(multi[1:])            # 2 x 2^24 in 2 cells: 2048 bins wanted, more than the partition holds
