@@ -136,16 +136,16 @@ def _select_worker(rank, world, port, n_local, nleaf, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nleaf", [2, 7])
-def test_two_rank_selection_search_protocol(nleaf):
-    """Both ranks end with the literal loop's margins / iterations / global count, and their local left counts add up."""
+@pytest.mark.parametrize("world,nleaf", [(2, 2), (2, 7), (3, 5)])
+def test_selection_search_protocol_over_ranks(world, nleaf):
+    """Every rank ends with the literal loop's margins / iterations / global count, and the local left counts add up."""
     import torch.multiprocessing as mp
     import test_select_model as m
 
-    world, n_local = 2, 1 << 15
+    n_local = 1 << 15
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + (os.getpid() % 2000) + nleaf
+    port = 31500 + (os.getpid() % 2000) + nleaf + 10 * world
     procs = [ctx.Process(target=_select_worker, args=(r, world, port, n_local, nleaf, q)) for r in range(world)]
     for p in procs:
         p.start()
