@@ -58,3 +58,13 @@ def test_reference_arm_line():
     # unsynchronised), so a multi-threaded run draws a different - partly duplicated - particle set every time.
     passes = d["value"] * d["ms_per_step"] * 1e-3
     assert 0.5 * g["particle_passes_per_build"] < passes < 2.0 * g["particle_passes_per_build"]
+
+
+def test_cpu_baseline_helper_runs_here():
+    """The cpu_baseline leg of the GPU arm is plain CPU work: run it on a small workload."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    c = bench.cpu_baseline_beside(18, 6)
+    assert c["value"] and c["value"] > 0 and c["cores"] >= 1 and c["kind"] in ("reference", "port")
+    assert "median of" in c["sample"] and c["build_ms"] > 0
