@@ -4,6 +4,7 @@
 #include "TraversePST.h"
 
 #include <algorithm>
+#include <memory>
 #include <vector>
 
 int TraversePST::operator()(int nIn, void *pIn, void *pOut) {
@@ -21,12 +22,16 @@ int TraversePST::operator()(int nIn, void *pIn, void *pOut) {
     // bottom: this rank's own work
     int nOut = Service(node, pIn, nIn, pOut, capacity);
 
-    // up: the most recently asked upper half is the sibling of the node we just finished
-    std::vector<char> theirs((size_t)std::max(capacity, 1));
-    while (!outstanding.empty()) {
-        const int nTheirs = rt->GetReply(outstanding.back(), theirs.data());
-        outstanding.pop_back();
-        nOut = Combine(pOut, theirs.data(), nIn, capacity, nTheirs);
+    // up: the most recently asked upper half is the sibling of the node we just finished.  (The receive buffer is only
+    // made when there is something to receive: a single rank never pays for maxOutBytes, which is tens of MB for the
+    // per-cell services at 2^20 cells.)
+    if (!outstanding.empty()) {
+        std::unique_ptr<char[]> theirs(new char[(size_t)std::max(capacity, 1)]);
+        while (!outstanding.empty()) {
+            const int nTheirs = rt->GetReply(outstanding.back(), theirs.get());
+            outstanding.pop_back();
+            nOut = Combine(pOut, theirs.get(), nIn, capacity, nTheirs);
+        }
     }
     return nOut;
 }
