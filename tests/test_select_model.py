@@ -254,3 +254,45 @@ def test_sharded_histograms_and_local_left_count():
         assert nleft_l == int(np.count_nonzero(sh < cutf))
         tot += nleft_l
     assert tot == want[4]
+
+
+def test_randomised_inputs_and_capacities():
+    """Seeded fuzz: distributions with clumps, lattices (many duplicates), ties, narrow ranges; random bin counts and
+    capacities; with and without a zoomed bin function.  Whenever the method answers, it answers like the literal loop."""
+    rng = np.random.default_rng(20261017)
+    answered = 0
+    for _ in range(160):
+        n = int(rng.choice([3, 17, 200, 5000, 30000]))
+        kind = int(rng.integers(0, 6))
+        if kind == 0:
+            v = rng.random(n, dtype=f32) - f32(0.5)
+        elif kind == 1:
+            v = rng.normal(rng.uniform(-0.4, 0.4), 10 ** rng.uniform(-6, -1), n).clip(-0.5, 0.5).astype(f32)
+        elif kind == 2:
+            v = rng.random(n, dtype=f32) - f32(0.5)
+            for _k in range(int(rng.integers(1, 4))):
+                v[rng.random(n) < rng.uniform(0.01, 0.4)] = f32(rng.uniform(-0.5, 0.5))
+        elif kind == 3:
+            v = (np.round((rng.random(n) - 0.5) * 2 ** int(rng.integers(3, 12))) / 2 ** 12).astype(f32)
+        elif kind == 4:
+            v = np.concatenate([rng.normal(0.1, 1e-4, n // 2), rng.random(n - n // 2) - 0.5]).clip(-0.5, 0.5).astype(f32)
+        else:
+            v = (rng.random(n, dtype=f32) * f32(1e-3) + f32(0.2)).astype(f32)
+        lo, hi = f32(-0.5), f32(0.5)
+        if rng.random() < 0.3:
+            lo, hi = f32(v.min()), f32(np.nextafter(v.max(), f32(1)))
+        nleaf = int(rng.integers(2, 40))
+        nb1, nb2 = int(rng.choice([16, 64, 512, 2048])), int(rng.choice([32, 256, 2048]))
+        amb, cap = int(rng.choice([4, 64, 2048])), int(rng.choice([50, 1000, 40960]))
+        want = literal_bisection(v, lo, hi, v.size, nleaf)
+        got = select_bisection(v, lo, hi, v.size, nleaf, nb1=nb1, nb2=nb2, amb_cap=amb, cand_cap=cap)
+        if got is not None:
+            answered += 1
+            assert same(got, want), (kind, n, nleaf, nb1, nb2, amb, cap, got, want)
+        zl, zh, _ = zoom_range(v, lo, hi, nb1, v.size, nleaf)
+        if np.isfinite(zl) and np.isfinite(zh) and zh > zl:
+            got = select_bisection(v, lo, hi, v.size, nleaf, nb1=2048, nb2=nb2, amb_cap=amb, cand_cap=cap, bins=(zl, zh))
+            if got is not None:
+                answered += 1
+                assert same(got, want), ("zoom", kind, n, nleaf, nb1, got, want)
+    assert answered > 150
