@@ -129,7 +129,7 @@ class OrbError(RuntimeError):
 
 def build_library(force: bool = False) -> Path:
     """Compile liborb_b200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    srcs = [PKG_DIR / "csrc" / n for n in ("orb_capi.cu", "orb_kernels.cuh", "orb_generate.cpp")] + [HEADER]
+    srcs = sorted((PKG_DIR / "csrc").glob("*.cu*")) + sorted((PKG_DIR / "csrc").glob("*.cpp")) + [PKG_DIR / "csrc" / "Makefile", HEADER]
     if not force and LIB_PATH.exists() and all(LIB_PATH.stat().st_mtime >= s.stat().st_mtime for s in srcs):
         return LIB_PATH
     subprocess.run(["make", "-C", str(PKG_DIR / "csrc")] + (["-B"] if force else []), check=True, capture_output=True)

@@ -23,6 +23,7 @@
 
 #include "orb_kernels.cuh"
 #include "orb_select.cuh"
+#include "orb_exchange.cuh"
 
 namespace {
 
@@ -81,7 +82,8 @@ struct NcclApi {
 constexpr int kMaxLevels = 40;
 constexpr uint32_t kSelValsCap = 49152;   // values one block of the selection search stages in shared memory (192 KB)
 constexpr uint32_t kSelMrMaxCells = 2048; // several ranks: levels up to this many cells use the selection search
-constexpr size_t kSelSlotWordsTotal = (size_t)1 << 20;   // candidate slots of one rank and level (4 MB)
+constexpr size_t kSelSlotWordsTotal = (size_t)1 << 20;   // candidate slots of one rank and level (4 MB; v2 arena: at least this)
+constexpr uint32_t kSelSlotWordsMax = 65536;             // largest slot of one rank and cell
 constexpr int kDbgPasses = 12;      // ORB_DEBUG_TIMES=2: passes and blocks recorded per level
 constexpr uint32_t kDbgBlocks = 1024;
 constexpr int kPassSlots = 40;   // >= 32 passes + slack, per level
@@ -181,6 +183,13 @@ struct orb_ctx {
     uint32_t xOffCursor = 0, xOffSlots = 0, xOffHist = 0;   // word offsets, identical on all ranks
     uint32_t *peerX[orb::kMaxPeers] = {nullptr};
     uint32_t xSeq = 0;                 // exchanges issued so far (same on all ranks)
+    // protocol v2 (orb_exchange.cuh): owner-computed search over peer memory for levels of any size.  Arena regions
+    // beyond the v1 ones: result records | candidate counts | received candidate slots | global rows
+    bool mrV2 = true;                  // ORB_MR_V1=1: the two-exchange kernels of orb_select.cuh (levels of <= 2048 cells)
+    bool mrSelf = false;               // ORB_MR_SELF=1 (testing): one rank runs the multi-rank protocol against itself
+    uint32_t xOffRes = 0, xOffRecvCnt = 0, xOffRecv = 0, xOffHistG = 0;
+    size_t slotTotal = 0;              // words of candidate slots per rank and level (v2 arena)
+    uint64_t nLocalMax = 0;
     std::vector<int> extraPasses;      // passes of the iterative fallback per level (host-driven on several ranks)
 
     // fused combine+update over NVLink peer memory (optional; see PeerSet in orb_kernels.cuh)
@@ -297,6 +306,12 @@ orb::PeerSet no_peers() {
     return ps;
 }
 
+orb::XArena no_arena() {
+    orb::XArena xa;
+    memset(&xa, 0, sizeof(xa));
+    return xa;
+}
+
 orb::FuseCtl no_fuse() {
     orb::FuseCtl fc;
     memset(&fc, 0, sizeof(fc));
@@ -360,6 +375,33 @@ inline void cpu_relax() {
 #endif
 }
 
+// Wait for a mapped status word the GPU writes (no stream synchronisation in the common case).  Every few thousand
+// polls the stream is queried, so that a kernel fault surfaces as ORB_ERR_CUDA instead of a hang; a rank that waits
+// longer than ORB_WAIT_TIMEOUT_S (default 120 s: a peer died or diverged) gives up with ORB_ERR_STATE.
+int wait_status(orb_ctx *c, volatile uint32_t *w, uint32_t *out) {
+    static const double limit = [] { const char *e = getenv("ORB_WAIT_TIMEOUT_S"); return e && atof(e) > 0 ? atof(e) : 120.0; }();
+    uint32_t s;
+    uint64_t polls = 0;
+    timespec t0{};
+    while ((s = *w) == 0u) {
+        cpu_relax();
+        if ((++polls & 0x3fffu) == 0) {
+            const cudaError_t q = cudaStreamQuery(c->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady)
+                return fail(ORB_ERR_CUDA, "stream failed while waiting for the device: %s", cudaGetErrorString(q));
+            timespec t1;
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            if (t0.tv_sec == 0 && t0.tv_nsec == 0) t0 = t1;
+            if ((double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec) > limit)
+                return fail(ORB_ERR_STATE, "no answer from the device after %.0f s (a peer rank stopped or took another branch?)", limit);
+            if (q == cudaSuccess && (s = *w) == 0u)    // everything enqueued has run and the word is still unset
+                return fail(ORB_ERR_STATE, "the stream drained without the status word being written");
+        }
+    }
+    *out = s;
+    return ORB_OK;
+}
+
 // Bisection loop of one level (orbit.cpp:146-232).  `slotBase` selects this level's private region of
 // the pass-control arrays (zeroed when the build / call starts).  Returns passes launched.
 int run_bisection(orb_ctx *c, uint32_t nCells, int M, int slotBase, int levelIdx, int *passesOut) {
@@ -410,8 +452,9 @@ int run_bisection(orb_ctx *c, uint32_t nCells, int M, int slotBase, int levelIdx
         // launched-1-runAhead; stop once a pass reported "no active cells".
         const int k = launched - 1 - c->runAhead;
         if (k >= 0) {
-            uint32_t s;
-            while ((s = hs[k]) == 0u) cpu_relax();
+            uint32_t s = 0;
+            rc = wait_status(c, hs + k, &s);
+            if (rc) return rc;
             if (s == 1u) break;
         }
     }
@@ -594,7 +637,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
             const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 4));
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                          nCells, nL, nTiles, nb1, rep, candCap, dbgBase, (float *)nullptr, 0u, 0));
+                          nCells, nL, nTiles, nb1, rep, candCap, dbgBase, (float *)nullptr, 0u, 0, no_arena()));
             if ((rc = count_event_end(c))) return rc;
             c->nCountLaunch++;
         }
@@ -607,7 +650,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
             CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
                           nCells, nL, nTiles, nb1, 1, c->selBigFinish ? 0x7fffffffu : candCap,
                           dbgBase ? dbgBase + (size_t)kDbgBlocks * 4 : (unsigned long long *)nullptr,
-                          (float *)nullptr, 0u, 0));
+                          (float *)nullptr, 0u, 0, no_arena()));
             if ((rc = count_event_end(c))) return rc;
         }
         {
@@ -665,31 +708,61 @@ int finalize_unfound(orb_ctx *c, uint32_t nCells, uint32_t *nUnfoundOut) {
 //      nLocalMin and nGlobal, which are identical on all ranks. ----
 struct SelMrPlan {
     bool ok;
+    bool v2;              // protocol of orb_exchange.cuh (peer memory); else the two-exchange kernels of orb_select.cuh
+    int regime;           // v2: 0 streaming passes (k_sel_stream), 1 one block per cell, 2 one warp per cell (k_xd_*)
+    bool warpFinish;      // v2: the owner searches a cell's candidates with one warp
     int nb1, rep;
     uint32_t candCap, slotWords;
-    size_t histWords;
+    size_t histWords;     // rows the level exchanges
+    size_t zeroWords;     // rows that must be cleared before the level starts (built with atomics)
 };
 SelMrPlan sel_plan_mr(const orb_ctx *c, uint32_t nCells, int M, int forcedNb = 0) {
     SelMrPlan p{};
     p.ok = false;
-    if (!(c->select && c->selectMr && c->nRanks > 1 && c->nRanks <= orb::kMaxPeers && M == 3 && c->d_slots_g && nCells >= 1 &&
-          nCells <= kSelMrMaxCells && c->nLocalMin > 0))
-        return p;
+    const bool multi = c->nRanks > 1 || c->mrSelf;
+    if (!(c->select && c->selectMr && multi && c->nRanks <= orb::kMaxPeers && M == 3 && nCells >= 1 && c->nLocalMin > 0)) return p;
+    p.v2 = c->mrV2 && c->peerEnabled;
+    if (!p.v2 && !(c->d_slots_g && nCells <= kSelMrMaxCells)) return p;
+    const size_t slotTotal = p.v2 ? c->slotTotal : kSelSlotWordsTotal;
     const uint64_t gavg = c->nGlobal / nCells, lavg = std::max<uint64_t>(c->nGlobal / c->nRanks, c->nLocalMin) / nCells;
+    // <= every rank's selHistWords
+    const size_t histFit = p.v2 ? (size_t)c->nLocalMin / 8 + 2 * (size_t)orb::kSelBinsMax : (size_t)c->nLocalMin / 16 + 2 * (size_t)orb::kSelBinsMax;
+    if (p.v2 && ((nCells >= 512 && lavg <= (1u << 20)) || lavg <= 8192) && !forcedNb) {
+        // ---- small cells: a group of threads per cell bins / gathers it; about 64 particles per bin over all ranks ----
+        p.regime = lavg >= 4096 ? 1 : 2;
+        int nb = 32;
+        while (nb < orb::kSelBins2 && gavg / (uint64_t)nb > 64) nb <<= 1;
+        while (nb > 32 && (size_t)nCells * (size_t)nb > histFit) nb >>= 1;
+        p.nb1 = nb;
+        p.rep = 1;
+        p.histWords = (size_t)nCells * (size_t)nb;
+        p.zeroWords = 0;
+        p.candCap = (uint32_t)std::min<uint64_t>(kSelValsCap, 4 * std::max<uint64_t>(1, gavg / (uint64_t)nb) + 128);
+        p.warpFinish = p.candCap <= orb::kXWarpCap;
+        const uint64_t want = std::min<uint64_t>(p.candCap, 4 * (lavg / (uint64_t)nb) + 32) + 1;
+        uint32_t sw = 32;
+        while (sw < want) sw <<= 1;
+        while (sw > 32 && (size_t)sw * nCells > slotTotal) sw >>= 1;
+        p.slotWords = sw;
+        p.ok = p.histWords <= histFit && (size_t)sw * nCells <= slotTotal;
+        return p;
+    }
+    p.regime = 0;
     p.nb1 = orb::kSelBinsMin;
     while (p.nb1 < orb::kSelBinsMax && gavg / (uint64_t)p.nb1 > (uint64_t)c->selBinAvg) p.nb1 <<= 1;
     if (forcedNb) p.nb1 = forcedNb;
     p.rep = p.nb1 <= 512 ? 4 : (p.nb1 <= 1024 ? 2 : 1);
     p.histWords = (size_t)nCells * (size_t)p.nb1;
+    p.zeroWords = p.histWords;
     p.candCap = (uint32_t)std::min<uint64_t>(kSelValsCap, 4 * (gavg / (uint64_t)p.nb1) + 4096);
+    p.warpFinish = false;
     // slot of one rank and cell: a few bins' worth of its own particles + the count word, a power of two
     uint64_t want = std::min<uint64_t>(p.candCap, 4 * (lavg / (uint64_t)p.nb1) + 96) + 1;
     uint32_t sw = 128;
     while (sw < want) sw <<= 1;
-    while (sw > 32 && (size_t)sw * nCells > kSelSlotWordsTotal) sw >>= 1;
+    while (sw > 32 && (size_t)sw * nCells > slotTotal) sw >>= 1;
     p.slotWords = sw;
-    const size_t histFit = (size_t)c->nLocalMin / 16 + 2 * (size_t)orb::kSelBinsMax;   // <= every rank's selHistWords
-    p.ok = p.histWords <= histFit && (size_t)sw * nCells <= kSelSlotWordsTotal;
+    p.ok = p.histWords <= histFit && (size_t)sw * nCells <= slotTotal;
     return p;
 }
 
@@ -706,9 +779,9 @@ int prefuse_nb(const orb_ctx *c, uint32_t nNext, int M) {
     // FINISH) the rows must have the bins the level would choose itself - coarser rows mean more candidates per bin
     // and, on clustered inputs, cells that overflow the finish kernel's staging; where one block searches a whole
     // cell it can zoom on its own (k_sel_percell), so coarser rows only cost that cell another read.
-    if (c->nRanks > 1) {
+    if (c->nRanks > 1 || c->mrSelf) {
         const SelMrPlan p = sel_plan_mr(c, nNext, M);
-        if (!p.ok || p.nb1 > 1024) return 0;
+        if (!p.ok || p.regime != 0 || p.nb1 > 1024) return 0;
         return p.nb1;
     }
     if (!level_can_select(c, nNext, M)) return 0;
@@ -766,7 +839,7 @@ int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int
         const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 4));
         if ((rc = count_event_begin(c))) return rc;
         CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                      nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u, 0));
+                      nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u, 0, no_arena()));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     }
@@ -790,7 +863,7 @@ int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int
         if ((rc = count_event_begin(c))) return rc;
         CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, peer ? ss : sg,
                       (const uint32_t *)c->d_tile_first, nCells, nL, nTiles, nb1, 1, pl.candCap, (unsigned long long *)nullptr,
-                      c->d_slots_l, pl.slotWords, peer ? 1 : 0));
+                      c->d_slots_l, pl.slotWords, peer ? 1 : 0, no_arena()));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     }
@@ -820,13 +893,158 @@ int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int
     return ORB_OK;
 }
 
+// Protocol v2 (orb_exchange.cuh): HIST -> REDUCE -> COMPACT (-> PUSH) -> FINISH by the owner -> APPLY.  No collective
+// call, no host synchronisation; the apply kernel's last block reports 1 + (cells flagged) like the v1 finish kernel.
+orb::XArena make_arena(orb_ctx *c) {
+    orb::XArena xa;
+    memset(&xa, 0, sizeof(xa));
+    xa.n = c->nRanks;
+    xa.self = c->rank;
+    for (int r = 0; r < c->nRanks; ++r) xa.arena[r] = c->peerX[r];
+    xa.offRes = c->xOffRes; xa.offRecvCnt = c->xOffRecvCnt; xa.offRecv = c->xOffRecv;
+    xa.offHistL = c->xOffHist; xa.offHistG = c->xOffHistG;
+    return xa;
+}
+
+int launch_level_select_mr2(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int slotBase, int levelIdx, int preNb = 0) {
+    using namespace orb;
+    const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
+    float *cand = c->x[c->cur ^ 1];
+    SelState ss = c->sel;                       // hist = this rank's rows
+    ss.n_flagged = c->d_sel_nflag + levelIdx;
+    SelState sg = ss;
+    sg.hist = c->d_xchg + c->xOffHistG;         // rows summed over ranks (this rank's copy)
+    SelCtl sc;
+    sc.active_particles = c->d_active_particles;
+    sc.level_iters = c->d_level_iters + levelIdx;
+    sc.passes_out = c->d_lvl_passes + levelIdx;
+    sc.n_unfound_out = c->d_lvl_unfound + levelIdx;
+    SelMrState mr;
+    memset(&mr, 0, sizeof(mr));
+    mr.hist_l = c->sel.hist;
+    mr.loc_base = c->d_sel_locbase;
+    mr.slots_l = c->d_slots_l;
+    mr.slotWords = pl.slotWords;
+    mr.nRanks = c->nRanks;
+    mr.self = c->rank;
+    mr.done = c->d_cdone + slotBase + kPassSlots - 1;
+    mr.h_status = (volatile uint32_t *)(c->h_status_dev + slotBase + kPassSlots - 1);
+    XArena xa = make_arena(c);
+    int rc;
+    const int nb1 = pl.nb1;
+    const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
+    const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
+    const uint32_t nL = (uint32_t)c->nLocal;
+    const uint32_t nSM = (uint32_t)c->nSM;
+    const uint32_t nOwnedMax = ceil_div(nCells, (uint32_t)c->nRanks);
+    // ---- HIST: this rank's rows ----
+    if (pl.regime == 0) {
+        if (nTiles && !preNb) {       // (preNb: the previous level's partition built them)
+            const size_t smem = ringBytes + (size_t)nb1 * pl.rep * 4;
+            int occ = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelHist>, kThreads, smem));
+            const uint32_t grid = std::min<uint32_t>(nTiles, nSM * (uint32_t)std::min(std::max(occ, 1), 4));
+            if ((rc = count_event_begin(c))) return rc;
+            CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
+                          nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u, 0, no_arena()));
+            if ((rc = count_event_end(c))) return rc;
+            c->nCountLaunch++;
+        }
+    } else {
+        if ((rc = count_event_begin(c))) return rc;
+        if (pl.regime == 1) {
+            const uint32_t grid = std::min<uint32_t>(nCells, nSM * 8u);
+            CK(launch_pdl(c, k_xd_hist<256>, dim3(grid), dim3(kThreads), (size_t)nb1 * 4, x, y, z, c->lv, c->sel.hist, nCells, nb1));
+        } else {
+            const uint32_t grid = std::min<uint32_t>(ceil_div(nCells, kWarps), nSM * 8u);
+            CK(launch_pdl(c, k_xd_hist<32>, dim3(grid), dim3(kThreads), (size_t)nb1 * 4 * kWarps, x, y, z, c->lv, c->sel.hist, nCells, nb1));
+        }
+        if ((rc = count_event_end(c))) return rc;
+        c->nCountLaunch++;
+    }
+    // ---- REDUCE: rows of all ranks -> global rows on every rank ----
+    {
+        const uint32_t n4 = (uint32_t)(pl.histWords / 4);
+        xa.seq = ++c->xSeq;
+        const uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>(ceil_div(ceil_div(n4, (uint32_t)c->nRanks), kThreads), 2u * nSM));
+        if ((rc = aux_begin(c, "x_reduce", levelIdx))) return rc;
+        CK(launch_pdl(c, k_xr_reduce, dim3(grid), dim3(kThreads), 0, xa, n4));
+        if ((rc = aux_end(c))) return rc;
+        c->nOtherLaunch++;
+    }
+    // ---- COMPACT: resolve from the global rows, own candidates to the owners ----
+    xa.seq = ++c->xSeq;
+    if (pl.regime == 0) {
+        if (nTiles) {
+            const size_t smem = ringBytes + (size_t)kWarps * kSelWarpStage * 4 + (size_t)nb1 * 4;
+            int occ = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelCompact>, kThreads, smem));
+            const uint32_t grid = std::min<uint32_t>(nTiles, nSM * (uint32_t)std::min(std::max(occ, 1), 3));
+            if ((rc = count_event_begin(c))) return rc;
+            CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, sg,
+                          (const uint32_t *)c->d_tile_first, nCells, nL, nTiles, nb1, 1, pl.candCap, (unsigned long long *)nullptr,
+                          c->d_slots_l, pl.slotWords, 0, xa));
+            if ((rc = count_event_end(c))) return rc;
+            c->nCountLaunch++;
+        }
+        {
+            // (no particles on this rank: the barrier the COMPACT pass would have made is made here)
+            XArena xb = xa;
+            if (nTiles) xb.n = 0;
+            const uint32_t grid = std::min<uint32_t>(nCells, nSM * 8u);
+            if ((rc = aux_begin(c, "x_push", levelIdx))) return rc;
+            CK(launch_pdl(c, k_xc_push, dim3(grid), dim3(kThreads), (size_t)nb1 * 4, c->lv, sg, mr, xa, xb, nCells, nb1, pl.candCap));
+            if ((rc = aux_end(c))) return rc;
+            c->nOtherLaunch++;
+        }
+    } else {
+        if ((rc = count_event_begin(c))) return rc;
+        if (pl.regime == 1) {
+            const uint32_t grid = std::min<uint32_t>(nCells, nSM * 8u);
+            CK(launch_pdl(c, k_xd_compact<256>, dim3(grid), dim3(kThreads), (size_t)nb1 * 4, x, y, z, c->lv, ss, mr, xa, nCells, nb1, pl.candCap));
+        } else {
+            const uint32_t grid = std::min<uint32_t>(ceil_div(nCells, kWarps), nSM * 8u);
+            CK(launch_pdl(c, k_xd_compact<32>, dim3(grid), dim3(kThreads), (size_t)nb1 * 4 * kWarps, x, y, z, c->lv, ss, mr, xa, nCells, nb1, pl.candCap));
+        }
+        if ((rc = count_event_end(c))) return rc;
+        c->nCountLaunch++;
+    }
+    // ---- FINISH: the owner searches its cells' candidates, results to every rank ----
+    xa.seq = ++c->xSeq;
+    if ((rc = aux_begin(c, "x_finish", levelIdx))) return rc;
+    if (pl.warpFinish) {
+        const size_t smem = (size_t)kWarps * (pl.candCap + 4u) * 4u;
+        const uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>(ceil_div(nOwnedMax, kWarps), nSM * 6u));
+        CK(launch_pdl(c, k_xf_finish_warp, dim3(grid), dim3(kThreads), smem, c->lv, ss, mr, xa, nCells, nb1, pl.candCap, c->d_err));
+    } else {
+        const size_t smem = sel_search_smem_bytes(pl.candCap);
+        const int threads = nOwnedMax <= 2u * nSM ? 1024 : (smem > 112 * 1024 ? 1024 : (smem > 56 * 1024 ? 512 : 256));
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_xf_finish_block, threads, smem));
+        const uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>(nOwnedMax, nSM * (uint32_t)std::max(occ, 1)));
+        CK(launch_pdl(c, k_xf_finish_block, dim3(grid), dim3(threads), smem, c->lv, ss, mr, xa, nCells, nb1, pl.candCap, c->d_err));
+    }
+    if ((rc = aux_end(c))) return rc;
+    c->nUpdateLaunch++;
+    // ---- APPLY ----
+    xa.seq = ++c->xSeq;
+    if ((rc = aux_begin(c, "x_apply", levelIdx))) return rc;
+    CK(launch_pdl(c, k_xa_apply, dim3(ceil_div(nCells, kThreads)), dim3(kThreads), 0, c->lv, ss, sc, mr, xa, nCells,
+                  pl.regime == 0 ? (preNb ? 1 : 2) : 2));
+    if ((rc = aux_end(c))) return rc;
+    c->nOtherLaunch++;
+    CK(cudaGetLastError());
+    return ORB_OK;
+}
+
 // Cells the multi-rank selection search left over at this level (the same number on every rank).  Spins on the
 // mapped status word the finish kernel's last block writes - no stream synchronisation.
-uint32_t select_mr_flagged(orb_ctx *c, int slotBase) {
-    volatile uint32_t *w = c->h_status + slotBase + kPassSlots - 1;
-    uint32_t s;
-    while ((s = *w) == 0u) cpu_relax();
-    return s - 1u;
+int select_mr_flagged(orb_ctx *c, int slotBase, uint32_t *nFlagged) {
+    uint32_t s = 0;
+    const int rc = wait_status(c, c->h_status + slotBase + kPassSlots - 1, &s);
+    if (rc) return rc;
+    *nFlagged = s - 1u;
+    return ORB_OK;
 }
 
 // iterative loop for the cells the multi-rank selection search flagged (every rank runs it: the flags agree)
@@ -946,6 +1164,38 @@ int launch_partition_hoare(orb_ctx *c, uint32_t nCells) {
     return ORB_OK;
 }
 
+// Exchange arena: flags[64] | slot fill levels | own candidate slots | (v2: result records | candidate counts | received
+// slots) | own histogram rows | (v2: global rows).  One allocation, one IPC handle; with several ranks every offset
+// derives from numbers all ranks share (d, the largest shard).
+int alloc_arena(orb_ctx *c, bool multi) {
+    const size_t L = c->maxLevelCells;
+    const size_t Lr = (L + 63) & ~(size_t)63;
+    if (c->d_xchg) { CK(cudaFree(c->d_xchg)); c->d_xchg = nullptr; }
+    c->slotTotal = kSelSlotWordsTotal;
+    size_t off = 64;
+    c->xOffCursor = (uint32_t)off; off += Lr;
+    if (multi) {
+        c->selHistWords = (size_t)c->nLocalMax / 8 + 2 * (size_t)orb::kSelBinsMax;
+        c->selHistWords = (c->selHistWords + 63) & ~(size_t)63;
+        c->slotTotal = std::max<size_t>(kSelSlotWordsTotal, 64 * L);
+    }
+    c->xOffSlots = (uint32_t)off; off += c->slotTotal;
+    if (multi) {
+        c->xOffRes = (uint32_t)off; off += 8 * Lr;
+        c->xOffRecvCnt = (uint32_t)off; off += Lr + 64;
+        c->xOffRecv = (uint32_t)off; off += c->slotTotal + (size_t)orb::kMaxPeers * kSelSlotWordsMax;
+    }
+    c->xOffHist = (uint32_t)off; off += c->selHistWords;
+    if (multi) { c->xOffHistG = (uint32_t)off; off += c->selHistWords; }
+    if (off >= ((size_t)1 << 32)) return fail(ORB_ERR_ARG, "exchange arena of %zu words exceeds 32-bit word offsets", off);
+    CK(cudaMalloc(&c->d_xchg, off * 4));
+    CK(cudaMemset(c->d_xchg, 0, off * 4));
+    c->sel.cursor = c->d_xchg + c->xOffCursor;
+    c->d_slots_l = reinterpret_cast<float *>(c->d_xchg + c->xOffSlots);
+    c->sel.hist = c->d_xchg + c->xOffHist;
+    return ORB_OK;
+}
+
 int reset_pass_ctl(orb_ctx *c) {
     CK(cudaMemsetAsync(c->d_nactive, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots, c->stream));
     CK(cudaMemsetAsync(c->d_done, 0, sizeof(uint32_t) * kMaxLevels * kPassSlots, c->stream));
@@ -987,9 +1237,25 @@ extern "C" {
 const char *orb_last_error(void) { return g_err; }
 int orb_version(void) { return 100; }
 
+static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cells, orb_ctx **partial);
+
 int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cells) {
     if (!out) return fail(ORB_ERR_ARG, "null ctx pointer");
     *out = nullptr;
+    orb_ctx *partial = nullptr;
+    const int rc = create_impl(out, device, n_local, n_leaf_cells, &partial);
+    if (rc != ORB_OK && partial) {      // e.g. cudaMalloc ran out of memory half-way: give everything back
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        orb_destroy(partial);           // tolerates null members
+        memcpy(g_err, keep, sizeof(keep));
+        cudaGetLastError();
+        *out = nullptr;
+    }
+    return rc;
+}
+
+static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cells, orb_ctx **partial) {
     if (n_leaf_cells < 1 || (n_leaf_cells & (n_leaf_cells - 1))) return fail(ORB_ERR_ARG, "n_leaf_cells must be a power of two (orbit.cpp:42)");
     if (n_local >= (1ull << 32) - orb::kCountTile) return fail(ORB_ERR_ARG, "n_local must fit 32-bit particle indices");
     int ndev = 0;
@@ -997,6 +1263,7 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     if (device < 0 || device >= ndev) return fail(ORB_ERR_CUDA, "no CUDA device %d (found %d); there is no CPU fallback", device, ndev);
     CK(cudaSetDevice(device));
     orb_ctx *c = new orb_ctx();
+    *partial = c;
     c->device = device;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -1043,6 +1310,9 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
         CK(cudaMemset(c->lv.tile_ncand, 0, nCountTiles * orb::kWarps * 4));
     }
     c->lvAlt = c->lv;                 // search scratch (cuts, counters, compaction state) is shared
+    c->lvAlt.bnd = nullptr; c->lvAlt.axis = nullptr; c->lvAlt.mL = c->lvAlt.mR = nullptr; c->lvAlt.total = nullptr;
+    c->lvAlt.nleaf = nullptr; c->lvAlt.active = c->lvAlt.found = nullptr; c->lvAlt.iter = nullptr;
+    c->lvAlt.nleft_g = c->lvAlt.nleft_l = nullptr;      // (own arrays: allocated below; orb_destroy frees exactly these)
     CK(cudaMalloc(&c->lvAlt.bnd, (L + 1) * 4));
     CK(cudaMalloc(&c->lvAlt.axis, L * 4));
     CK(cudaMalloc(&c->lvAlt.mL, L * 4));
@@ -1075,17 +1345,9 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     CK(cudaMalloc(&c->d_lvl_unfound, sizeof(uint32_t) * kMaxLevels));
     {
         c->selHistWords = (size_t)n_local / 16 + 2 * (size_t)orb::kSelBinsMax;
-        {   // exchange arena: one allocation so that one IPC handle maps all of it; offsets do not depend on n_local
-            const size_t Lr = (L + 63) & ~(size_t)63;
-            c->xOffCursor = 64;
-            c->xOffSlots = (uint32_t)(64 + Lr);
-            c->xOffHist = (uint32_t)(64 + Lr + kSelSlotWordsTotal);
-            const size_t words = (size_t)c->xOffHist + c->selHistWords;
-            CK(cudaMalloc(&c->d_xchg, words * 4));
-            CK(cudaMemset(c->d_xchg, 0, words * 4));
-            c->sel.cursor = c->d_xchg + c->xOffCursor;
-            c->d_slots_l = reinterpret_cast<float *>(c->d_xchg + c->xOffSlots);
-            c->sel.hist = c->d_xchg + c->xOffHist;
+        {   // exchange arena: one allocation so that one IPC handle maps all of it
+            int rcA = alloc_arena(c, false);
+            if (rcA) return rcA;
         }
         CK(cudaMalloc(&c->sel.bfirst, L * 4));
         CK(cudaMalloc(&c->sel.blast, L * 4));
@@ -1110,6 +1372,7 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
         CK(cudaFuncSetAttribute(orb::k_sel_percell<512, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
         CK(cudaFuncSetAttribute(orb::k_sel_percell<1024, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
     }
+    CK(cudaFuncSetAttribute(orb::k_xf_finish_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_search_smem_bytes(kSelValsCap)));
     CK(cudaMalloc(&c->d_misc, 64));
     CK(cudaMalloc(&c->d_active_particles, 16));
     CK(cudaMalloc(&c->d_level_iters, sizeof(int32_t) * kMaxLevels));
@@ -1179,6 +1442,19 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
     if (se) c->select = atoi(se) != 0;
     const char *sem = getenv("ORB_SELECT_MR");
     if (sem) c->selectMr = atoi(sem) != 0;
+    const char *mv1 = getenv("ORB_MR_V1");
+    if (mv1) c->mrV2 = atoi(mv1) == 0;
+    const char *msf = getenv("ORB_MR_SELF");
+    if (msf && atoi(msf) != 0 && c->mrV2) {
+        // testing aid: the multi-rank protocol of orb_exchange.cuh with this rank as its only peer
+        c->mrSelf = true;
+        c->nLocalMin = c->nGlobal = c->nLocalMax = c->nLocal;
+        int rcA = alloc_arena(c, true);
+        if (rcA) return rcA;
+        CK(cudaMalloc(&c->d_sel_locbase, (size_t)c->maxLevelCells * 4));
+        c->peerX[0] = c->d_xchg;
+        c->peerEnabled = true;
+    }
     const char *smt = getenv("ORB_STREAM_MIN_TILES");
     if (smt && atoi(smt) >= 1) c->streamMinTiles = atoi(smt);
     const char *pe = getenv("ORB_PERSIST");
@@ -1197,7 +1473,7 @@ int orb_create(orb_ctx **out, int device, uint64_t n_local, uint32_t n_leaf_cell
 int orb_destroy(orb_ctx *c) {
     if (!c) return ORB_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && c->ownComm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (int b = 0; b < 2; ++b) { cudaFree(c->x[b]); cudaFree(c->y[b]); cudaFree(c->z[b]); }
     cudaFree(c->d_heap); cudaFree(c->d_cells); cudaFree(c->d_range); cudaFree(c->d_total);
@@ -1222,11 +1498,12 @@ int orb_destroy(orb_ctx *c) {
     cudaFree(c->d_final_cut); cudaFree(c->d_tile_first); cudaFree(c->d_blk_left); cudaFree(c->d_blk_restart); cudaFree(c->d_blk_le); cudaFree(c->d_nGE); cudaFree(c->d_nLE); cudaFree(c->d_tickets);
     cudaFree(c->d_nactive); cudaFree(c->d_done); cudaFree(c->d_misc); cudaFree(c->d_active_particles);
     cudaFree(c->d_level_iters); cudaFree(c->d_err); cudaFree(c->d_bb); cudaFree(c->d_bb6);
-    cudaFreeHost((void *)c->h_status);
+    if (c->h_status) cudaFreeHost((void *)c->h_status);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
     for (auto &e : c->evCount) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto &e : c->evPart) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    cudaStreamDestroy(c->stream);
+    for (auto &e : c->evAux) { if (e.e0) cudaEventDestroy(e.e0); if (e.e1) cudaEventDestroy(e.e1); }
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return ORB_OK;
 }
@@ -1261,13 +1538,18 @@ int orb_plan_level(uint64_t n_local, uint64_t n_global, uint64_t n_local_min, in
     c->occPersist[3] = 1;
     c->prefuseHist = prefuse_mode < 0 ? -1 : (prefuse_mode ? 1 : 0);
     c->d_slots_g = reinterpret_cast<float *>(uintptr_t(16));     // "allocated" (sel_plan_mr only tests the pointer)
+    c->nLocalMax = c->nLocalMin;      // (the plan never reads it: buffers are sized from it, decisions use the minimum)
+    c->peerEnabled = n_ranks > 1;     // plan of the peer-memory protocol (orb_exchange.cuh)
+    c->slotTotal = std::max<size_t>(kSelSlotWordsTotal, 64 * (size_t)c->maxLevelCells);
+    const char *mv1 = getenv("ORB_MR_V1");
+    if (mv1) c->mrV2 = atoi(mv1) == 0;
     memset(out, 0, sizeof(*out));
     const int M = 3;
     const int pre = n_cells >= 2 ? prefuse_nb(c.get(), n_cells, M) : 0;
     out->prefuse_bins = pre;
     const SelMrPlan mr = sel_plan_mr(c.get(), n_cells, M, pre);
     if (mr.ok) {
-        out->search = 3;
+        out->search = !mr.v2 ? 3 : (mr.regime == 0 ? 3 : (mr.regime == 1 ? 4 : 5));
         out->hist_bins = mr.nb1;
         out->cand_cap = mr.candCap;
         out->slot_words = mr.slotWords;
@@ -1306,19 +1588,26 @@ static int setup_multi(orb_ctx *c) {
         c->lv.cnt_g = c->d_cnt_g_buf;
         c->lvAlt.cnt_g = c->d_cnt_g_buf;
     }
-    c->nLocalMin = c->nGlobal = c->nLocal;
+    c->nLocalMin = c->nGlobal = c->nLocalMax = c->nLocal;
     if (c->nRanks > 1) {
-        // shard sizes over ranks (min, sum): whatever shapes a collective must be decided from rank-invariant numbers
-        unsigned long long h[2] = {~(unsigned long long)c->nLocal, (unsigned long long)c->nLocal}, *d = nullptr;
-        CK(cudaMalloc(&d, 16));
-        CK(cudaMemcpyAsync(d, h, 16, cudaMemcpyHostToDevice, c->stream));
+        // shard sizes over ranks (min, sum, max): whatever shapes a collective or an exchange must be decided from
+        // rank-invariant numbers
+        unsigned long long h[3] = {~(unsigned long long)c->nLocal, (unsigned long long)c->nLocal, (unsigned long long)c->nLocal}, *d = nullptr;
+        CK(cudaMalloc(&d, 24));
+        CK(cudaMemcpyAsync(d, h, 24, cudaMemcpyHostToDevice, c->stream));
         NK(g_nccl.AllReduce(d, d, 1, ncclUint64, ncclMax, c->comm, c->stream));          // max of ~n = ~min
         NK(g_nccl.AllReduce(d + 1, d + 1, 1, ncclUint64, ncclSum, c->comm, c->stream));
-        CK(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, c->stream));
+        NK(g_nccl.AllReduce(d + 2, d + 2, 1, ncclUint64, ncclMax, c->comm, c->stream));
+        CK(cudaMemcpyAsync(h, d, 24, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaFree(d));
         c->nLocalMin = ~h[0];
         c->nGlobal = h[1];
+        c->nLocalMax = h[2];
+        if (c->mrV2) {     // the arena of the multi-rank protocol (must precede orb_peer_export)
+            int rcA = alloc_arena(c, true);
+            if (rcA) return rcA;
+        }
         if (!c->d_sel_hist_g) {
             CK(cudaMalloc(&c->d_sel_hist_g, c->selHistWords * 4));
             CK(cudaMalloc(&c->d_sel_locbase, (size_t)c->maxLevelCells * 4));
@@ -1470,30 +1759,29 @@ int orb_get_ranges(orb_ctx *c, uint32_t first_id, uint32_t n, uint32_t *out) {
 }
 
 // ---------------------------------------------------------------- service-granular calls
+// particles per cell of the level (already uploaded to d_cells), summed over ranks, into lv.cnt_g[0..n) and into
+// d_total[id]: the device side of ServiceCount (count.cpp:8-30)
+static int level_totals(orb_ctx *c, uint32_t n_cells) {
+    const uint32_t blocks = ceil_div(n_cells, 256);
+    orb::k_cell_sizes<<<blocks, 256, 0, c->stream>>>(c->d_cells, n_cells, c->d_range, c->lv.cnt_l);
+    if (c->nRanks > 1) NK(g_nccl.AllReduce(c->lv.cnt_l, c->lv.cnt_g, n_cells, ncclUint32, ncclSum, c->comm, c->stream));
+    orb::k_store_totals<<<blocks, 256, 0, c->stream>>>(c->d_cells, n_cells, c->lv.cnt_g, c->d_total);
+    c->nOtherLaunch += 2;
+    CK(cudaGetLastError());
+    return ORB_OK;
+}
+
 int orb_count(orb_ctx *c, const orb_cell *cells, uint32_t n_cells, uint32_t *out) {
     if (!c || !out) return fail(ORB_ERR_ARG, "null argument");
     if (!c->haveParticles) return fail(ORB_ERR_STATE, "no particles uploaded");
     CK(cudaSetDevice(c->device));
     int rc = upload_cells(c, cells, n_cells);
     if (rc) return rc;
-    // local sizes come straight from the range map (count.cpp:16); sum over ranks like Combine (count.cpp:21-30)
-    rc = ensure_scratch(c, (size_t)c->nHeap * 8);
+    // local sizes come straight from the range map (count.cpp:16), summed over ranks like Combine (count.cpp:21-30);
+    // only the level's n_cells words travel back
+    rc = level_totals(c, n_cells);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(c->h_scratch, c->d_range, (size_t)c->nHeap * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    for (uint32_t i = 0; i < n_cells; ++i) out[i] = c->h_scratch[2 * cells[i].id + 1] - c->h_scratch[2 * cells[i].id];
-    if (c->nRanks > 1) {
-        CK(cudaMemcpyAsync(c->lv.cnt_l, out, (size_t)n_cells * 4, cudaMemcpyHostToDevice, c->stream));
-        NK(g_nccl.AllReduce(c->lv.cnt_l, c->lv.cnt_g, n_cells, ncclUint32, ncclSum, c->comm, c->stream));
-        CK(cudaMemcpyAsync(out, c->lv.cnt_g, (size_t)n_cells * 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-    }
-    // remember global totals per id for the fused paths
-    std::vector<uint32_t> tot(c->nHeap, 0u);
-    CK(cudaMemcpyAsync(tot.data(), c->d_total, (size_t)c->nHeap * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    for (uint32_t i = 0; i < n_cells; ++i) tot[cells[i].id] = out[i];
-    CK(cudaMemcpyAsync(c->d_total, tot.data(), (size_t)c->nHeap * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(out, c->lv.cnt_g, (size_t)n_cells * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return ORB_OK;
 }
@@ -1526,6 +1814,10 @@ int orb_partition(orb_ctx *c, const orb_cell *cells, uint32_t n_cells) {
     CK(cudaSetDevice(c->device));
     int rc = upload_cells(c, cells, n_cells);
     if (rc) return rc;
+    // the children's ranges are written at ids 2 id + 1 and 2 id + 2 (partition.cpp:54-60): leaves have none
+    for (uint32_t i = 0; i < n_cells; ++i)
+        if (2ull * (uint64_t)cells[i].id + 2ull >= (uint64_t)c->nHeap)
+            return fail(ORB_ERR_ARG, "cell id %d has no children in a heap of %u cells", cells[i].id, c->nHeap);
     // count at the final cut of EVERY cell (found or not) to get the split offsets, then scatter
     std::vector<orb_cell> tmp(cells, cells + n_cells);
     for (auto &t : tmp) t.foundCut = 0;
@@ -1602,6 +1894,10 @@ int orb_find_cuts(orb_ctx *c, orb_cell *cells, uint32_t n_cells, int32_t *iters,
     if (rc) return rc;
     rc = reset_pass_ctl(c);
     if (rc) return rc;
+    // the bisection's target is half of each cell's particle count over all ranks (orbit.cpp:204-205): derived here
+    // from the range map, so the call does not depend on an earlier orb_count
+    rc = level_totals(c, n_cells);
+    if (rc) return rc;
     const int M = c->trialDepth;
     rc = level_prepare(c, c->d_cells, n_cells, (1 << M) - 1, c->d_nactive);
     if (rc) return rc;
@@ -1630,9 +1926,13 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
     const int nLevelsRef = (int)std::ceil(std::log2((double)c->d));            // Cell::getNLevels (cell.h:65-67)
     const int lEnd = (flags & ORB_FULL_LEVELS) ? nLevelsRef + 1 : nLevelsRef;  // orbit.cpp:102
     if (lEnd - 1 > kMaxLevels) return fail(ORB_ERR_ARG, "too many levels");
-    cudaEvent_t evA, evB;
-    CK(cudaEventCreate(&evA));
-    CK(cudaEventCreate(&evB));
+    struct EventPair {      // destroyed on every return path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } evp;
+    CK(cudaEventCreate(&evp.a));
+    CK(cudaEventCreate(&evp.b));
+    const cudaEvent_t evA = evp.a, evB = evp.b;
     CK(cudaEventRecord(evA, c->stream));   // the build's clock starts before any of its bookkeeping
     int rc = reset_pass_ctl(c);
     if (rc) return rc;
@@ -1677,7 +1977,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         const int slot = (l - 1) * kPassSlots;
         const bool useSelect = level_can_select(c, nCells, M);
         const SelMrPlan mrPlan = sel_plan_mr(c, nCells, M, preNb);
-        const size_t histWords = useSelect ? sel_plan(c, nCells, preNb).histWords : (mrPlan.ok ? mrPlan.histWords : 0);
+        const size_t histWords = mrPlan.ok ? mrPlan.zeroWords : (useSelect ? sel_plan(c, nCells, preNb).histWords : 0);
         if (!prepared) {
             rc = level_prepare(c, c->d_heap + first, nCells, (1 << M) - 1, c->d_nactive + slot, c->sel.hist, std::min(histWords, c->selHistWords));
             if (rc) return rc;
@@ -1687,13 +1987,14 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
         uint32_t nu = 0;
         bool speculate = false;     // split + partition enqueued behind the search before its flag count is known
         if (mrPlan.ok) {
-            rc = launch_level_select_mr(c, nCells, mrPlan, slot, l - 1, preNb);
+            rc = mrPlan.v2 ? launch_level_select_mr2(c, nCells, mrPlan, slot, l - 1, preNb) : launch_level_select_mr(c, nCells, mrPlan, slot, l - 1, preNb);
             if (rc) return rc;
             np = -1;
             speculate = c->tieMode != 1;
-            if (!speculate && select_mr_flagged(c, slot)) {
-                rc = select_mr_fallback(c, nCells, slot, l - 1);
-                if (rc) return rc;
+            if (!speculate) {
+                uint32_t nf = 0;
+                if ((rc = select_mr_flagged(c, slot, &nf))) return rc;
+                if (nf && (rc = select_mr_fallback(c, nCells, slot, l - 1))) return rc;
             }
         } else if (useSelect) {
             rc = launch_level_select(c, nCells, slot, l - 1, preNb);
@@ -1733,7 +2034,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             const uint32_t nNext = 2u * nCells;
             preNext = prefuse_nb(c, nNext, M);
             const SelMrPlan mrNext = sel_plan_mr(c, nNext, M, preNext);
-            const size_t hwNext = level_can_select(c, nNext, M) ? sel_plan(c, nNext, preNext).histWords : (mrNext.ok ? mrNext.histWords : 0);
+            const size_t hwNext = mrNext.ok ? mrNext.zeroWords : (level_can_select(c, nNext, M) ? sel_plan(c, nNext, preNext).histWords : 0);
             if (preNext) {
                 nh.enabled = 1;
                 nh.hist = c->sel.hist;
@@ -1758,7 +2059,10 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
                 rc = launch_partition(c, nCells, c->d_tickets + (l - 1), gate, nh);
                 if (rc) return rc;
             }
-            if (!gate || select_mr_flagged(c, slot) == 0u) break;
+            if (!gate) break;
+            uint32_t nf = 0;
+            if ((rc = select_mr_flagged(c, slot, &nf))) return rc;
+            if (nf == 0u) break;
             c->cur ^= 1;                  // the gated partition did nothing: undo the ping-pong flip
             rc = select_mr_fallback(c, nCells, slot, l - 1);
             if (rc) return rc;
@@ -1875,8 +2179,6 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             stats->ms_partition = sum_events(c->evPart, c->evPartUsed);
         }
     }
-    cudaEventDestroy(evA);
-    cudaEventDestroy(evB);
     return ORB_OK;
 }
 

@@ -13,9 +13,9 @@
 //                  m iterations of orbit.cpp:149-232.            4 B / active particle / pass
 //   k_update<M>    one thread per cell: replays the reference's float decision rule
 //                  (orbit.cpp:204-229) over the counted trial cuts; emits the next cuts.
-//   k_partition    stable split of every cell in one launch: block scan + decoupled
-//                  look-back across tiles with restarts at cell boundaries, scatter staged
-//                  through shared memory.                      24 B / particle / level
+//   k_partition_*  stable split of every cell in one launch: cooperative reduce-then-scan over
+//                  contiguous tile ranges (or one block per small cell), scatter staged through
+//                  shared memory.                              24 B / particle / level
 //   k_bbox         per-cell min/max of x,y,z (north-star extension).  12 B / particle
 //   k_level_setup, k_tile_map, k_split, k_finalize_*  O(nCells) bookkeeping.
 #pragma once
@@ -169,6 +169,19 @@ __global__ void k_level_setup(const orb_cell *__restrict__ cells, uint32_t nCell
     lv.nleft_g[c] = 0;
     lv.nleft_l[c] = 0;
     init_first_cuts(lv, c, L, R, nc);
+}
+
+// ServiceCount on the device (count.cpp:16): local size of every cell of the level from the range map
+__global__ void k_cell_sizes(const orb_cell *__restrict__ cells, uint32_t nCells, const uint32_t *__restrict__ range,
+                             uint32_t *__restrict__ out) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nCells) out[c] = range[2 * cells[c].id + 1] - range[2 * cells[c].id];
+}
+// ... and the sizes summed over ranks remembered per cell id (the totals the bisection's target derives from)
+__global__ void k_store_totals(const orb_cell *__restrict__ cells, uint32_t nCells, const uint32_t *__restrict__ tot,
+                               uint32_t *__restrict__ total_by_id) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nCells) total_by_id[cells[c].id] = tot[c];
 }
 
 // first cell whose range extends beyond the start of each map tile

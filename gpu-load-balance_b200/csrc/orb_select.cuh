@@ -127,7 +127,8 @@ struct SelResolveSmem {
 };
 __device__ __forceinline__ void sel_resolve_cell(const LevelState &lv, const SelState &ss, uint32_t c, int nb1, uint32_t candCap,
                                                  bool publish, uint32_t *hbuf, SelResolveSmem &rs, uint32_t &bfOut, uint32_t &blOut,
-                                                 bool preloaded = false /* hbuf already holds the row (barrier done by the caller) */) {
+                                                 bool preloaded = false /* hbuf already holds the row (barrier done by the caller) */,
+                                                 bool countFlag = true /* false: the caller counts flagged cells elsewhere */) {
     const int tid = threadIdx.x;
     const int per = nb1 / kThreads;          // 2 .. 32
     if (!preloaded) __syncthreads();
@@ -175,7 +176,7 @@ __device__ __forceinline__ void sel_resolve_cell(const LevelState &lv, const Sel
         ss.base[c] = ok ? rs.base : 0u;
         ss.ncand[c] = ok ? rs.end - rs.base : 0u;
         ss.flag[c] = ok ? 0u : 1u;
-        if (!ok) atomicAdd(ss.n_flagged, 1u);
+        if (!ok && countFlag) atomicAdd(ss.n_flagged, 1u);
     }
     __syncthreads();
 }
@@ -203,14 +204,47 @@ __device__ __forceinline__ void sel_bin_bounds(uint32_t first, uint32_t last, in
     if (first > last) { fLo = 1.f; fHi = 0.f; }     // empty
 }
 
+// Exchange arenas of all ranks (protocol of orb_exchange.cuh) and the cross-rank barrier at the start of a kernel:
+// block 0 stores the exchange's sequence number into every peer's flag word (this rank's preceding kernel has
+// completed: call after pdl_enter), every block spins on its own rank's flag words.  n <= 1: nothing to wait for.
+struct XArena {
+    int n, self;
+    uint32_t seq;                      // sequence number of this kernel's barrier (monotone, identical on all ranks)
+    uint32_t *arena[kMaxPeers];        // flags[64] | ... (word offsets below, identical on all ranks)
+    // result records [nCells][8] | candidate counts [R][ownedStride] | candidate slots [R][ownedStride][slotWords] |
+    // local rows | global rows
+    uint32_t offRes, offRecvCnt, offRecv, offHistL, offHistG;
+};
+__device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void x_barrier(const XArena &xa) {
+    const int t = threadIdx.x;
+    if (xa.n <= 1) return;
+    if (blockIdx.x == 0 && t < xa.n && t != xa.self) {
+        __threadfence_system();
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(xa.arena[t] + xa.self), "r"(xa.seq) : "memory");
+    }
+    if (t < xa.n && t != xa.self) {
+        const uint32_t *f = xa.arena[xa.self] + t;
+        while ((int32_t)(ld_sys_u32(f) - xa.seq) < 0) {}
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, MODE == kSelHist ? 4 : 3)
 k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z, float *__restrict__ cand,
              LevelState lv, SelState ss, const uint32_t *__restrict__ tile_first, uint32_t nCells, uint32_t nLocal,
              uint32_t nTiles, int nb1, int rep, uint32_t candCap, unsigned long long *dbg, float *__restrict__ slots,
-             uint32_t slotWords, int preResolved) {
+             uint32_t slotWords, int preResolved, XArena xa /* n > 1: cross-rank barrier before the pass (the rows it
+             resolves from are the all-reduced ones) */) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     pdl_enter();
+    x_barrier(xa);
     unsigned long long *bs = dbg ? dbg + (size_t)blockIdx.x * 4 : nullptr;      // ORB_DEBUG_TIMES=2: per-block phase stamps
     if (bs && threadIdx.x == 0) bs[0] = gtimer();
     // dynamic: ring (kCountStages x 16 KB) | HIST: hist[nb1][rep]  /  COMPACT: stage[kWarps][kSelWarpStage] | hbuf[nb1]
@@ -441,12 +475,17 @@ struct SelSearchSmem {
     uint32_t base2, end2, namb, finalCnt;
     float lo2, scale2, cutf;
     int needFinal;
+    float resL, resR;             // result of sel_block_search_core
+    int resIt, resFnd;
+    uint32_t resNleft;
 };
 
-__device__ __forceinline__ bool sel_block_search(const float *vals, uint32_t K, uint32_t base, int hasOuter, float lo1,
-                                                 float scale1, int nb1, int bfirst, int blast, uint32_t *hist2, float *amb,
-                                                 const LevelState &lv, const SelState &ss, const SelCtl &sc, uint32_t c,
-                                                 int hbmPasses, SelSearchSmem &sm, unsigned long long *dbg = nullptr) {
+// Core of the search: computes the cell's result into sm.res* (valid for every thread on return) and returns true, or
+// returns false when the cell has to be left to the iterative path (block-uniform).  Writes no global memory.
+__device__ __forceinline__ bool sel_block_search_core(const float *vals, uint32_t K, uint32_t base, int hasOuter, float lo1,
+                                                      float scale1, int nb1, int bfirst, int blast, uint32_t *hist2, float *amb,
+                                                      const LevelState &lv, uint32_t c, SelSearchSmem &sm,
+                                                      unsigned long long *dbg = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nThreads = (int)blockDim.x, nWarps = nThreads >> 5;
     const float inf = __int_as_float(0x7f800000);
     SelTarget tg;
@@ -529,10 +568,7 @@ __device__ __forceinline__ bool sel_block_search(const float *vals, uint32_t K, 
     const uint32_t base2 = sm.base2;
     const uint32_t K2 = sm.end2 - base2;
     const bool tooMany = !(first <= last) || K2 > (uint32_t)kSelAmbCap;
-    if (tooMany) {   // massive ties: leave the cell to the iterative path
-        if (tid == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
-        return false;
-    }
+    if (tooMany) return false;   // massive ties: leave the cell to the iterative path
     for (uint32_t i = tid; i < K; i += nThreads) {
         const float v = vals[i];
         const int b = sel_bin(v, lo2, scale2, nb2);
@@ -582,10 +618,7 @@ __device__ __forceinline__ bool sel_block_search(const float *vals, uint32_t K, 
     __syncthreads();
     if (dbg && tid == 0) dbg[6] = gtimer();
     const int needFinal = sm.needFinal;
-    if (needFinal == 2) {   // final cut outside the candidate bins: its exact count is not known here
-        if (tid == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
-        return false;
-    }
+    if (needFinal == 2) return false;   // final cut outside the candidate bins: its exact count is not known here
     if (needFinal == 1) {
         const float cutf = sm.cutf;
         uint32_t n = 0;
@@ -595,21 +628,37 @@ __device__ __forceinline__ bool sel_block_search(const float *vals, uint32_t K, 
         __syncthreads();
         nleft = base + sm.finalCnt;
     }
-    if (tid == 0) {
-        lv.mL[c] = L; lv.mR[c] = R; lv.iter[c] = it;
-        lv.found[c] = fnd ? 1u : 0u;
-        lv.active[c] = 0u;
-        lv.nleft_g[c] = nleft;
-        lv.nleft_l[c] = nleft;
-        const unsigned long long np = (unsigned long long)(lv.bnd[c + 1] - lv.bnd[c]);
-        if (np) {
-            atomicAdd(sc.active_particles, np * (unsigned long long)hbmPasses);
-            atomicAdd(sc.active_particles + 1, np * (unsigned long long)it);
-        }
-        atomicMax(sc.level_iters, it);
-        if (!fnd) atomicAdd(sc.n_unfound_out, 1u);
-    }
+    if (tid == 0) { sm.resL = L; sm.resR = R; sm.resIt = it; sm.resFnd = fnd ? 1 : 0; sm.resNleft = nleft; }
+    __syncthreads();
     return true;
+}
+
+// Search + commit: writes the cell's result (margins, iter, found, nleft) and the level statistics and returns true, or
+// flags the cell and returns false (block-uniform); nothing else is written for a flagged cell.
+__device__ __forceinline__ bool sel_block_search(const float *vals, uint32_t K, uint32_t base, int hasOuter, float lo1,
+                                                 float scale1, int nb1, int bfirst, int blast, uint32_t *hist2, float *amb,
+                                                 const LevelState &lv, const SelState &ss, const SelCtl &sc, uint32_t c,
+                                                 int hbmPasses, SelSearchSmem &sm, unsigned long long *dbg = nullptr) {
+    const bool ok = sel_block_search_core(vals, K, base, hasOuter, lo1, scale1, nb1, bfirst, blast, hist2, amb, lv, c, sm, dbg);
+    if (threadIdx.x == 0) {
+        if (!ok) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
+        else {
+            const int it = sm.resIt;
+            lv.mL[c] = sm.resL; lv.mR[c] = sm.resR; lv.iter[c] = it;
+            lv.found[c] = sm.resFnd ? 1u : 0u;
+            lv.active[c] = 0u;
+            lv.nleft_g[c] = sm.resNleft;
+            lv.nleft_l[c] = sm.resNleft;
+            const unsigned long long np = (unsigned long long)(lv.bnd[c + 1] - lv.bnd[c]);
+            if (np) {
+                atomicAdd(sc.active_particles, np * (unsigned long long)hbmPasses);
+                atomicAdd(sc.active_particles + 1, np * (unsigned long long)it);
+            }
+            atomicMax(sc.level_iters, it);
+            if (!sm.resFnd) atomicAdd(sc.n_unfound_out, 1u);
+        }
+    }
+    return ok;
 }
 
 // dynamic shared memory of the two search kernels: vals[cap + 4] | hist2[kSelBins2] | amb[kSelAmbCap]
@@ -878,11 +927,6 @@ struct SelMrState {
     volatile uint32_t *h_status;   // finish: mapped pinned word, receives 1 + cells flagged at this level
 };
 
-__device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 // Cross-rank barrier at the start of a kernel (after pdl_enter: this rank's preceding kernel has completed).
 __device__ __forceinline__ void selx_barrier(const SelPeers &px) {
     const int t = threadIdx.x;

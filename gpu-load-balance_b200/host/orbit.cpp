@@ -238,6 +238,11 @@ void *worker_init(MDL vmdl) {
     mdl->AddService(std::make_unique<ServiceCountLeftGPU>(pst));
     mdl->AddService(std::make_unique<ServiceCountLeftGPUAxis>(pst));
     mdl->AddService(std::make_unique<ServicePartitionGPU>(pst));
+    // the ids of the reference's CPU services (orbit.cpp:303,306,309): registered so that its o=0 / o=1 control flow
+    // dispatches here too - count and partition run on the device, MakeAxis has nothing to do
+    mdl->AddService(std::make_unique<ServiceCountLeft>(pst));
+    mdl->AddService(std::make_unique<ServicePartition>(pst));
+    mdl->AddService(std::make_unique<ServiceMakeAxis>(pst));
     mdl->AddService(std::make_unique<ServiceFinalize>(pst));
     mdl->AddService(std::make_unique<ServiceBBox>(pst));
     mdl->AddService(std::make_unique<ServiceFindCuts>(pst));

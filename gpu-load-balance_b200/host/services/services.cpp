@@ -124,6 +124,25 @@ int ServiceCountLeftGPUAxis::Service(PST pst, void *vin, int nIn, void *vout, in
 }
 int ServiceCountLeftGPUAxis::Combine(void *, void *, int nIn, int, int) { return (nIn / sizeof(input)) * sizeof(output); }
 
+// the CPU service id (countLeft.cpp:9-53): same device count
+int ServiceCountLeft::Service(PST pst, void *vin, int nIn, void *vout, int) {
+    const unsigned nCells = nIn / sizeof(input);
+    ORB_CHECK(orb_count_left(pst->lcl->ctx, asOrb(vin), nCells, static_cast<output *>(vout)));
+    return nCells * sizeof(output);
+}
+int ServiceCountLeft::Combine(void *, void *, int nIn, int, int) { return (nIn / sizeof(input)) * sizeof(output); }
+
+// ------------------------------------------------------------------ MakeAxis (makeAxis.cpp:9-33): nothing to gather
+int ServiceMakeAxis::Service(PST, void *, int, void *, int) { return 0; }
+int ServiceMakeAxis::Combine(void *, void *, int, int, int) { return 0; }
+
+// ------------------------------------------------------------------ Partition under the CPU service id (partition.cpp:18-65)
+int ServicePartition::Service(PST pst, void *vin, int nIn, void *, int) {
+    ORB_CHECK(orb_partition(pst->lcl->ctx, asOrb(vin), nIn / sizeof(input)));
+    return 0;
+}
+int ServicePartition::Combine(void *, void *, int, int, int) { return 0; }
+
 // ------------------------------------------------------------------ Partition on the GPU (partitionGPU.cu:283-527)
 int ServicePartitionGPU::Service(PST pst, void *vin, int nIn, void *, int) {
     ORB_CHECK(orb_partition(pst->lcl->ctx, asOrb(vin), nIn / sizeof(input)));

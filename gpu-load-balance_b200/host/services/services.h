@@ -90,6 +90,44 @@ protected:
     virtual int Combine(void *vout, void *vout2, int nIn, int nOut1, int nOut2);
 };
 
+// ---- countLeft.h:5-15 (the CPU service id of o=0): the unmodified control flow of orbit.cpp:154-189 keeps working, the
+//      count itself runs on the device like the two GPU flavours ----
+class ServiceCountLeft : public TraverseCombinePST {
+public:
+    typedef struct Cell input;
+    typedef unsigned int output;
+    explicit ServiceCountLeft(PST pst)
+        : TraverseCombinePST(pst, PST_COUNTLEFT, MAX_CELLS * sizeof(input), MAX_CELLS * sizeof(output), "CountLeft") {}
+protected:
+    virtual int Service(PST pst, void *vin, int nIn, void *vout, int nOut);
+    virtual int Combine(void *vout, void *vout2, int nIn, int nOut1, int nOut2);
+};
+
+// ---- partition.h:5-15 (the CPU service id of o=0 / o=1, orbit.cpp:263-273) ----
+class ServicePartition : public TraverseCombinePST {
+public:
+    typedef struct Cell input;
+    typedef int output;
+    explicit ServicePartition(PST pst)
+        : TraverseCombinePST(pst, PST_PARTITION, MAX_CELLS * sizeof(input), sizeof(output), "Reshuffle") {}
+protected:
+    virtual int Service(PST pst, void *vin, int nIn, void *vout, int nOut);
+    virtual int Combine(void *vout, void *vout2, int nIn, int nOut1, int nOut2);
+};
+
+// ---- makeAxis.h:5-15: the axis-column gather is designed out (the kernels read x/y/z by per-cell axis); the id stays
+//      registered so that orbit.cpp:113-121 can call it ----
+class ServiceMakeAxis : public TraverseCombinePST {
+public:
+    typedef struct Cell input;
+    typedef int output;
+    explicit ServiceMakeAxis(PST pst)
+        : TraverseCombinePST(pst, PST_MAKEAXIS, MAX_CELLS * sizeof(input), sizeof(output), "MakeAxis") {}
+protected:
+    virtual int Service(PST pst, void *vin, int nIn, void *vout, int nOut);
+    virtual int Combine(void *vout, void *vout2, int nIn, int nOut1, int nOut2);
+};
+
 // ---- partitionGPU.h:4-14 ----
 class ServicePartitionGPU : public TraverseCombinePST {
 public:

@@ -52,7 +52,7 @@ class Stats(C.Structure):
 def build_oracle():
     subprocess.run(["make", "-C", str(ORACLE_DIR), "oracle"], check=True, capture_output=True)
     if (Path("/root/reference/src/orbit.cpp")).exists():
-        subprocess.run(["make", "-C", str(ORACLE_DIR), "ref"], check=True, capture_output=True)
+        subprocess.run(["make", "-C", str(ORACLE_DIR), "ref", "refbig"], check=True, capture_output=True)
 
 
 _lib = None
@@ -132,11 +132,15 @@ def range_hashes(x, y, z, begin, end):
 
 
 def build(x, y, z, d, *, ties=TIES_CANONICAL, full_levels=False, n_shards=1, n_threads=1, tight_box=False,
-          trace_path=None, trace_particles=False, shard_off=None):
-    """Run the oracle build in place on copies of x,y,z. Returns dict(heap, ranges, stats, x, y, z)."""
-    x = np.array(x, dtype=np.float32, copy=True)
-    y = np.array(y, dtype=np.float32, copy=True)
-    z = np.array(z, dtype=np.float32, copy=True)
+          trace_path=None, trace_particles=False, shard_off=None, copy=True):
+    """Run the oracle build in place on copies of x,y,z (copy=False: on the arrays themselves, which must be
+    contiguous float32). Returns dict(heap, ranges, stats, x, y, z)."""
+    if copy:
+        x = np.array(x, dtype=np.float32, copy=True)
+        y = np.array(y, dtype=np.float32, copy=True)
+        z = np.array(z, dtype=np.float32, copy=True)
+    else:
+        assert all(a.dtype == np.float32 and a.flags.c_contiguous for a in (x, y, z))
     n = x.size
     if shard_off is None:
         per = n // n_shards
@@ -205,8 +209,18 @@ def trace_levels(recs):
     return init_particles, levels
 
 
-def run_reference(x: int, y: int, o: int = 0, trace_path=None, trace_particles=False, threads=1, timeout=600):
-    """Run the unmodified reference binary built by oracle/Makefile; returns its stdout+stderr."""
+REF_BIN_BIG = ORACLE_DIR / "_ref" / "orbit_ref_big"
+
+
+def big_stack():
+    """preexec_fn for orbit_ref_big: its per-level stack arrays / allocas grow with the lifted MAX_CELLS"""
+    import resource
+
+    resource.setrlimit(resource.RLIMIT_STACK, (1 << 30, resource.RLIM_INFINITY))
+
+
+def run_reference(x: int, y: int, o: int = 0, trace_path=None, trace_particles=False, threads=1, timeout=600, big=False):
+    """Run the reference binary built by oracle/Makefile (big: the build with MAX_CELLS lifted); returns its stdout+stderr."""
     env = dict(os.environ)
     env["ORB_MDL_THREADS"] = str(threads)
     if trace_path:
@@ -215,7 +229,8 @@ def run_reference(x: int, y: int, o: int = 0, trace_path=None, trace_particles=F
         env.pop("ORB_REF_TRACE", None)
     if trace_particles:
         env["ORB_REF_TRACE_PARTICLES"] = "1"
-    r = subprocess.run([str(REF_BIN), str(x), str(y), str(o)], env=env, capture_output=True, text=True, timeout=timeout)
+    r = subprocess.run([str(REF_BIN_BIG if big else REF_BIN), str(x), str(y), str(o)], env=env, capture_output=True, text=True,
+                       timeout=timeout, preexec_fn=big_stack if big else None)
     if r.returncode != 0:
         raise RuntimeError(f"orbit_ref failed: {r.returncode}\n{r.stdout}\n{r.stderr}")
     return r.stdout + r.stderr

@@ -22,10 +22,11 @@ def test_committed_gpu_line_has_the_contract_keys():
     d, name = latest_gpu_line()
     assert BASE <= set(d), (name, BASE - set(d))
     assert d["metric"] == "orb_particle_passes_per_s" and d["unit"] == "particle-passes/s" and d["higher_is_better"] is True
-    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["scaling"] == "strong" and d["vs_baseline"] is None
     assert d["dtype"] == "f32" and d["data"] == "synthetic" and "workload" in d["config"] and "l2" in d["config"]
+    assert d["config"]["workload"].startswith("c3:")          # N = 1 default: the largest single-GPU config of BASELINE.json
     assert d["gpu_launches"] > 0
-    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"]) and d["clocks"]["samples"] > 0
     e = d["e2e"]
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e) and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     assert e["value"] < d["value"]                      # host buffers in and out cannot beat the resident number
@@ -36,6 +37,12 @@ def test_committed_gpu_line_has_the_contract_keys():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("reference", "port")
     # value = particle passes of the job / build time
     assert d["value"] == pytest.approx(d["particle_passes_per_build"] / (d["ms_per_step"] * 1e-3), rel=1e-9)
+    # parity is part of the line: the primary leg and every extra leg were compared with the CPU oracle's digests
+    assert d["parity"]["status"] == "pass" and d["parity_all_legs"] == "pass"
+    assert {"c2", "c4g", "c4p"} <= set(d["legs"])
+    for leg in d["legs"].values():
+        assert leg["parity"]["status"] == "pass" and leg["clocks"]["samples"] > 0 and leg["roofline"]["frac"] > 0
+    assert d["reference_exact_mode"]["parity"]["status"] == "pass"
 
 
 def test_reference_arm_line():
@@ -49,8 +56,8 @@ def test_reference_arm_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and BASE <= set(d)
     g, _ = latest_gpu_line()
-    assert (d["metric"], d["unit"], d["higher_is_better"]) == (g["metric"], g["unit"], g["higher_is_better"])
-    assert d["config"]["workload"] == g["config"]["workload"]
+    assert (d["metric"], d["unit"], d["higher_is_better"], d["scaling"]) == (g["metric"], g["unit"], g["higher_is_better"], g["scaling"])
+    assert d["config"] == g["config"]                    # both arms name the same workload, key for key
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1 and d["gpu_launches"] == 0
     # Same kind of numerator as the GPU arm (particles in unfound cells summed over bisection iterations).  Not the same
@@ -60,11 +67,28 @@ def test_reference_arm_line():
     assert 0.5 * g["particle_passes_per_build"] < passes < 2.0 * g["particle_passes_per_build"]
 
 
-def test_cpu_baseline_helper_runs_here():
-    """The cpu_baseline leg of the GPU arm is plain CPU work: run it on a small workload."""
+def test_reference_arm_same_workload_at_every_gpu_count():
+    """N > 1 shards the SAME job (strong scaling), so the reference arm builds the same workload for every --gpus."""
     sys.path.insert(0, str(ROOT))
     import bench
 
-    c = bench.cpu_baseline_beside(18, 6)
-    assert c["value"] and c["value"] > 0 and c["cores"] >= 1 and c["kind"] in ("reference", "port")
-    assert "median of" in c["sample"] and c["build_ms"] > 0
+    c1 = bench.config_dict(bench.config_of(bench.default_legs(1)[0], 1), 1)
+    for n in (2, 4, 8):
+        cn = bench.config_dict(bench.config_of(bench.default_legs(n)[0], n), n)
+        assert cn["workload"] == c1["workload"] and cn["particles_total"] == c1["particles_total"]
+    assert bench.default_legs(8)[1] == "c5"
+
+
+def test_cpu_baseline_helper_runs_here():
+    """The cpu_baseline leg of the GPU arm is plain CPU work: run it on small workloads - below the reference's cell cap
+    (the unmodified binary) and above it (the build with MAX_CELLS lifted)."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    for y, binary in ((6, "orbit_ref "), (13, "orbit_ref_big")):
+        cfg = dict(bench.config_of("c1", 1), x=18, y=y)
+        c = bench.cpu_baseline_beside(cfg, budget_s=2.0)
+        assert c["value"] and c["value"] > 0 and c["cores"] >= 1 and c["kind"] in ("reference", "port")
+        assert "median of" in c["sample"] and c["build_ms"] > 0
+        if (ROOT / "oracle" / "_ref" / binary.strip()).exists():
+            assert c["kind"] == "reference" and c["binary"].startswith(binary)

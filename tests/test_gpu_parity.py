@@ -441,3 +441,44 @@ def test_full_size_properties_c4_clustered(orb, oracle, kind):
     # the reference's |difference| < 3 rule balances every split to within a few particles unless a cell hit the cap
     if sum(st.not_found[:13]) == 0:
         assert sizes.max() - sizes.min() <= 64
+
+
+def tie_columns(n, seed=17):
+    """A fifth of the particles share one value near the median on every axis: the selection search must flag cells."""
+    rng = np.random.default_rng(seed)
+    cols = []
+    for a in range(3):
+        v = (rng.random(n, dtype=np.float32) - 0.5).astype(np.float32)
+        tie = rng.random(n) < 0.2
+        v[tie] = np.float32(0.01 * (a + 1))
+        cols.append(v)
+    return cols
+
+
+@pytest.mark.parametrize("n,d,gen", [(1 << 16, 1 << 8, "uniform"), (1 << 22, 1 << 13, "uniform"), (1 << 20, 1 << 14, "uniform"),
+                                     (100_003, 1 << 11, "uniform"), (1 << 21, 1 << 12, "plummer"), (1 << 20, 1 << 11, "ties"),
+                                     (1 << 23, 1 << 4, "uniform")])
+def test_multi_rank_protocol_against_itself(orb, oracle, n, d, gen, monkeypatch):
+    """ORB_MR_SELF=1: one rank runs the whole multi-rank protocol of orb_exchange.cuh (REDUCE, owner FINISH, APPLY; streaming,
+    block-per-cell and warp-per-cell levels) with itself as the only peer - every kernel of the exchange path on one GPU."""
+    monkeypatch.setenv("ORB_MR_SELF", "1")
+    if gen == "uniform":
+        x, y, z = orb.generate_uniform(n)
+    elif gen == "ties":
+        x, y, z = tie_columns(n)
+    else:
+        x, y, z = orb.generate_clustered(n, gen)
+    ref = oracle.build(x, y, z, d, ties=oracle.TIES_CANONICAL)
+    with orb.Orb(n, d) as ctx:
+        ctx.upload(x, y, z)
+        heap, st = ctx.build()
+        gx, gy, gz = ctx.download()
+        rng = ctx.ranges()
+    L = st.n_levels
+    assert list(st.iters[:L]) == list(ref["stats"].iters[:L])
+    assert list(st.not_found[:L]) == list(ref["stats"].not_found[:L])
+    assert heap.tobytes() == ref["heap"].tobytes()
+    assert np.array_equal(rng, ref["ranges"][0])
+    for a, b in ((gx, ref["x"]), (gy, ref["y"]), (gz, ref["z"])):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert (st.search_fallback_cells > 0) == (gen == "ties")

@@ -14,25 +14,44 @@ def fields(p):
 @pytest.mark.parametrize("ranks", [2, 4, 8])
 @pytest.mark.parametrize("x_min", [14, 20, 24, 27])
 def test_multi_rank_plan_depends_on_shared_numbers_only(orb, ranks, x_min):
+    """Peer-memory protocol (orb_exchange.cuh): every level of every tree takes the selection search - streaming passes
+    (3), one block per cell (4) or one warp per cell (5) - and all ranks plan it alike."""
     n_min = (1 << x_min) + 12345
     shards = [n_min, n_min + n_min // 3, 2 * n_min][:ranks] + [n_min + 7] * max(0, ranks - 3)
     n_global = sum(shards)
     for y in (4, 12, 16, 20):
+        slot_total = max(1 << 20, 64 << y)
         for level in range(1, y + 1):
             n_cells = 1 << (level - 1)
             plans = [fields(orb.plan_level(n, n_cells, 1 << y, n_ranks=ranks, n_global=n_global, n_local_min=n_min)) for n in shards]
             assert all(p == plans[0] for p in plans), (ranks, x_min, y, level, plans)
             search, bins, cand_cap, slot_words, hist_words, pre = plans[0]
-            assert search in (0, 3)
+            hist_fit = n_min // 8 + 2 * 8192                     # fits every rank's buffer, also the smallest shard's
+            if search == 0:      # only when even 32 bins per cell do not fit the smallest shard's rows
+                assert n_cells * 32 > hist_fit or 32 * n_cells > slot_total
+                assert (bins, cand_cap, slot_words, hist_words, pre) == (0, 0, 0, 0, 0)
+                continue
+            assert hist_words == n_cells * bins and hist_words <= hist_fit
+            assert slot_words in POW2 and slot_words * n_cells <= slot_total
+            assert cand_cap <= 49152
+            lavg = max(n_global // ranks, n_min) // n_cells
             if search == 3:
-                assert n_cells <= 2048
-                assert bins in (512, 1024, 2048, 4096, 8192) and hist_words == n_cells * bins
-                assert hist_words <= n_min // 16 + 2 * 8192              # fits every rank's buffer, also the smallest shard's
-                assert 4096 < cand_cap <= 49152
-                assert slot_words in POW2 and slot_words * n_cells <= 1 << 20
+                assert (n_cells < 512 or lavg > 1 << 20) and lavg > 8192
+                assert bins in (512, 1024, 2048, 4096, 8192)
                 assert pre in (0, 512, 1024) and (pre == 0 or pre == bins)
             else:
-                assert (bins, cand_cap, slot_words, hist_words, pre) == (0, 0, 0, 0, 0)
+                assert search in (4, 5) and (n_cells >= 512 or lavg <= 8192) and pre == 0
+                assert bins in (32, 64, 128, 256, 512, 1024, 2048)
+                assert (search == 5) == (lavg < 4096)
+
+
+def test_north_star_levels_never_take_the_iterative_search(orb):
+    """C3 (2^27 -> 2^16) on 2, 4, 8 ranks and C5 (2^30 -> 2^20) on 8 ranks: every level uses the selection search."""
+    for x, y, ranks in ((27, 16, 2), (27, 16, 4), (27, 16, 8), (30, 20, 8)):
+        n = (1 << x) // ranks
+        kinds = [orb.plan_level(n, 1 << (l - 1), 1 << y, n_ranks=ranks).search for l in range(1, y)]
+        assert all(k in (3, 4, 5) for k in kinds), (x, y, ranks, kinds)
+        assert kinds[0] == 3 and kinds[-1] in (4, 5)
 
 
 @pytest.mark.parametrize("x", [10, 16, 20, 24, 26, 27, 30])
@@ -68,4 +87,6 @@ def test_automatic_prefuse_policy(orb):
     assert not any(small)
     assert big[:2] == [0, 0] and all(big[3:])          # 2^26 / 2^25-particle cells want more than 1024 bins: separate pass
     assert all(forced)
-    assert multi[0] == 0 and all(multi[1:])            # 2 x 2^24 in 2 cells: 2048 bins wanted, more than the partition holds
+    # 2 x 2^24 in 2 cells: 2048 bins wanted, more than the partition holds; from 512 cells on the cells are searched by
+    # one block each (their rows come from k_xd_hist, not from the partition)
+    assert multi[0] == 0 and all(multi[1:8]) and not any(multi[8:])
