@@ -156,6 +156,14 @@ struct orb_ctx {
     int selBinAvg = 8192;          // ORB_SELECT_BIN_AVG: HIST bins per cell are doubled (512..8192) until a bin holds at most this many particles on average
     int selT512MinAvg = 32768;     // ORB_SELECT_T512_MIN: cells of at least this many particles get 512-thread blocks
     bool pdl = true;               // programmatic dependent launch between the small kernels of a level
+    // partition without its phase-1 read (PreLeft, orb_kernels.cuh): the search's last pass and the partition share one
+    // chunk per block; ORB_PRELEFT=0 disables
+    bool preLeft = true;
+    orb::PreLeft *d_pre = nullptr; // [64 * nSM]
+    uint32_t preTagSeq = 0;        // tag of the current level's records
+    uint32_t chunkTiles = 0;       // count tiles (4096 particles) per block of the current level's shared chunking; 0: none
+    uint32_t preListStride = 0;    // several ranks: words of one cell's candidate slot (the records index into d_slots_l)
+    bool preValid = false;         // this level's search wrote records the partition may use
     orb::SelState sel{};
     size_t selHistWords = 0;
     uint32_t *d_sel_nflag = nullptr;   // [kMaxLevels] cells left to the iterative path per level
@@ -593,6 +601,20 @@ SelPlan sel_plan(const orb_ctx *c, uint32_t nCells, int forcedNb = 0 /* rows alr
     return p;
 }
 
+// does the partition of a level of nCells cells run as the cooperative reduce-then-scan kernel (see launch_partition)?
+inline bool partition_is_coop(const orb_ctx *c, uint32_t nCells) {
+    const uint64_t avg = c->nLocal / nCells;
+    return !(avg <= 16ull * orb::kPartTile && nCells >= 2u * (uint32_t)c->nSM);
+}
+// Chunk per block (in count tiles) that the search's last pass and the cooperative partition share at this level, so
+// that the search can hand the partition the left counts of its blocks' trailing segments (PreLeft); 0: not at this level.
+uint32_t level_chunk_tiles(const orb_ctx *c, uint32_t nCells) {
+    if (!c->preLeft || c->tieMode == 1 || !c->nLocal || !partition_is_coop(c, nCells)) return 0u;
+    const uint32_t nTiles = ceil_div(c->nLocal, orb::kCountTile);
+    const uint32_t G = (uint32_t)c->nSM * (uint32_t)std::max(1, std::min(std::min(c->occPartStream, c->occSelStream[1]), 3));
+    return std::max<uint32_t>(1u, ceil_div(nTiles, G));
+}
+
 int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx, int preNb = 0) {
     using namespace orb;
     const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
@@ -606,6 +628,13 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
     sc.n_unfound_out = c->d_lvl_unfound + levelIdx;
     int rc;
     const SelPlan pl = sel_plan(c, nCells, preNb);
+    SelDone dn;
+    dn.done = c->d_cdone + slotBase + kPassSlots - 1;
+    dn.h_status = (volatile uint32_t *)(c->h_status_dev + slotBase + kPassSlots - 1);
+    c->chunkTiles = level_chunk_tiles(c, nCells);
+    c->preValid = c->chunkTiles != 0u;
+    PreLeft *pre = c->preValid ? c->d_pre : nullptr;
+    const uint32_t preTag = ++c->preTagSeq;
     // block size of the per-cell search kernels: big blocks when shared memory allows one block per SM anyway
     auto search_threads = [](size_t smem) { return smem > 112 * 1024 ? 1024 : (smem > 56 * 1024 ? 512 : 256); };
     if (pl.cellsInSmem) {
@@ -617,7 +646,8 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, pl.threads, smem));
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
         if ((rc = count_event_begin(c))) return rc;
-        CK(launch_pdl(c, kern, dim3(grid), dim3(pl.threads), smem, x, y, z, c->lv, ss, sc, nCells, pl.cellCap, preNb));
+        CK(launch_pdl(c, kern, dim3(grid), dim3(pl.threads), smem, x, y, z, c->lv, ss, sc, nCells, pl.cellCap, preNb, dn, pre, preTag,
+                      c->chunkTiles * (uint32_t)kCountTile, (uint32_t)c->nLocal));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     } else {
@@ -637,7 +667,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
             const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 4));
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                          nCells, nL, nTiles, nb1, rep, candCap, dbgBase, (float *)nullptr, 0u, 0, no_arena()));
+                          nCells, nL, nTiles, nb1, rep, candCap, dbgBase, (float *)nullptr, 0u, 0, no_arena(), (PreLeft *)nullptr, 0u, 0u));
             if ((rc = count_event_end(c))) return rc;
             c->nCountLaunch++;
         }
@@ -645,12 +675,13 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
             const size_t smem = ringBytes + (size_t)kWarps * kSelWarpStage * 4 + (size_t)nb1 * 4;
             int occ = 1;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelCompact>, kThreads, smem));
-            const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 3));
+            const uint32_t grid = c->chunkTiles ? ceil_div(nTiles, c->chunkTiles)
+                                                : std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 3));
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
                           nCells, nL, nTiles, nb1, 1, c->selBigFinish ? 0x7fffffffu : candCap,
                           dbgBase ? dbgBase + (size_t)kDbgBlocks * 4 : (unsigned long long *)nullptr,
-                          (float *)nullptr, 0u, 0, no_arena()));
+                          (float *)nullptr, 0u, 0, no_arena(), pre, preTag, c->chunkTiles));
             if ((rc = count_event_end(c))) return rc;
         }
         {
@@ -662,18 +693,26 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
             if ((rc = aux_begin(c, "finish", levelIdx))) return rc;
             CK(launch_pdl(c, k_sel_finish, dim3(grid), dim3(threads), smem, (const float *)cand, c->lv, ss, sc, nCells, nb1, candCap, c->d_err,
                           dbgBase ? dbgBase + (size_t)2 * kDbgBlocks * 4 : (unsigned long long *)nullptr, preNb ? 1 : 2,
-                          c->selBigFinish ? 1 : 0));
+                          c->selBigFinish ? 1 : 0, dn));
             if ((rc = aux_end(c))) return rc;
         }
         c->nCountLaunch += 1;
         c->nUpdateLaunch += 1;    // the finish kernel takes the place of the per-pass update kernels
     }
     CK(cudaGetLastError());
-    // cells the search could not finish: the iterative search, gated on the device by this level's flag count
-    if ((rc = aux_begin(c, "fallback_gate", levelIdx))) return rc;
+    // Cells the search could not finish are reported, not handled here: the last block of the search writes 1 + their
+    // number into mapped memory; orb_build enqueues split + partition gated on that count and runs the iterative search
+    // (select_fallback) only if the host then reads a non-zero count - no launch at all in the common case.
+    return ORB_OK;
+}
+
+// iterative search for the cells the single-rank selection search flagged at this level (cooperative, host-free)
+int select_fallback(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx) {
+    int rc;
+    if ((rc = aux_begin(c, "fallback", levelIdx))) return rc;
     const bool prof = c->profile;
     c->profile = false;            // its time belongs to the aux group, not to ms_count
-    rc = launch_level_persistent(c, nCells, 3, slotBase, levelIdx, ss.n_flagged, ss.flag);
+    rc = launch_level_persistent(c, nCells, 3, slotBase, levelIdx, nullptr, c->sel.flag);
     c->profile = prof;
     if (rc) return rc;
     return aux_end(c);
@@ -796,6 +835,8 @@ int prefuse_nb(const orb_ctx *c, uint32_t nNext, int M) {
 // reports 1 + (cells flagged) in h_status[slotBase + kPassSlots - 1] (see select_mr_flagged).
 int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int slotBase, int levelIdx, int preNb = 0) {
     using namespace orb;
+    c->chunkTiles = 0;
+    c->preValid = false;
     const float *x = c->x[c->cur], *y = c->y[c->cur], *z = c->z[c->cur];
     float *cand = c->x[c->cur ^ 1];
     const bool peer = c->peerEnabled && c->peerX[c->rank] != nullptr;
@@ -839,7 +880,7 @@ int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int
         const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 4));
         if ((rc = count_event_begin(c))) return rc;
         CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                      nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u, 0, no_arena()));
+                      nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u, 0, no_arena(), (PreLeft *)nullptr, 0u, 0u));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     }
@@ -863,7 +904,7 @@ int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int
         if ((rc = count_event_begin(c))) return rc;
         CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, peer ? ss : sg,
                       (const uint32_t *)c->d_tile_first, nCells, nL, nTiles, nb1, 1, pl.candCap, (unsigned long long *)nullptr,
-                      c->d_slots_l, pl.slotWords, peer ? 1 : 0, no_arena()));
+                      c->d_slots_l, pl.slotWords, peer ? 1 : 0, no_arena(), (PreLeft *)nullptr, 0u, 0u));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     }
@@ -936,6 +977,11 @@ int launch_level_select_mr2(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, in
     const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
     const uint32_t nL = (uint32_t)c->nLocal;
     const uint32_t nSM = (uint32_t)c->nSM;
+    // streaming levels: the COMPACT pass records the partition's per-block left counts (candidates in this rank's slots)
+    c->chunkTiles = pl.regime == 0 ? level_chunk_tiles(c, nCells) : 0u;
+    c->preValid = c->chunkTiles != 0u;
+    c->preListStride = pl.slotWords;
+    ++c->preTagSeq;
     const uint32_t nOwnedMax = ceil_div(nCells, (uint32_t)c->nRanks);
     // ---- HIST: this rank's rows ----
     if (pl.regime == 0) {
@@ -946,7 +992,7 @@ int launch_level_select_mr2(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, in
             const uint32_t grid = std::min<uint32_t>(nTiles, nSM * (uint32_t)std::min(std::max(occ, 1), 4));
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                          nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u, 0, no_arena()));
+                          nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u, 0, no_arena(), (PreLeft *)nullptr, 0u, 0u));
             if ((rc = count_event_end(c))) return rc;
             c->nCountLaunch++;
         }
@@ -979,11 +1025,11 @@ int launch_level_select_mr2(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, in
             const size_t smem = ringBytes + (size_t)kWarps * kSelWarpStage * 4 + (size_t)nb1 * 4;
             int occ = 1;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelCompact>, kThreads, smem));
-            const uint32_t grid = std::min<uint32_t>(nTiles, nSM * (uint32_t)std::min(std::max(occ, 1), 3));
+            const uint32_t grid = c->chunkTiles ? ceil_div(nTiles, c->chunkTiles) : std::min<uint32_t>(nTiles, nSM * (uint32_t)std::min(std::max(occ, 1), 3));
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, sg,
                           (const uint32_t *)c->d_tile_first, nCells, nL, nTiles, nb1, 1, pl.candCap, (unsigned long long *)nullptr,
-                          c->d_slots_l, pl.slotWords, 0, xa));
+                          c->d_slots_l, pl.slotWords, 0, xa, c->preValid ? c->d_pre : (PreLeft *)nullptr, c->preTagSeq, c->chunkTiles));
             if ((rc = count_event_end(c))) return rc;
             c->nCountLaunch++;
         }
@@ -1075,7 +1121,8 @@ orb::NextHist no_next_hist() {
     return nh;
 }
 
-int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket, const uint32_t *gate = nullptr, orb::NextHist nh = no_next_hist()) {
+int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket, const uint32_t *gate = nullptr, orb::NextHist nh = no_next_hist(),
+                     bool usePre = false /* this level's search left PreLeft records for the chunking c->chunkTiles */) {
     using namespace orb;
     (void)ticket;
     const uint32_t nTiles = ceil_div(c->nLocal, kPartTile);
@@ -1098,15 +1145,29 @@ int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket, const uint32
     float *x2 = c->x[o], *y2 = c->y[o], *z2 = c->z[o];
     const uint64_t avg = c->nLocal / nCells;
     const size_t smem = sizeof(PartSmem);
-    if (avg <= 16ull * kPartTile && nCells >= 2u * (uint32_t)c->nSM) {
+    (void)avg;
+    if (!partition_is_coop(c, nCells)) {
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)c->occPartCells);
         k_partition_cells<<<grid, kThreads, smem, c->stream>>>(x, y, z, x2, y2, z2, c->lv, c->d_final_cut, nCells, (uint32_t)c->nLocal, gate, nh);
     } else {
-        const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)c->occPartStream);
+        uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)c->occPartStream);
+        // PreLeft: same chunk per block as the search's last pass (count tiles of 4096 = two partition tiles)
+        const PreLeft *pre = nullptr;
+        uint32_t preTag = 0, tpb = 0, listStride = 0;
+        const float *preList = nullptr;
+        if (usePre && c->preValid && c->chunkTiles) {
+            tpb = 2u * c->chunkTiles;
+            grid = ceil_div(ceil_div(c->nLocal, kCountTile), c->chunkTiles);
+            pre = c->d_pre;
+            preTag = c->preTagSeq;
+            if (c->nRanks > 1 || c->mrSelf) { preList = c->d_slots_l; listStride = c->preListStride; }
+            else preList = x2;      // the cells' candidate lists lie in the idle column, which this launch overwrites - after phase 1
+        }
         uint32_t nLocal32 = (uint32_t)c->nLocal, nT = nTiles, nC = nCells;
         void *args[] = {(void *)&x, (void *)&y, (void *)&z, (void *)&x2, (void *)&y2, (void *)&z2, (void *)&c->lv,
                         (void *)&c->d_final_cut, (void *)&c->d_tile_first, (void *)&nC, (void *)&nLocal32, (void *)&nT,
-                        (void *)&c->d_blk_left, (void *)&c->d_blk_restart, (void *)&gate, (void *)&nh};
+                        (void *)&c->d_blk_left, (void *)&c->d_blk_restart, (void *)&gate, (void *)&nh,
+                        (void *)&pre, (void *)&preTag, (void *)&tpb, (void *)&preList, (void *)&listStride};
         CK(cudaLaunchCooperativeKernel((const void *)k_partition_coop, dim3(grid), dim3(kThreads), args, smem, c->stream));
     }
     if (c->profile) CK(cudaEventRecord(e1, c->stream));
@@ -1331,6 +1392,8 @@ static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_l
     CK(cudaMalloc(&c->d_blk_left, sizeof(uint32_t) * 64 * (size_t)c->nSM));
     CK(cudaMalloc(&c->d_blk_restart, sizeof(uint32_t) * 64 * (size_t)c->nSM));
     CK(cudaMalloc(&c->d_blk_le, sizeof(uint32_t) * 64 * (size_t)c->nSM));
+    CK(cudaMalloc(&c->d_pre, sizeof(orb::PreLeft) * 64 * (size_t)c->nSM));
+    CK(cudaMemset(c->d_pre, 0, sizeof(orb::PreLeft) * 64 * (size_t)c->nSM));
     CK(cudaMalloc(&c->d_nGE, (size_t)std::max<uint32_t>(1u, n_leaf_cells) * 4));
     CK(cudaMalloc(&c->d_nLE, (size_t)std::max<uint32_t>(1u, n_leaf_cells) * 4));
     CK(cudaMalloc(&c->d_tickets, sizeof(uint32_t) * kMaxLevels));
@@ -1422,6 +1485,8 @@ static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_l
             CK(cudaMemset(c->d_dbg_blocks, 0, bytes));
         }
     }
+    const char *plf = getenv("ORB_PRELEFT");
+    if (plf) c->preLeft = atoi(plf) != 0;
     const char *pd = getenv("ORB_PDL");
     if (pd) c->pdl = atoi(pd) != 0;
     const char *spc = getenv("ORB_SELECT_PERCELL_MIN");
@@ -1495,7 +1560,7 @@ int orb_destroy(orb_ctx *c) {
     for (int r = 0; r < orb::kMaxPeers; ++r)
         if (c->peerIpc[r]) { cudaIpcCloseMemHandle(c->peerCnt[r]); cudaIpcCloseMemHandle(c->peerFlag[r]); }
     cudaFree(c->d_lvl_passes); cudaFree(c->d_lvl_unfound); cudaFree(c->d_cdone); cudaFree(c->d_peer_cnt); cudaFree(c->d_peer_flag);
-    cudaFree(c->d_final_cut); cudaFree(c->d_tile_first); cudaFree(c->d_blk_left); cudaFree(c->d_blk_restart); cudaFree(c->d_blk_le); cudaFree(c->d_nGE); cudaFree(c->d_nLE); cudaFree(c->d_tickets);
+    cudaFree(c->d_final_cut); cudaFree(c->d_tile_first); cudaFree(c->d_blk_left); cudaFree(c->d_blk_restart); cudaFree(c->d_blk_le); cudaFree(c->d_pre); cudaFree(c->d_nGE); cudaFree(c->d_nLE); cudaFree(c->d_tickets);
     cudaFree(c->d_nactive); cudaFree(c->d_done); cudaFree(c->d_misc); cudaFree(c->d_active_particles);
     cudaFree(c->d_level_iters); cudaFree(c->d_err); cudaFree(c->d_bb); cudaFree(c->d_bb6);
     if (c->h_status) cudaFreeHost((void *)c->h_status);
@@ -1983,6 +2048,8 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             if (rc) return rc;
         }
         prepared = false;
+        c->chunkTiles = 0;
+        c->preValid = false;
         int np = 0;
         uint32_t nu = 0;
         bool speculate = false;     // split + partition enqueued behind the search before its flag count is known
@@ -2000,6 +2067,12 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             rc = launch_level_select(c, nCells, slot, l - 1, preNb);
             if (rc) return rc;
             np = -1;
+            speculate = c->tieMode != 1;
+            if (!speculate) {
+                uint32_t nf = 0;
+                if ((rc = select_mr_flagged(c, slot, &nf))) return rc;
+                if (nf && (rc = select_fallback(c, nCells, slot, l - 1))) return rc;
+            }
         } else if (level_can_persist(c, nCells, M)) {
             // host-free: the whole loop (and the extra count of capped cells) is one cooperative launch;
             // passes / unfound are read back with the other statistics after the build
@@ -2056,7 +2129,8 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             CK(launch_pdl(c, k_split, dim3(splitBlocks), dim3(256), 0, c->d_heap, first, nCells, c->lv, c->d_range, c->d_total, c->d_final_cut, gate, nx));
             c->nOtherLaunch++;
             if (c->tieMode != 1) {
-                rc = launch_partition(c, nCells, c->d_tickets + (l - 1), gate, nh);
+                // (a second attempt follows the iterative fallback: the flagged cells have no PreLeft records)
+                rc = launch_partition(c, nCells, c->d_tickets + (l - 1), gate, nh, attempt == 0);
                 if (rc) return rc;
             }
             if (!gate) break;
@@ -2064,7 +2138,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             if ((rc = select_mr_flagged(c, slot, &nf))) return rc;
             if (nf == 0u) break;
             c->cur ^= 1;                  // the gated partition did nothing: undo the ping-pong flip
-            rc = select_mr_fallback(c, nCells, slot, l - 1);
+            rc = mrPlan.ok ? select_mr_fallback(c, nCells, slot, l - 1) : select_fallback(c, nCells, slot, l - 1);
             if (rc) return rc;
             gate = nullptr;
         }

@@ -1425,6 +1425,21 @@ __global__ void k_ranges_from_level(const orb_cell *__restrict__ cells, uint32_t
 // before the tile.  k_partition_coop gets the carries by reduce-then-scan over contiguous per-block tile ranges,
 // k_partition_cells (small cells) walks each cell with one block.
 // =====================================================================================
+// Left counts of the partition's per-block trailing segments, known BEFORE the partition runs (no phase-1 read of the
+// cut-axis column): the search's last pass over the column (COMPACT) uses the same contiguous chunk per block as the
+// partition, counts the chunk's particles below the candidate bins and remembers where the block's candidates went;
+// once the cut is final, lefts = below + #{those candidates < cut}.  Blocks of k_sel_percell, which own a whole cell,
+// record final numbers for the chunks that end inside their cell.  A record that does not carry the level's tag or
+// names another cell is ignored (the block then counts the column itself, as before).
+struct PreLeft {
+    uint32_t tag;        // level tag (stale records of earlier levels never match)
+    uint32_t cell;       // level-local index of the chunk's trailing cell
+    uint32_t below;      // kind 0: particles of the segment below the candidate bins; kind 1: its left particles
+    uint32_t gbase, tot; // kind 0: the segment's candidates are list[gbase .. gbase + tot)
+    uint32_t kind;
+    uint32_t pad_[2];
+};
+
 // Histogram rows of the NEXT level's selection search, produced while the particles pass through the partition
 // anyway: every particle is binned on its child's cut axis with the child's bin function (sel_bin over the child's
 // margins) - the next level's HIST pass, 4 B per particle, is not needed.  k_split has prepared the children's level
@@ -1753,13 +1768,16 @@ __global__ void __launch_bounds__(kThreads, 3) k_partition_coop(const float *__r
                                                                LevelState lv, const float *__restrict__ final_cut,
                                                                const uint32_t *__restrict__ tile_first, uint32_t nCells,
                                                                uint32_t nLocal, uint32_t nTiles, uint32_t *blkLeft,
-                                                               uint32_t *blkRestart, const uint32_t *__restrict__ gate, NextHist nh) {
+                                                               uint32_t *blkRestart, const uint32_t *__restrict__ gate, NextHist nh,
+                                                               const PreLeft *__restrict__ pre, uint32_t preTag, uint32_t tilesPerBlockIn,
+                                                               const float *__restrict__ preList, uint32_t preListStride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PartSmem &sm = *reinterpret_cast<PartSmem *>(smem_raw);
     if (gate && *((volatile const uint32_t *)gate) != 0u) return;     // see k_split; uniform over the grid
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tilesPerBlock = (nTiles + gridDim.x - 1) / gridDim.x;
+    // (tilesPerBlockIn: the chunking the search's last pass used, so that `pre` describes this block's chunk)
+    const uint32_t tilesPerBlock = tilesPerBlockIn ? tilesPerBlockIn : (nTiles + gridDim.x - 1) / gridDim.x;
     const uint32_t tb0 = min(blockIdx.x * tilesPerBlock, nTiles), tb1 = min(tb0 + tilesPerBlock, nTiles);
     const uint32_t chunkStart = tb0 * (uint32_t)kPartTile, chunkEnd = min(tb1 * (uint32_t)kPartTile, nLocal);
 
@@ -1775,9 +1793,21 @@ __global__ void __launch_bounds__(kThreads, 3) k_partition_coop(const float *__r
             while (lv.bnd[c + 1] < chunkEnd) ++c;            // cell that contains particle chunkEnd-1
             const uint32_t cb = lv.bnd[c];
             restart = cb >= chunkStart ? 1u : 0u;
-            const uint32_t b = max(cb, chunkStart), e = chunkEnd;
+            const uint32_t b = max(cb, chunkStart);
+            uint32_t e = chunkEnd;
             const float *col = pick_col(lv.axis[c], x, y, z);
             const float cutv = final_cut[c];
+            if (pre) {      // block-uniform: the search already knows this segment's left count (or all but its candidates)
+                const PreLeft P = pre[blockIdx.x];
+                if (P.tag == preTag && P.cell == c) {
+                    if (tid == 0) cnt = P.below;
+                    if (P.kind == 0u) {
+                        const float *list = preList + (preListStride ? (size_t)c * preListStride : (size_t)cb) + P.gbase;
+                        for (uint32_t i = tid; i < P.tot; i += kThreads) cnt += (__ldcg(list + i) < cutv) ? 1u : 0u;
+                    }
+                    e = b;      // nothing left to read
+                }
+            }
             const uint32_t a0 = min((b + 3u) & ~3u, e), a1 = max(a0, e & ~3u);
             if (tid < 8) {
                 const uint32_t ee = (tid < 4) ? b + tid : a1 + (tid - 4);

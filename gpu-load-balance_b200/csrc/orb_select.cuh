@@ -194,6 +194,7 @@ struct SelStreamSmem {
     uint32_t wS[kWarps], wF[kWarps];
     uint32_t wN[kWarps];                          // COMPACT: staged candidates per warp
     uint32_t gbase;
+    uint32_t below, spilled;                      // COMPACT: PreLeft bookkeeping of the running cell
     SelResolveSmem rs;
 };
 
@@ -241,7 +242,9 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
              LevelState lv, SelState ss, const uint32_t *__restrict__ tile_first, uint32_t nCells, uint32_t nLocal,
              uint32_t nTiles, int nb1, int rep, uint32_t candCap, unsigned long long *dbg, float *__restrict__ slots,
              uint32_t slotWords, int preResolved, XArena xa /* n > 1: cross-rank barrier before the pass (the rows it
-             resolves from are the all-reduced ones) */) {
+             resolves from are the all-reduced ones) */,
+             PreLeft *__restrict__ pre /* COMPACT: records for the partition's phase 1 (may be null) */, uint32_t preTag,
+             uint32_t tilesPerBlockIn /* != 0: chunk per block in count tiles, shared with the partition */) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     pdl_enter();
     x_barrier(xa);
@@ -258,14 +261,17 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
 
     if (MODE == kSelHist) for (int i = tid; i < nb1 * rep; i += kThreads) s_hist[i] = 0u;
     if (MODE == kSelCompact && tid < kWarps) sm.wN[tid] = 0u;
+    if (tid == 0) { sm.below = 0u; sm.spilled = 0u; }
     __syncthreads();
 
     // block b owns the contiguous tiles [tb0, tb1)
-    const uint32_t tilesPerBlock = (nTiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t tilesPerBlock = tilesPerBlockIn ? tilesPerBlockIn : (nTiles + gridDim.x - 1) / gridDim.x;
     const uint32_t tb0 = min(blockIdx.x * tilesPerBlock, nTiles), tb1 = min(tb0 + tilesPerBlock, nTiles);
     int cur = -1;
     float lo = 0.f, scale = 0.f, fLo = 1.f, fHi = 0.f;
     const float nbm1 = (float)(nb1 - 1);
+    unsigned below = 0u;          // COMPACT: this thread's particles of the running cell below the candidate bins
+    bool curOk = false;           // ... the running cell has candidate bins (not flagged by the resolve)
 
     // ---- flush of the per-cell block state (block-uniform) ----
     auto flush = [&]() {
@@ -281,9 +287,24 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
             uint32_t tot = 0, off = 0;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) { const uint32_t n = sm.wN[w]; if (w < warp) off += n; tot += n; }
+            if (pre) {      // block-uniform
+                const unsigned wb = __reduce_add_sync(0xffffffffu, below);
+                if (lane == 0 && wb) atomicAdd(&sm.below, wb);
+                below = 0u;
+            }
+            if (tid == 0) sm.gbase = tot ? atomicAdd(&ss.cursor[cur], tot) : 0u;
+            __syncthreads();
+            if (pre && tid == 0) {
+                // The last record a block writes describes its trailing segment (cells are entered in order).  A warp
+                // that spilled on its own has scattered the segment's candidates: no record for it.
+                const uint32_t lim2 = slotWords ? slotWords - 1u : 0xffffffffu;
+                PreLeft P;
+                P.tag = (curOk && !sm.spilled && sm.gbase + tot <= lim2) ? preTag : ~preTag;
+                P.cell = (uint32_t)cur; P.below = sm.below; P.gbase = sm.gbase; P.tot = tot; P.kind = 0u; P.pad_[0] = P.pad_[1] = 0u;
+                pre[blockIdx.x] = P;
+                sm.below = 0u; sm.spilled = 0u;
+            }
             if (tot) {
-                if (tid == 0) sm.gbase = atomicAdd(&ss.cursor[cur], tot);
-                __syncthreads();
                 // one rank: the cell's list in the idle column.  Several ranks: the cell's fixed-size slot of the
                 // all-gather buffer (values beyond the slot are dropped; the count word tells every rank)
                 float *dst = slotWords ? slots + (size_t)cur * slotWords : cand + lv.bnd[cur];
@@ -303,7 +324,7 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
         const uint32_t n = sm.wN[warp];
         if (n + 512u <= (uint32_t)kSelWarpStage) return;
         uint32_t g = 0;
-        if (lane == 0) g = atomicAdd(&ss.cursor[cur], n);
+        if (lane == 0) { g = atomicAdd(&ss.cursor[cur], n); sm.spilled = 1u; }
         g = __shfl_sync(0xffffffffu, g, 0);
         float *dst = slotWords ? slots + (size_t)cur * slotWords : cand + lv.bnd[cur];
         const uint32_t lim = slotWords ? slotWords - 1u : 0xffffffffu;
@@ -327,6 +348,7 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
             if (preResolved) { bf = __ldcg(&ss.bfirst[c]); bl = __ldcg(&ss.blast[c]); }     // k_selx_resolve did it for the level
             else sel_resolve_cell(lv, ss, c, nb1, candCap, publish, s_hbuf, sm.rs, bf, bl);
             sel_bin_bounds(bf, bl, nb1, fLo, fHi);
+            curOk = bf <= bl;
         }
     };
     // bin coordinate: max((x - lo) * scale, 0); NaN (inf * 0) -> 0
@@ -396,13 +418,15 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
                         for (int j = 0; j < 16; ++j)
                             if (inMask & (1u << j)) atomicAdd(&s_hist[__float2int_rz(fminf(coord(v[j]), nbm1)) * rep + repSel], 1u);
                     } else {
-                        unsigned keep = 0u;
+                        unsigned keep = 0u, lows = 0u;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float tc = coord(v[j]);
                             keep |= (unsigned)(tc >= fLo && tc < fHi) << j;
+                            lows |= (unsigned)(tc < fLo) << j;
                         }
                         keep &= inMask;
+                        below += __popc(lows & inMask);
                         warp_spill();
                         sel_warp_append<16>(v, keep, s_stage + warp * kSelWarpStage, &sm.wN[warp]);
                     }
@@ -440,12 +464,14 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
                         atomicAdd(&s_hist[b * rep + repSel], 1u);
                     }
                 } else {
-                    unsigned keep = 0u;
+                    unsigned keep = 0u, lows = 0u;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float tc = coord(v[j]);
                         keep |= (unsigned)(tc >= fLo && tc < fHi) << j;
+                        lows |= (unsigned)(tc < fLo) << j;
                     }
+                    below += __popc(lows);
                     warp_spill();
                     sel_warp_append<16>(v, keep, s_stage + warp * kSelWarpStage, &sm.wN[warp]);
                 }
@@ -685,11 +711,29 @@ __device__ __forceinline__ float *sel_stage_vals(float *sbuf, const float *__res
     return vals;
 }
 
+// level-wide "all blocks done" report of the single-rank search kernels: the last block writes 1 + (cells flagged) into
+// mapped pinned memory, which is all the host ever waits for (see orb_build)
+struct SelDone {
+    uint32_t *done;                 // blocks-finished counter (zeroed per build)
+    volatile uint32_t *h_status;
+};
+__device__ __forceinline__ void sel_report_done(const SelDone &dn, const uint32_t *n_flagged) {
+    __syncthreads();
+    if (threadIdx.x == 0 && dn.done) {
+        __threadfence();
+        if (atomicAdd(dn.done, 1u) == gridDim.x - 1u) {
+            __threadfence();
+            *dn.h_status = *((volatile const uint32_t *)n_flagged) + 1u;
+        }
+    }
+}
+
 // FINISH (streaming regime): one block per cell, candidates from the dense list written by COMPACT
 __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ cand, LevelState lv, SelState ss, SelCtl sc,
                                                      uint32_t nCells, int nb1, uint32_t cap, int *__restrict__ err,
                                                      unsigned long long *dbg, int hbmPasses /* reads of the column: 2, or 1 when the partition built the rows */,
-                                                     int allowGlobal /* more candidates than `cap`: search them where they lie instead of failing */) {
+                                                     int allowGlobal /* more candidates than `cap`: search them where they lie instead of failing */,
+                                                     SelDone dn) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     float *sbuf = reinterpret_cast<float *>(sel_smem);
     uint32_t *hist2 = reinterpret_cast<uint32_t *>(sbuf + cap + 4);
@@ -727,6 +771,7 @@ __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ c
                          c == blockIdx.x ? bs : nullptr);
         if (bs && threadIdx.x == 0 && c == blockIdx.x) bs[7] = gtimer();
     }
+    sel_report_done(dn, ss.n_flagged);
 }
 
 // =====================================================================================
@@ -737,11 +782,13 @@ __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ c
 // =====================================================================================
 __host__ __device__ inline size_t sel_percell_smem_bytes(uint32_t candCap) { return ((size_t)kSelBins2 + candCap + kSelAmbCap) * 4u; }
 
+constexpr int kSelMaxSeg = 8;     // chunk segments of one cell for which k_sel_percell records left counts
 struct SelPerCellSmem {
     SelSearchSmem search;
     uint32_t w[32];
     int first, last;
     uint32_t base, end, nlist;
+    uint32_t segBelow[kSelMaxSeg], segListEnd[kSelMaxSeg], segLeft[kSelMaxSeg];
 };
 
 // apply f(value) to every element of src[0..K): 16-byte loads where src is aligned, U loads in flight per thread
@@ -770,7 +817,10 @@ __device__ __forceinline__ void sel_for_each(const float *__restrict__ src, uint
 template <int THREADS, int MINBLOCKS, int U = 4>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float *__restrict__ x, const float *__restrict__ y,
                                                                     const float *__restrict__ z, LevelState lv, SelState ss,
-                                                                    SelCtl sc, uint32_t nCells, uint32_t candCap, int preNb) {
+                                                                    SelCtl sc, uint32_t nCells, uint32_t candCap, int preNb, SelDone dn,
+                                                                    PreLeft *__restrict__ pre, uint32_t preTag,
+                                                                    uint32_t chunk /* particles per partition block; 0: no records */,
+                                                                    uint32_t nLocal) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     uint32_t *hist = reinterpret_cast<uint32_t *>(sel_smem);
     float *list = reinterpret_cast<float *>(hist + kSelBins2);
@@ -878,14 +928,71 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float 
         // ---- COMPACT: another read (L2), candidates into shared memory ----
         float fLo, fHi;
         sel_bin_bounds((uint32_t)first, (uint32_t)last, nb, fLo, fHi);
-        sel_for_each<U>(col, K, [&](float v) {
-            const float t = fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f);
-            if (t >= fLo && t < fHi) list[atomicAdd(&sm.nlist, 1u)] = v;
-        });
+        // With `pre`: the cell is read segment by segment (pieces between the partition's chunk boundaries), so that the
+        // left count of every chunk that ends inside this cell is known afterwards: particles below the candidate bins
+        // + the segment's candidates left of the cut.
+        const uint32_t e = b + K;
+        int nSeg = 1;
+        if (pre && chunk) {
+            const uint32_t k0 = b / chunk, k1 = (e - 1u) / chunk;      // chunks of the first / last particle (K > 0 here)
+            nSeg = (int)(k1 - k0 + 1u);
+        }
+        const bool segs = pre && chunk && nSeg <= kSelMaxSeg && K > 0u;
+        if (!segs) nSeg = 1;
+        if (segs) {
+            if (tid < kSelMaxSeg) sm.segBelow[tid] = 0u;
+            __syncthreads();
+        }
+        for (int sgi = 0; sgi < nSeg; ++sgi) {
+            uint32_t s0 = b, s1 = e;
+            if (segs) {
+                const uint32_t k = b / chunk + (uint32_t)sgi;
+                s0 = max(b, k * chunk);
+                s1 = min(e, (k + 1u) * chunk);
+            }
+            unsigned lows = 0u;
+            sel_for_each<U>(col + (s0 - b), s1 - s0, [&](float v) {
+                const float t = fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f);
+                if (t >= fLo && t < fHi) list[atomicAdd(&sm.nlist, 1u)] = v;
+                lows += (t < fLo) ? 1u : 0u;
+            });
+            if (segs) {
+                lows = __reduce_add_sync(0xffffffffu, lows);
+                __syncthreads();                                  // the segment's candidates are all in the list
+                if ((tid & 31) == 0 && lows) atomicAdd(&sm.segBelow[sgi], lows);
+                if (tid == 0) sm.segListEnd[sgi] = sm.nlist;
+                __syncthreads();                                  // ... before anyone appends the next segment's
+            }
+        }
         __syncthreads();
         // ---- FINISH ----
-        sel_block_search(list, K2, base, 1, lo, scale, nb, first, last, hist, amb, lv, ss, sc, c, reads, sm.search);
+        const bool done = sel_block_search(list, K2, base, 1, lo, scale, nb, first, last, hist, amb, lv, ss, sc, c, reads, sm.search);
+        if (segs && done) {       // block-uniform
+            const float cutf = mid_cut(sm.search.resL, sm.search.resR);
+            if (tid < kSelMaxSeg) sm.segLeft[tid] = 0u;
+            __syncthreads();
+            for (int sgi = 0; sgi < nSeg; ++sgi) {
+                const uint32_t l0 = sgi ? sm.segListEnd[sgi - 1] : 0u, l1 = sm.segListEnd[sgi];
+                uint32_t m = 0;
+                for (uint32_t i = l0 + tid; i < l1; i += nThreads) m += (list[i] < cutf) ? 1u : 0u;
+                m = __reduce_add_sync(0xffffffffu, m);
+                if ((tid & 31) == 0 && m) atomicAdd(&sm.segLeft[sgi], m);
+            }
+            __syncthreads();
+            if (tid < nSeg) {
+                const uint32_t k = b / chunk + (uint32_t)tid;
+                const uint32_t segEnd = min(e, (k + 1u) * chunk);
+                // the segment is chunk k's trailing segment iff it reaches the chunk's end (the last chunk ends at nLocal)
+                if (segEnd == (k + 1u) * chunk || segEnd == nLocal) {
+                    PreLeft P;
+                    P.tag = preTag; P.cell = c; P.below = sm.segBelow[tid] + sm.segLeft[tid]; P.gbase = 0u; P.tot = 0u; P.kind = 1u;
+                    P.pad_[0] = P.pad_[1] = 0u;
+                    pre[k] = P;
+                }
+            }
+        }
     }
+    sel_report_done(dn, ss.n_flagged);
 }
 
 // =====================================================================================

@@ -481,4 +481,9 @@ def test_multi_rank_protocol_against_itself(orb, oracle, n, d, gen, monkeypatch)
     assert np.array_equal(rng, ref["ranges"][0])
     for a, b in ((gx, ref["x"]), (gy, ref["y"]), (gz, ref["z"])):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
-    assert (st.search_fallback_cells > 0) == (gen == "ties")
+    # uniform inputs never fall back; massive ties always do; dense Plummer cores may (a bin of the per-cell regimes can
+    # hold more candidates than the owner stages - the result is exact either way)
+    if gen == "uniform":
+        assert st.search_fallback_cells == 0
+    elif gen == "ties":
+        assert st.search_fallback_cells > 0
