@@ -84,6 +84,7 @@ constexpr uint32_t kSelValsCap = 49152;   // values one block of the selection s
 constexpr uint32_t kSelMrMaxCells = 2048; // several ranks: levels up to this many cells use the selection search
 constexpr size_t kSelSlotWordsTotal = (size_t)1 << 20;   // candidate slots of one rank and level (4 MB; v2 arena: at least this)
 constexpr uint32_t kSelSlotWordsMax = 65536;             // largest slot of one rank and cell
+constexpr size_t kXScratchWords = (size_t)1 << 22;       // owner's scratch for cells whose candidates exceed shared memory (16 MB)
 constexpr int kDbgPasses = 12;      // ORB_DEBUG_TIMES=2: passes and blocks recorded per level
 constexpr uint32_t kDbgBlocks = 1024;
 constexpr int kPassSlots = 40;   // >= 32 passes + slack, per level
@@ -158,6 +159,7 @@ struct orb_ctx {
     bool pdl = true;               // programmatic dependent launch between the small kernels of a level
     // partition without its phase-1 read (PreLeft, orb_kernels.cuh): the search's last pass and the partition share one
     // chunk per block; ORB_PRELEFT=0 disables
+    int partWarpMax = 2048;        // ORB_PART_WARP_MAX: average local cell size up to which the partition runs one warp per cell
     bool preLeft = true;
     orb::PreLeft *d_pre = nullptr; // [64 * nSM]
     uint32_t preTagSeq = 0;        // tag of the current level's records
@@ -198,6 +200,8 @@ struct orb_ctx {
     uint32_t xOffRes = 0, xOffRecvCnt = 0, xOffRecv = 0, xOffHistG = 0;
     size_t slotTotal = 0;              // words of candidate slots per rank and level (v2 arena)
     uint64_t nLocalMax = 0;
+    float *d_xscratch = nullptr;       // [kXScratchWords]
+    uint32_t xCandCap = kSelValsCap;   // ORB_X_CAND_CAP (testing): candidates an owner block stages in shared memory
     std::vector<int> extraPasses;      // passes of the iterative fallback per level (host-driven on several ranks)
 
     // fused combine+update over NVLink peer memory (optional; see PeerSet in orb_kernels.cuh)
@@ -750,6 +754,7 @@ struct SelMrPlan {
     bool v2;              // protocol of orb_exchange.cuh (peer memory); else the two-exchange kernels of orb_select.cuh
     int regime;           // v2: 0 streaming passes (k_sel_stream), 1 one block per cell, 2 one warp per cell (k_xd_*)
     bool warpFinish;      // v2: the owner searches a cell's candidates with one warp
+    uint32_t candCapBig;  // v2 streaming levels: candidates a cell may have when the owner searches them in global scratch (0: candCap)
     int nb1, rep;
     uint32_t candCap, slotWords;
     size_t histWords;     // rows the level exchanges
@@ -768,10 +773,17 @@ SelMrPlan sel_plan_mr(const orb_ctx *c, uint32_t nCells, int M, int forcedNb = 0
     const size_t histFit = p.v2 ? (size_t)c->nLocalMin / 8 + 2 * (size_t)orb::kSelBinsMax : (size_t)c->nLocalMin / 16 + 2 * (size_t)orb::kSelBinsMax;
     if (p.v2 && ((nCells >= 512 && lavg <= (1u << 20)) || lavg <= 8192) && !forcedNb) {
         // ---- small cells: a group of threads per cell bins / gathers it; about 64 particles per bin over all ranks ----
-        p.regime = lavg >= 4096 ? 1 : 2;
+        p.regime = lavg >= 4096 ? 1 : 2;        // (2: one warp per cell; its rows must fit the warp's shared memory)
+        // Bins per cell: the level exchanges its rows (nCells * nb words per rank, reduced and broadcast) and its
+        // candidates (about 1.5 bins' worth of particles per cell, once); the two balance at about 3 sqrt(cell size)
+        // particles per bin.  (64 per bin - rows of 64 MB per level at 2^30 particles - cost 200 us per level in the
+        // row exchange alone, profiles/r02d_c5_8gpu_levels.txt.)
+        uint64_t perBin = 64;
+        while (perBin * perBin < 4 * gavg) perBin <<= 1;          // power of two >= 2 sqrt(gavg)
         int nb = 32;
-        while (nb < orb::kSelBins2 && gavg / (uint64_t)nb > 64) nb <<= 1;
+        while (nb < orb::kSelBins2 && gavg / (uint64_t)nb > perBin) nb <<= 1;
         while (nb > 32 && (size_t)nCells * (size_t)nb > histFit) nb >>= 1;
+        if (nb > 512) p.regime = 1;
         p.nb1 = nb;
         p.rep = 1;
         p.histWords = (size_t)nCells * (size_t)nb;
@@ -793,15 +805,23 @@ SelMrPlan sel_plan_mr(const orb_ctx *c, uint32_t nCells, int M, int forcedNb = 0
     p.rep = p.nb1 <= 512 ? 4 : (p.nb1 <= 1024 ? 2 : 1);
     p.histWords = (size_t)nCells * (size_t)p.nb1;
     p.zeroWords = p.histWords;
-    p.candCap = (uint32_t)std::min<uint64_t>(kSelValsCap, 4 * (gavg / (uint64_t)p.nb1) + 4096);
+    p.candCap = (uint32_t)std::min<uint64_t>(p.v2 ? c->xCandCap : kSelValsCap, 4 * (gavg / (uint64_t)p.nb1) + 4096);
     p.warpFinish = false;
-    // slot of one rank and cell: a few bins' worth of its own particles + the count word, a power of two
-    uint64_t want = std::min<uint64_t>(p.candCap, 4 * (lavg / (uint64_t)p.nb1) + 96) + 1;
+    // slot of one rank and cell: a few bins' worth of its own particles + the count word, a power of two (v2: not bounded
+    // by what a block stages in shared memory - the owner may search a huge cell in global scratch)
+    uint64_t want = std::min<uint64_t>(p.v2 ? kSelSlotWordsMax - 1 : p.candCap, 4 * (lavg / (uint64_t)p.nb1) + 96) + 1;
     uint32_t sw = 128;
     while (sw < want) sw <<= 1;
     while (sw > 32 && (size_t)sw * nCells > slotTotal) sw >>= 1;
     p.slotWords = sw;
     p.ok = p.histWords <= histFit && (size_t)sw * nCells <= slotTotal;
+    // cells too large for a block's shared memory even with the most bins (more than 2^26 particles): global scratch
+    p.candCapBig = 0;
+    if (p.v2 && 4 * (gavg / (uint64_t)p.nb1) + 4096 > c->xCandCap) {
+        const uint64_t nOwnedMax = (nCells + c->nRanks - 1) / c->nRanks;
+        const uint64_t big = std::min<uint64_t>((uint64_t)c->nRanks * (sw - 1u), kXScratchWords / nOwnedMax);
+        if (big > p.candCap) p.candCapBig = (uint32_t)big;
+    }
     return p;
 }
 
@@ -814,6 +834,8 @@ int prefuse_nb(const orb_ctx *c, uint32_t nNext, int M) {
     // the HIST pass it replaces, whose column is still half in L2 at that size - but pays from ~2^25 particles per GPU
     // (HIST is then a full HBM pass: -9 % build time at 2^27) and whenever ranks have to agree on the rows anyway.
     if (c->prefuseHist < 0 && c->nRanks == 1 && c->nLocal < (1ull << 25)) return 0;
+    // tiny cells are partitioned by one warp each (k_partition_warp), which does not bin
+    if (nNext >= 2 && !partition_is_coop(c, nNext / 2) && c->nLocal / (nNext / 2) <= (uint64_t)c->partWarpMax) return 0;
     // The partition's block histogram holds at most 1024 bins per child.  Where the level streams (HIST / COMPACT /
     // FINISH) the rows must have the bins the level would choose itself - coarser rows mean more candidates per bin
     // and, on clustered inputs, cells that overflow the finish kernel's staging; where one block searches a whole
@@ -1003,7 +1025,7 @@ int launch_level_select_mr2(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, in
             CK(launch_pdl(c, k_xd_hist<256>, dim3(grid), dim3(kThreads), (size_t)nb1 * 4, x, y, z, c->lv, c->sel.hist, nCells, nb1));
         } else {
             const uint32_t grid = std::min<uint32_t>(ceil_div(nCells, kWarps), nSM * 8u);
-            CK(launch_pdl(c, k_xd_hist<32>, dim3(grid), dim3(kThreads), (size_t)nb1 * 4 * kWarps, x, y, z, c->lv, c->sel.hist, nCells, nb1));
+            CK(launch_pdl(c, k_xd_hist_warp, dim3(grid), dim3(kThreads), (size_t)nb1 * 4 * kWarps, x, y, z, c->lv, c->sel.hist, nCells, nb1));
         }
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
@@ -1019,6 +1041,7 @@ int launch_level_select_mr2(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, in
         c->nOtherLaunch++;
     }
     // ---- COMPACT: resolve from the global rows, own candidates to the owners ----
+    const uint32_t resolveCap = std::max(pl.candCap, pl.candCapBig);     // candidates a cell may have without being flagged
     xa.seq = ++c->xSeq;
     if (pl.regime == 0) {
         if (nTiles) {
@@ -1028,7 +1051,7 @@ int launch_level_select_mr2(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, in
             const uint32_t grid = c->chunkTiles ? ceil_div(nTiles, c->chunkTiles) : std::min<uint32_t>(nTiles, nSM * (uint32_t)std::min(std::max(occ, 1), 3));
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, sg,
-                          (const uint32_t *)c->d_tile_first, nCells, nL, nTiles, nb1, 1, pl.candCap, (unsigned long long *)nullptr,
+                          (const uint32_t *)c->d_tile_first, nCells, nL, nTiles, nb1, 1, resolveCap, (unsigned long long *)nullptr,
                           c->d_slots_l, pl.slotWords, 0, xa, c->preValid ? c->d_pre : (PreLeft *)nullptr, c->preTagSeq, c->chunkTiles));
             if ((rc = count_event_end(c))) return rc;
             c->nCountLaunch++;
@@ -1039,7 +1062,7 @@ int launch_level_select_mr2(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, in
             if (nTiles) xb.n = 0;
             const uint32_t grid = std::min<uint32_t>(nCells, nSM * 8u);
             if ((rc = aux_begin(c, "x_push", levelIdx))) return rc;
-            CK(launch_pdl(c, k_xc_push, dim3(grid), dim3(kThreads), (size_t)nb1 * 4, c->lv, sg, mr, xa, xb, nCells, nb1, pl.candCap));
+            CK(launch_pdl(c, k_xc_push, dim3(grid), dim3(kThreads), (size_t)nb1 * 4, c->lv, sg, mr, xa, xb, nCells, nb1, resolveCap));
             if ((rc = aux_end(c))) return rc;
             c->nOtherLaunch++;
         }
@@ -1050,7 +1073,7 @@ int launch_level_select_mr2(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, in
             CK(launch_pdl(c, k_xd_compact<256>, dim3(grid), dim3(kThreads), (size_t)nb1 * 4, x, y, z, c->lv, ss, mr, xa, nCells, nb1, pl.candCap));
         } else {
             const uint32_t grid = std::min<uint32_t>(ceil_div(nCells, kWarps), nSM * 8u);
-            CK(launch_pdl(c, k_xd_compact<32>, dim3(grid), dim3(kThreads), (size_t)nb1 * 4 * kWarps, x, y, z, c->lv, ss, mr, xa, nCells, nb1, pl.candCap));
+            CK(launch_pdl(c, k_xd_compact_warp, dim3(grid), dim3(kThreads), xd_compact_warp_smem(nb1), x, y, z, c->lv, ss, mr, xa, nCells, nb1, pl.candCap));
         }
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
@@ -1068,7 +1091,8 @@ int launch_level_select_mr2(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, in
         int occ = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_xf_finish_block, threads, smem));
         const uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>(nOwnedMax, nSM * (uint32_t)std::max(occ, 1)));
-        CK(launch_pdl(c, k_xf_finish_block, dim3(grid), dim3(threads), smem, c->lv, ss, mr, xa, nCells, nb1, pl.candCap, c->d_err));
+        CK(launch_pdl(c, k_xf_finish_block, dim3(grid), dim3(threads), smem, c->lv, ss, mr, xa, nCells, nb1, pl.candCap, c->d_err,
+                      pl.candCapBig ? c->d_xscratch : (float *)nullptr, pl.candCapBig));
     }
     if ((rc = aux_end(c))) return rc;
     c->nUpdateLaunch++;
@@ -1145,8 +1169,11 @@ int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket, const uint32
     float *x2 = c->x[o], *y2 = c->y[o], *z2 = c->z[o];
     const uint64_t avg = c->nLocal / nCells;
     const size_t smem = sizeof(PartSmem);
-    (void)avg;
-    if (!partition_is_coop(c, nCells)) {
+    if (!partition_is_coop(c, nCells) && avg <= (uint64_t)c->partWarpMax && !nh.enabled) {
+        // tiny cells: one warp per cell
+        const uint32_t grid = std::min<uint32_t>(ceil_div(nCells, kWarps), (uint32_t)c->nSM * 8u);
+        k_partition_warp<<<grid, kThreads, 0, c->stream>>>(x, y, z, x2, y2, z2, c->lv, c->d_final_cut, nCells, gate);
+    } else if (!partition_is_coop(c, nCells)) {
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)c->occPartCells);
         k_partition_cells<<<grid, kThreads, smem, c->stream>>>(x, y, z, x2, y2, z2, c->lv, c->d_final_cut, nCells, (uint32_t)c->nLocal, gate, nh);
     } else {
@@ -1249,6 +1276,7 @@ int alloc_arena(orb_ctx *c, bool multi) {
     c->xOffHist = (uint32_t)off; off += c->selHistWords;
     if (multi) { c->xOffHistG = (uint32_t)off; off += c->selHistWords; }
     if (off >= ((size_t)1 << 32)) return fail(ORB_ERR_ARG, "exchange arena of %zu words exceeds 32-bit word offsets", off);
+    if (multi && !c->d_xscratch) CK(cudaMalloc(&c->d_xscratch, kXScratchWords * 4));
     CK(cudaMalloc(&c->d_xchg, off * 4));
     CK(cudaMemset(c->d_xchg, 0, off * 4));
     c->sel.cursor = c->d_xchg + c->xOffCursor;
@@ -1436,6 +1464,8 @@ static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_l
         CK(cudaFuncSetAttribute(orb::k_sel_percell<1024, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
     }
     CK(cudaFuncSetAttribute(orb::k_xf_finish_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_search_smem_bytes(kSelValsCap)));
+    CK(cudaFuncSetAttribute(orb::k_xd_compact_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::xd_compact_warp_smem(512)));
+    CK(cudaFuncSetAttribute(orb::k_xf_finish_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(orb::kWarps * (orb::kXWarpCap + 4u) * 4u)));
     CK(cudaMalloc(&c->d_misc, 64));
     CK(cudaMalloc(&c->d_active_particles, 16));
     CK(cudaMalloc(&c->d_level_iters, sizeof(int32_t) * kMaxLevels));
@@ -1485,6 +1515,8 @@ static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_l
             CK(cudaMemset(c->d_dbg_blocks, 0, bytes));
         }
     }
+    const char *pwm = getenv("ORB_PART_WARP_MAX");
+    if (pwm) c->partWarpMax = atoi(pwm);
     const char *plf = getenv("ORB_PRELEFT");
     if (plf) c->preLeft = atoi(plf) != 0;
     const char *pd = getenv("ORB_PDL");
@@ -1509,6 +1541,8 @@ static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_l
     if (sem) c->selectMr = atoi(sem) != 0;
     const char *mv1 = getenv("ORB_MR_V1");
     if (mv1) c->mrV2 = atoi(mv1) == 0;
+    const char *xcc = getenv("ORB_X_CAND_CAP");
+    if (xcc && atoi(xcc) >= 256 && (uint32_t)atoi(xcc) <= kSelValsCap) c->xCandCap = (uint32_t)atoi(xcc);
     const char *msf = getenv("ORB_MR_SELF");
     if (msf && atoi(msf) != 0 && c->mrV2) {
         // testing aid: the multi-rank protocol of orb_exchange.cuh with this rank as its only peer
@@ -1557,6 +1591,7 @@ int orb_destroy(orb_ctx *c) {
     for (int r = 0; r < orb::kMaxPeers; ++r)
         if (c->peerIpc[r] && c->peerX[r]) cudaIpcCloseMemHandle(c->peerX[r]);
     cudaFree(c->d_xchg);
+    cudaFree(c->d_xscratch);
     for (int r = 0; r < orb::kMaxPeers; ++r)
         if (c->peerIpc[r]) { cudaIpcCloseMemHandle(c->peerCnt[r]); cudaIpcCloseMemHandle(c->peerFlag[r]); }
     cudaFree(c->d_lvl_passes); cudaFree(c->d_lvl_unfound); cudaFree(c->d_cdone); cudaFree(c->d_peer_cnt); cudaFree(c->d_peer_flag);

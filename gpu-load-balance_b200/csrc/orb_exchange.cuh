@@ -297,6 +297,191 @@ __global__ void __launch_bounds__(kThreads) k_xd_compact(const float *__restrict
     }
 }
 
+// ---- warp-per-cell versions for the deepest levels (a few hundred to a couple of thousand particles per cell and
+//      rank).  At that size a cell costs a handful of dependent memory latencies, not bandwidth: the per-cell scalars of
+//      the NEXT cell are fetched while the current one is processed, and everything the current cell needs (its rows,
+//      its particles) is requested at once - the particles land in the warp's shared-memory staging area. ----
+struct CellMeta {
+    uint32_t b, e, total, active;
+    int nleaf, axis;
+    float L, R;
+};
+__device__ __forceinline__ CellMeta cell_meta(const LevelState &lv, uint32_t c, uint32_t nCells) {
+    CellMeta m;
+    m.b = m.e = m.total = m.active = 0u; m.nleaf = 1; m.axis = 0; m.L = m.R = 0.f;
+    if (c < nCells) {
+        m.b = lv.bnd[c]; m.e = lv.bnd[c + 1]; m.total = lv.total[c]; m.active = lv.active[c];
+        m.nleaf = lv.nleaf[c]; m.axis = lv.axis[c]; m.L = lv.mL[c]; m.R = lv.mR[c];
+    }
+    return m;
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+constexpr uint32_t kXdStage = 2048;       // particles of one cell a warp stages (larger cells are read in place)
+
+// HIST, one warp per cell.  dynamic shared memory: kWarps x nb words
+__global__ void __launch_bounds__(kThreads) k_xd_hist_warp(const float *__restrict__ x, const float *__restrict__ y,
+                                                           const float *__restrict__ z, LevelState lv, uint32_t *__restrict__ hist_l,
+                                                           uint32_t nCells, int nb) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    pdl_enter();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *h = reinterpret_cast<uint32_t *>(sel_smem) + (size_t)warp * nb;
+    const float nbm1 = (float)(nb - 1);
+    const uint32_t stride = gridDim.x * kWarps;
+    uint32_t c = blockIdx.x * kWarps + warp;
+    CellMeta cur = cell_meta(lv, c, nCells);
+    while (c < nCells) {
+        const CellMeta nxt = cell_meta(lv, c + stride, nCells);
+        if (cur.active) {       // warp-uniform
+            const float lo = cur.L, scale = sel_scale(lo, cur.R, nb);
+            for (int i = lane; i < nb; i += 32) h[i] = 0u;
+            __syncwarp();
+            grp_for_each<32, 4>(pick_col(cur.axis, x, y, z) + cur.b, cur.e - cur.b, lane, [&](float v) {
+                const float t = fminf(fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f), nbm1);      // == sel_bin(v, lo, scale, nb)
+                atomicAdd(&h[__float2int_rz(t)], 1u);
+            });
+            __syncwarp();
+            for (int i = lane; i < nb; i += 32) hist_l[(size_t)c * nb + i] = h[i];
+            __syncwarp();
+        }
+        c += stride;
+        cur = nxt;
+    }
+}
+
+// RESOLVE + COMPACT, one warp per cell.  dynamic shared memory per warp: rowG[nb] | rowL[nb] | vals[kXdStage]
+__host__ __device__ inline size_t xd_compact_warp_smem(int nb) { return (size_t)kWarps * (2u * (size_t)nb + kXdStage) * 4u; }
+__global__ void __launch_bounds__(kThreads) k_xd_compact_warp(const float *__restrict__ x, const float *__restrict__ y,
+                                                              const float *__restrict__ z, LevelState lv, SelState ss, SelMrState mr,
+                                                              XArena xa, uint32_t nCells, int nb, uint32_t candCap) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    __shared__ uint32_t s_cnt[kWarps], s_base[kWarps], s_end[kWarps];
+    pdl_enter();
+    x_barrier(xa);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *rowG = reinterpret_cast<uint32_t *>(sel_smem) + (size_t)warp * (2u * (size_t)nb + kXdStage);
+    uint32_t *rowL = rowG + nb;
+    float *vals = reinterpret_cast<float *>(rowL + nb);
+    const uint32_t ostride = x_owned_stride(nCells, xa.n);
+    const uint32_t *histG = xa.arena[xa.self] + xa.offHistG;
+    const int per = (nb + 31) / 32;
+    const uint32_t stride = gridDim.x * kWarps;
+    uint32_t c = blockIdx.x * kWarps + warp;
+    CellMeta cur = cell_meta(lv, c, nCells);
+    while (c < nCells) {
+        const CellMeta nxt = cell_meta(lv, c + stride, nCells);
+        const int owner = (int)(c % (uint32_t)xa.n);
+        const uint32_t slot = (uint32_t)xa.self * ostride + c / (uint32_t)xa.n;
+        uint32_t *cntDst = xa.arena[owner] + xa.offRecvCnt + slot;
+        if (!cur.active) {
+            if (lane == 0) { ss.flag[c] = 0u; *cntDst = 0u; mr.loc_base[c] = 0u; }
+        } else {
+            const uint32_t K = cur.e - cur.b;
+            const float *col = pick_col(cur.axis, x, y, z) + cur.b;
+            const bool staged = K + 4u <= kXdStage;
+            // everything this cell needs, requested at once (rows: nb is a multiple of 32 words, 16-byte pieces; the
+            // particles start at any 4-byte address: the staged copy begins `mis` floats into the buffer so that shared
+            // and global addresses agree mod 16, head and tail go in 4-byte pieces)
+            for (int i = lane; i < nb / 4; i += 32) {
+                cp_async16(reinterpret_cast<uint4 *>(rowG) + i, reinterpret_cast<const uint4 *>(histG + (size_t)c * nb) + i);
+                cp_async16(reinterpret_cast<uint4 *>(rowL) + i, reinterpret_cast<const uint4 *>(mr.hist_l + (size_t)c * nb) + i);
+            }
+            const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(col) >> 2) & 3u);
+            float *sv = vals + mis;         // sv[i] <-> col[i]
+            if (staged) {
+                const uint32_t head = mis ? min(4u - mis, K) : 0u, body4 = (K - head) / 4u, tail0 = head + body4 * 4u;
+                for (uint32_t i = lane; i < body4; i += 32u)
+                    cp_async16(reinterpret_cast<float4 *>(sv + head) + i, reinterpret_cast<const float4 *>(col + head) + i);
+                if ((uint32_t)lane < head) cp_async4(sv + lane, col + lane);
+                if (tail0 + (uint32_t)lane < K) cp_async4(sv + tail0 + lane, col + tail0 + lane);
+            }
+            cp_async_commit();
+            if (lane == 0) s_cnt[warp] = 0u;
+            cp_async_wait<0>();
+            __syncwarp();
+            // ---- resolve (same arithmetic on every rank: the row is the global one) ----
+            SelTarget tg;
+            tg.init(cur.total, cur.nleaf);
+            uint32_t sum = 0;
+            for (int j = 0; j < per; ++j) { const int bb = lane * per + j; if (bb < nb) sum += rowG[bb]; }
+            uint32_t total;
+            const uint32_t excl = grp_scan<32>(sum, nullptr, total);
+            int myFirst = nb, myLast = -1;
+            {
+                uint32_t p = excl;
+                for (int j = 0; j < per; ++j) {
+                    const int bb = lane * per + j;
+                    if (bb < nb) {
+                        const uint32_t pn = p + rowG[bb];
+                        if (tg.diff(pn) > -3) myFirst = min(myFirst, bb);
+                        if (tg.diff(p) < 3) myLast = max(myLast, bb);
+                        p = pn;
+                    }
+                }
+            }
+            const int first = __reduce_min_sync(0xffffffffu, myFirst), last = __reduce_max_sync(0xffffffffu, myLast);
+            {
+                uint32_t p = excl;
+                for (int j = 0; j < per; ++j) {
+                    const int bb = lane * per + j;
+                    if (bb < nb) {
+                        if (bb == first) s_base[warp] = p;
+                        p += rowG[bb];
+                        if (bb == last) s_end[warp] = p;
+                    }
+                }
+            }
+            __syncwarp();
+            const bool okBins = first <= last && first < nb && last >= 0;
+            const uint32_t base = okBins ? s_base[warp] : 0u, K2 = okBins ? s_end[warp] - s_base[warp] : 0u;
+            const bool ok = okBins && K2 <= candCap;
+            uint32_t lb = 0;
+            if (ok) for (int i = lane; i < first; i += 32) lb += rowL[i];
+            lb = __reduce_add_sync(0xffffffffu, lb);
+            if (lane == 0) {
+                ss.bfirst[c] = ok ? (uint32_t)first : 1u; ss.blast[c] = ok ? (uint32_t)last : 0u;
+                ss.base[c] = ok ? base : 0u; ss.ncand[c] = ok ? K2 : 0u; ss.flag[c] = ok ? 0u : 1u;
+                mr.loc_base[c] = lb;
+            }
+            if (ok) {
+                const float lo = cur.L, scale = sel_scale(lo, cur.R, nb);
+                float fLo, fHi;
+                sel_bin_bounds((uint32_t)first, (uint32_t)last, nb, fLo, fHi);
+                float *dst = reinterpret_cast<float *>(xa.arena[owner] + xa.offRecv + (size_t)slot * mr.slotWords);
+                const uint32_t lim = mr.slotWords - 1u;
+                // all lanes take part in every round (ballot), out-of-range lanes just keep nothing
+                const uint32_t rounds = (K + 31u) / 32u;
+                uint32_t p0 = 0;
+                for (uint32_t r = 0; r < rounds; ++r) {
+                    const uint32_t i = r * 32u + (uint32_t)lane;
+                    float v = 0.f;
+                    bool keep = false;
+                    if (i < K) {
+                        v = staged ? sv[i] : __ldg(col + i);
+                        const float t = fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f);
+                        keep = t >= fLo && t < fHi;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (keep) {
+                        const uint32_t p = p0 + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                        if (p < lim) dst[p] = v;
+                    }
+                    p0 += (uint32_t)__popc(m);
+                }
+                if (lane == 0) s_cnt[warp] = p0;
+            }
+            __syncwarp();
+            if (lane == 0) *cntDst = ok ? s_cnt[warp] : 0u;
+            __syncwarp();
+        }
+        c += stride;
+        cur = nxt;
+    }
+}
+
 // ---- FINISH by the owner ----
 // result record pushed to every rank (8 words): mL, mR, meta, nleft_g, nloc (of the receiving rank), 0, 0, 0
 constexpr uint32_t kXMetaFound = 1u << 8, kXMetaFlag = 1u << 16;
@@ -309,8 +494,12 @@ __device__ __forceinline__ void x_push_record(const XArena &xa, uint32_t c, int 
 }
 
 // block per owned cell (candidates beyond what a warp stages): the block search of orb_select.cuh
+// (capBig > cap with `scratch`: a cell whose candidates do not fit shared memory - the top levels of a 2^30-particle
+//  build, 131072 particles per bin - is searched in a global scratch array instead: the block search only needs a
+//  pointer it can read a few times, and a few hundred KB stay in L2)
 __global__ void __launch_bounds__(1024) k_xf_finish_block(LevelState lv, SelState ss, SelMrState mr, XArena xa, uint32_t nCells,
-                                                          int nb1, uint32_t cap, int *__restrict__ err) {
+                                                          int nb1, uint32_t cap, int *__restrict__ err, float *__restrict__ scratch,
+                                                          uint32_t capBig) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     float *sbuf = reinterpret_cast<float *>(sel_smem);
     uint32_t *hist2 = reinterpret_cast<uint32_t *>(sbuf + cap + 4);
@@ -338,10 +527,12 @@ __global__ void __launch_bounds__(1024) k_xf_finish_block(LevelState lv, SelStat
         bool over = false;
         for (int r = 0; r < xa.n; ++r) { over |= s_cnt[r] > mr.slotWords - 1u; sum += s_cnt[r]; }
         bool flagged = flg != 0u || over;
-        if (!flagged && (sum != K || K > cap)) {     // cannot happen: all ranks bin with the same function and resolve the same rows
+        const bool big = K > cap;
+        if (!flagged && (sum != K || (big && (!scratch || K > capBig)))) {     // cannot happen: all ranks bin with the same function and resolve the same rows
             if (tid == 0) atomicExch(err, ORB_ERR_STATE);
             flagged = true;
         }
+        float *vals = big ? scratch + (size_t)oi * capBig : sbuf;
         if (!flagged) {
             uint32_t off = 0;
             for (int r = 0; r < xa.n; ++r) {
@@ -351,7 +542,7 @@ __global__ void __launch_bounds__(1024) k_xf_finish_block(LevelState lv, SelStat
                 for (uint32_t i = tid; i < n4; i += nThreads) {
                     const float4 q = __ldcg(s4 + i);
                     const uint32_t k = 4u * i;
-                    float *d = sbuf + off + k;
+                    float *d = vals + off + k;
                     d[0] = q.x;
                     if (k + 1u < n) d[1] = q.y;
                     if (k + 2u < n) d[2] = q.z;
@@ -360,7 +551,7 @@ __global__ void __launch_bounds__(1024) k_xf_finish_block(LevelState lv, SelStat
                 off += n;
             }
             __syncthreads();
-            flagged = !sel_block_search_core(sbuf, K, base, 1, L, sel_scale(L, R, nb1), nb1, (int)bf, (int)bl, hist2, amb, lv, c, sm);
+            flagged = !sel_block_search_core(vals, K, base, 1, L, sel_scale(L, R, nb1), nb1, (int)bf, (int)bl, hist2, amb, lv, c, sm);
             __syncthreads();
         }
         if (!flagged) {
@@ -371,7 +562,7 @@ __global__ void __launch_bounds__(1024) k_xf_finish_block(LevelState lv, SelStat
             for (int r = 0; r < xa.n; ++r) {
                 const uint32_t n = s_cnt[r];
                 uint32_t m = 0;
-                for (uint32_t i = tid; i < n; i += nThreads) m += (sbuf[off + i] < cutf) ? 1u : 0u;
+                for (uint32_t i = tid; i < n; i += nThreads) m += (vals[off + i] < cutf) ? 1u : 0u;
                 m = __reduce_add_sync(0xffffffffu, m);
                 if (lane == 0 && m) atomicAdd(&s_nl[r], m);
                 off += n;
@@ -386,7 +577,7 @@ __global__ void __launch_bounds__(1024) k_xf_finish_block(LevelState lv, SelStat
 }
 
 // warp per owned cell (deep levels: a few hundred candidates): the replay counts over the staged candidates directly
-constexpr uint32_t kXWarpCap = 1024;     // candidates one warp stages
+constexpr uint32_t kXWarpCap = 2048;     // candidates one warp stages
 __global__ void __launch_bounds__(kThreads) k_xf_finish_warp(LevelState lv, SelState ss, SelMrState mr, XArena xa, uint32_t nCells,
                                                              int nb1, uint32_t cap /* <= kXWarpCap */, int *__restrict__ err) {
     extern __shared__ __align__(16) unsigned char sel_smem[];

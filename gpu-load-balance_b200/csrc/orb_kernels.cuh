@@ -1966,6 +1966,64 @@ __global__ void __launch_bounds__(kThreads, 3) k_partition_cells(const float *__
     (void)nLocal;
 }
 
+// Regime C: cells of at most a couple of thousand particles (the deepest levels of a 2^20-leaf tree: 512 particles
+// per cell and rank).  One WARP per cell, no shared memory, no barrier: lane i takes particle b + 32 k + i, the split
+// position of each particle is a ballot prefix, lefts and rights go out as two contiguous runs.  A block-per-cell tile
+// (regime B) would read a whole 2048-particle tile for a 512-particle cell.
+__global__ void __launch_bounds__(kThreads) k_partition_warp(const float *__restrict__ x, const float *__restrict__ y,
+                                                              const float *__restrict__ z, float *__restrict__ x2,
+                                                              float *__restrict__ y2, float *__restrict__ z2, LevelState lv,
+                                                              const float *__restrict__ final_cut, uint32_t nCells,
+                                                              const uint32_t *__restrict__ gate) {
+    if (gate && *((volatile const uint32_t *)gate) != 0u) return;     // see k_split
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t warpId = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+    // the next cell's scalars are fetched while the current cell streams (a cell is a few memory latencies, not bandwidth)
+    uint32_t c = warpId;
+    uint32_t nb_ = 0, ne_ = 0, nnl_ = 0;
+    float ncut_ = 0.f;
+    int nax_ = 0;
+    if (c < nCells) { nb_ = lv.bnd[c]; ne_ = lv.bnd[c + 1]; nnl_ = lv.nleft_l[c]; ncut_ = final_cut[c]; nax_ = lv.axis[c]; }
+    for (; c < nCells; c += nWarps) {
+        const uint32_t b = nb_, e = ne_, nl = nnl_;
+        const float cutv = ncut_;
+        const int ax = nax_;
+        const uint32_t cn = c + nWarps;
+        if (cn < nCells) { nb_ = lv.bnd[cn]; ne_ = lv.bnd[cn + 1]; nnl_ = lv.nleft_l[cn]; ncut_ = final_cut[cn]; nax_ = lv.axis[cn]; }
+        if (e <= b) continue;
+        const float *col = pick_col(ax, x, y, z);
+        uint32_t posL = b, posR = b + nl;
+        constexpr int U = 4;        // iterations in flight
+        for (uint32_t i0 = b; i0 < e; i0 += 32u * U) {
+            float vx[U], vy[U], vz[U], vc[U];
+            bool in[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t i = i0 + (uint32_t)u * 32u + (uint32_t)lane;
+                in[u] = i < e;
+                vx[u] = in[u] ? __ldg(x + i) : 0.f;
+                vy[u] = in[u] ? __ldg(y + i) : 0.f;
+                vz[u] = in[u] ? __ldg(z + i) : 0.f;
+                vc[u] = in[u] ? __ldg(col + i) : 0.f;      // (one of the three lines just requested)
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool left = in[u] && vc[u] < cutv;
+                const unsigned mIn = __ballot_sync(0xffffffffu, in[u]);
+                const unsigned mL = __ballot_sync(0xffffffffu, left);
+                const unsigned mR = mIn & ~mL;
+                if (in[u]) {
+                    const uint32_t d = left ? posL + (uint32_t)__popc(mL & lt) : posR + (uint32_t)__popc(mR & lt);
+                    x2[d] = vx[u]; y2[d] = vy[u]; z2[d] = vz[u];
+                }
+                posL += (uint32_t)__popc(mL);
+                posR += (uint32_t)__popc(mR);
+            }
+        }
+    }
+}
+
 // =====================================================================================
 // Hoare-exact partition: reproduces partition.cpp:30-60 bit for bit, including WHICH particles
 // with coord == cut land on which side and the resulting particle ORDER (later tie decisions depend on it).

@@ -487,3 +487,22 @@ def test_multi_rank_protocol_against_itself(orb, oracle, n, d, gen, monkeypatch)
         assert st.search_fallback_cells == 0
     elif gen == "ties":
         assert st.search_fallback_cells > 0
+
+
+def test_multi_rank_owner_search_in_global_scratch(orb, oracle, monkeypatch):
+    """Cells with more candidates than an owner block stages in shared memory (the root of a 2^30-particle build: 131072
+    particles per bin) are searched in global scratch; here the shared-memory capacity is turned down to force that path."""
+    monkeypatch.setenv("ORB_MR_SELF", "1")
+    monkeypatch.setenv("ORB_X_CAND_CAP", "1024")
+    n, d = 1 << 22, 1 << 5
+    x, y, z = orb.generate_uniform(n)
+    ref = oracle.build(x, y, z, d, ties=oracle.TIES_CANONICAL)
+    with orb.Orb(n, d) as ctx:
+        ctx.upload(x, y, z)
+        heap, st = ctx.build()
+        gx, gy, gz = ctx.download()
+        rng = ctx.ranges()
+    assert st.search_fallback_cells == 0
+    assert heap.tobytes() == ref["heap"].tobytes() and np.array_equal(rng, ref["ranges"][0])
+    for a, b in ((gx, ref["x"]), (gy, ref["y"]), (gz, ref["z"])):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
