@@ -159,6 +159,8 @@ struct orb_ctx {
     bool pdl = true;               // programmatic dependent launch between the small kernels of a level
     // partition without its phase-1 read (PreLeft, orb_kernels.cuh): the search's last pass and the partition share one
     // chunk per block; ORB_PRELEFT=0 disables
+    int partBulk = 0;              // ORB_PART_BULK=1: the cooperative partition loads its tiles with cp.async.bulk + mbarrier instead of
+                                   // per-thread cp.async (measured 2.8 % slower at C3 with two tiles of shared memory: profiles/r02h_partition_bulk_ab.txt)
     int partWarpMax = 2048;        // ORB_PART_WARP_MAX: average local cell size up to which the partition runs one warp per cell
     bool preLeft = true;
     orb::PreLeft *d_pre = nullptr; // [64 * nSM]
@@ -783,6 +785,14 @@ SelMrPlan sel_plan_mr(const orb_ctx *c, uint32_t nCells, int M, int forcedNb = 0
         int nb = 32;
         while (nb < orb::kSelBins2 && gavg / (uint64_t)nb > perBin) nb <<= 1;
         while (nb > 32 && (size_t)nCells * (size_t)nb > histFit) nb >>= 1;
+        // ... and a rank's slot (a few bins' worth of its own particles) must fit its share of the slot area: more bins
+        // where it would not (a slot that overflows sends its cell to the iterative search)
+        while (nb < orb::kSelBins2 && (size_t)nCells * (size_t)(2 * nb) <= histFit) {
+            uint64_t w = 4 * (lavg / (uint64_t)nb) + 32 + 1, sw2 = 32;
+            while (sw2 < w) sw2 <<= 1;
+            if (sw2 * nCells <= slotTotal) break;
+            nb <<= 1;
+        }
         if (nb > 512) p.regime = 1;
         p.nb1 = nb;
         p.rep = 1;
@@ -1194,7 +1204,7 @@ int launch_partition(orb_ctx *c, uint32_t nCells, uint32_t *ticket, const uint32
         void *args[] = {(void *)&x, (void *)&y, (void *)&z, (void *)&x2, (void *)&y2, (void *)&z2, (void *)&c->lv,
                         (void *)&c->d_final_cut, (void *)&c->d_tile_first, (void *)&nC, (void *)&nLocal32, (void *)&nT,
                         (void *)&c->d_blk_left, (void *)&c->d_blk_restart, (void *)&gate, (void *)&nh,
-                        (void *)&pre, (void *)&preTag, (void *)&tpb, (void *)&preList, (void *)&listStride};
+                        (void *)&pre, (void *)&preTag, (void *)&tpb, (void *)&preList, (void *)&listStride, (void *)&c->partBulk};
         CK(cudaLaunchCooperativeKernel((const void *)k_partition_coop, dim3(grid), dim3(kThreads), args, smem, c->stream));
     }
     if (c->profile) CK(cudaEventRecord(e1, c->stream));
@@ -1265,7 +1275,7 @@ int alloc_arena(orb_ctx *c, bool multi) {
     if (multi) {
         c->selHistWords = (size_t)c->nLocalMax / 8 + 2 * (size_t)orb::kSelBinsMax;
         c->selHistWords = (c->selHistWords + 63) & ~(size_t)63;
-        c->slotTotal = std::max<size_t>(kSelSlotWordsTotal, 64 * L);
+        c->slotTotal = std::max<size_t>(std::max<size_t>(kSelSlotWordsTotal, 64 * L), (((size_t)c->nLocalMax / 8) + 63) & ~(size_t)63);
     }
     c->xOffSlots = (uint32_t)off; off += c->slotTotal;
     if (multi) {
@@ -1515,6 +1525,8 @@ static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_l
             CK(cudaMemset(c->d_dbg_blocks, 0, bytes));
         }
     }
+    const char *pbk = getenv("ORB_PART_BULK");
+    if (pbk) c->partBulk = atoi(pbk) != 0 ? 1 : 0;
     const char *pwm = getenv("ORB_PART_WARP_MAX");
     if (pwm) c->partWarpMax = atoi(pwm);
     const char *plf = getenv("ORB_PRELEFT");
@@ -1640,7 +1652,7 @@ int orb_plan_level(uint64_t n_local, uint64_t n_global, uint64_t n_local_min, in
     c->d_slots_g = reinterpret_cast<float *>(uintptr_t(16));     // "allocated" (sel_plan_mr only tests the pointer)
     c->nLocalMax = c->nLocalMin;      // (the plan never reads it: buffers are sized from it, decisions use the minimum)
     c->peerEnabled = n_ranks > 1;     // plan of the peer-memory protocol (orb_exchange.cuh)
-    c->slotTotal = std::max<size_t>(kSelSlotWordsTotal, 64 * (size_t)c->maxLevelCells);
+    c->slotTotal = std::max<size_t>(std::max<size_t>(kSelSlotWordsTotal, 64 * (size_t)c->maxLevelCells), (((size_t)n_local_min / 8) + 63) & ~(size_t)63);
     const char *mv1 = getenv("ORB_MR_V1");
     if (mv1) c->mrV2 = atoi(mv1) == 0;
     memset(out, 0, sizeof(*out));

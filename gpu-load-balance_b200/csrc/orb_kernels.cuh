@@ -1464,6 +1464,7 @@ struct PartSmem {
     uint32_t lbsum[kWarps];
     float chLo[2], chScale[2];        // NextHist: bin function of the running cell's left / right child
     int chAx[2];
+    alignas(8) unsigned long long mbar[2];   // bulk-copy tile loads: one transaction barrier per buffer
 };
 
 // NextHist helpers (block-uniform calls).  The block histogram of the running cell's two children lives in sm.sd.
@@ -1502,6 +1503,45 @@ __device__ __forceinline__ void part_prefetch(PartSmem &sm, int bsel, const floa
         cp_async16(&sm.raw[bsel][0][o], x + T + o);
         cp_async16(&sm.raw[bsel][1][o], y + T + o);
         cp_async16(&sm.raw[bsel][2][o], z + T + o);
+    }
+}
+
+// ---- the same tile load as ONE bulk asynchronous copy per column (cp.async.bulk, the TMA engine's linear mode):
+//      a single thread arms the buffer's transaction barrier with the tile's byte count and issues three 8 KB
+//      copies; every thread then waits on the barrier's phase.  No thread spends issue slots on LDGSTS. ----
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem, const void *gmem, unsigned bytes, unsigned long long *bar) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem), ba = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(sa), "l"(gmem), "r"(bytes), "r"(ba) : "memory");
+}
+__device__ __forceinline__ void part_prefetch_bulk(PartSmem &sm, int bsel, const float *__restrict__ x, const float *__restrict__ y,
+                                                   const float *__restrict__ z, uint32_t T) {
+    if (threadIdx.x == 0) {
+        constexpr unsigned bytes = kPartTile * sizeof(float);
+        mbar_expect_tx(&sm.mbar[bsel], 3u * bytes);
+        bulk_load(&sm.raw[bsel][0][0], x + T, bytes, &sm.mbar[bsel]);
+        bulk_load(&sm.raw[bsel][1][0], y + T, bytes, &sm.mbar[bsel]);
+        bulk_load(&sm.raw[bsel][2][0], z + T, bytes, &sm.mbar[bsel]);
     }
 }
 
@@ -1770,10 +1810,16 @@ __global__ void __launch_bounds__(kThreads, 3) k_partition_coop(const float *__r
                                                                uint32_t nLocal, uint32_t nTiles, uint32_t *blkLeft,
                                                                uint32_t *blkRestart, const uint32_t *__restrict__ gate, NextHist nh,
                                                                const PreLeft *__restrict__ pre, uint32_t preTag, uint32_t tilesPerBlockIn,
-                                                               const float *__restrict__ preList, uint32_t preListStride) {
+                                                               const float *__restrict__ preList, uint32_t preListStride,
+                                                               int bulk /* tile loads by cp.async.bulk + mbarrier instead of per-thread cp.async */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PartSmem &sm = *reinterpret_cast<PartSmem *>(smem_raw);
     if (gate && *((volatile const uint32_t *)gate) != 0u) return;     // see k_split; uniform over the grid
+    unsigned mphase[2] = {0u, 0u};
+    if (bulk) {
+        if (threadIdx.x == 0) { mbar_init(&sm.mbar[0], 1u); mbar_init(&sm.mbar[1], 1u); mbar_fence_init(); }
+        __syncthreads();
+    }
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // (tilesPerBlockIn: the chunking the search's last pass used, so that `pre` describes this block's chunk)
@@ -1782,7 +1828,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_partition_coop(const float *__r
     const uint32_t chunkStart = tb0 * (uint32_t)kPartTile, chunkEnd = min(tb1 * (uint32_t)kPartTile, nLocal);
 
     // start the first tile's copy right away; it lands while phase 1 runs
-    if (tb0 < tb1) part_prefetch(sm, 0, x, y, z, chunkStart);
+    if (tb0 < tb1) {
+        if (bulk) part_prefetch_bulk(sm, 0, x, y, z, chunkStart);
+        else part_prefetch(sm, 0, x, y, z, chunkStart);
+    }
     cp_async_commit();
 
     // ---------------- phase 1: left particles of the trailing segment ----------------
@@ -1878,14 +1927,21 @@ __global__ void __launch_bounds__(kThreads, 3) k_partition_coop(const float *__r
     for (uint32_t t = tb0; t < tb1; ++t, ++it) {
         const int bsel = it & 1;
         const uint32_t T = t * (uint32_t)kPartTile, tEnd = min(T + (uint32_t)kPartTile, nLocal);
-        if (t + 1 < tb1) {
-            part_prefetch(sm, bsel ^ 1, x, y, z, T + (uint32_t)kPartTile);
-            cp_async_commit();
-            cp_async_wait<1>();
+        if (bulk) {
+            // (the buffer being refilled was last read before the barrier that ended the previous iteration)
+            if (t + 1 < tb1) part_prefetch_bulk(sm, bsel ^ 1, x, y, z, T + (uint32_t)kPartTile);
+            mbar_wait(&sm.mbar[bsel], mphase[bsel]);
+            mphase[bsel] ^= 1u;
         } else {
-            cp_async_wait<0>();
+            if (t + 1 < tb1) {
+                part_prefetch(sm, bsel ^ 1, x, y, z, T + (uint32_t)kPartTile);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();   // tile t is in sm.raw[bsel]
         }
-        __syncthreads();   // tile t is in sm.raw[bsel]
         if (ce >= tEnd) {
             // ---- tile inside the running cell ----
             const uint32_t baseL = cb + carry;

@@ -506,3 +506,20 @@ def test_multi_rank_owner_search_in_global_scratch(orb, oracle, monkeypatch):
     assert heap.tobytes() == ref["heap"].tobytes() and np.array_equal(rng, ref["ranges"][0])
     for a, b in ((gx, ref["x"]), (gy, ref["y"]), (gz, ref["z"])):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,d", [(1 << 21, 1 << 6), (100_003, 32)])
+def test_partition_bulk_copy_path(orb, oracle, n, d, monkeypatch):
+    """ORB_PART_BULK=1: the cooperative partition loads its tiles with cp.async.bulk + mbarrier (the default is per-thread
+    cp.async, which measured faster - profiles/r02h_partition_bulk_ab.txt); same bits either way."""
+    monkeypatch.setenv("ORB_PART_BULK", "1")
+    x, y, z = orb.generate_uniform(n)
+    ref = oracle.build(x, y, z, d, ties=oracle.TIES_CANONICAL)
+    with orb.Orb(n, d) as ctx:
+        ctx.upload(x, y, z)
+        heap, st = ctx.build()
+        gx, gy, gz = ctx.download()
+        rng = ctx.ranges()
+    assert heap.tobytes() == ref["heap"].tobytes() and np.array_equal(rng, ref["ranges"][0])
+    for a, b in ((gx, ref["x"]), (gy, ref["y"]), (gz, ref["z"])):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))

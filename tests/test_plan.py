@@ -20,7 +20,7 @@ def test_multi_rank_plan_depends_on_shared_numbers_only(orb, ranks, x_min):
     shards = [n_min, n_min + n_min // 3, 2 * n_min][:ranks] + [n_min + 7] * max(0, ranks - 3)
     n_global = sum(shards)
     for y in (4, 12, 16, 20):
-        slot_total = max(1 << 20, 64 << y)
+        slot_total = max(1 << 20, 64 << y, ((n_min // 8) + 63) & ~63)
         for level in range(1, y + 1):
             n_cells = 1 << (level - 1)
             plans = [fields(orb.plan_level(n, n_cells, 1 << y, n_ranks=ranks, n_global=n_global, n_local_min=n_min)) for n in shards]
