@@ -34,6 +34,11 @@ def known_answer_summary(out, rank, heap, st, rng, before, after):
     props["leaf_particles_inside_leaf_boxes"] = inside
     props["multiset_preserved"] = oracle_py.range_hashes(*before, 0, n)[0] == oracle_py.range_hashes(*after, 0, n)[0]
     rec = {"rank": rank, "props": props}
+    import digests
+    rec["digests"] = digests.rank_digests(rng, L, *after)
+    rec["heapDigest"] = digests.heap_hash(heap)
+    rec["iters_all"] = list(st.iters[:L])
+    rec["not_found_all"] = list(st.not_found[:L])
     if rank == 0:
         h = FNV_OFFSET
         for v in e.tolist():

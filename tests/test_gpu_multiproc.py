@@ -88,7 +88,7 @@ KNOWN = {
 }
 
 
-@pytest.mark.parametrize("x,y,R", [(24, 16, 2), (30, 20, 8)])
+@pytest.mark.parametrize("x,y,R", [(24, 16, 2), (27, 16, 2), (30, 20, 8)])
 def test_full_size_known_answers(tmp_path, x, y, R):
     """Full-size runs (C5: 2^30 -> 2^20 on 8 GPUs), one process per GPU: digests equal the CPU oracle's, and on every rank the leaf ranges tile
     the slice, every particle lies inside its leaf's box and the particle multiset is preserved."""
@@ -98,13 +98,21 @@ def test_full_size_known_answers(tmp_path, x, y, R):
     if torch.cuda.device_count() < R:
         pytest.skip(f"needs {R} GPUs")
     _torchrun(R, 29950 + os.getpid() % 40, tmp_path, x, y, 1, "known")
-    want = KNOWN[(x, y, R)]
+    want = KNOWN.get((x, y, R))
     for rank in range(R):
         rec = json.loads((tmp_path / f"known{rank}.json").read_text())
         assert all(rec["props"].values()), rec
-        if rank == 0:
+        if rank == 0 and want:
             assert rec["iters"] == want["iters"]
             assert rec["rangeHash"] == want["rangeHash"]
             if want["heapHash"]:
                 assert rec["heapHash"] == want["heapHash"]
             print(f"{x}/{y}/{R} build ms", rec["ms_total"], "passes", rec["passes"], "not_found", rec["not_found"])
+        # every rank against the digest table of the CPU oracle (tests/golden/known_answers.json), where the workload is in it
+        import digests
+        key = {(27, 16): "c3", (30, 20): "c5"}.get((x, y))
+        known = digests.load_known().get(f"{key}_r{R}") if key else None
+        if known:
+            assert rec["iters_all"] == known["iters"] and rec["not_found_all"] == known["not_found"] and rec["heapDigest"] == known["heapHash"]
+            for k in ("rangeHash", "leafSetHash", "orderHash"):
+                assert rec["digests"][k] == known["ranks"][rank][k], (rank, k)

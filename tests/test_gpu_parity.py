@@ -380,6 +380,18 @@ def test_full_size_properties_c2(orb, oracle):
     leaves = heap[(1 << st.n_levels) - 1:(1 << (st.n_levels + 1)) - 1]
     sizes = rng[leaves["id"], 1] - rng[leaves["id"], 0]
     assert sizes.sum() == n and sizes.min() >= 8188 - 8 and sizes.max() <= 8196 + 8
+    _check_known_answers("c2_r1", heap, st, rng, gx, gy, gz)
+
+
+def _check_known_answers(key, heap, st, rng, gx, gy, gz):
+    """bit-exact digests of the CPU oracle's build of the same workload (tests/golden/known_answers.json): iterations,
+    capped cells, the whole cell heap, leaf ranges, per-leaf particle sets and the particle order"""
+    import digests
+
+    rec = digests.load_known()[key]
+    L = st.n_levels
+    res = digests.compare(rec, 0, iters=st.iters[:L], not_found=st.not_found[:L], heap=heap, ranges=rng, n_levels=L, x=gx, y=gy, z=gz)
+    assert res["ok"], (key, res["mismatch"])
 
 
 def _check_build_properties(orb, oracle, x, y, z, d, heap, rng, gx, gy, gz, n_levels, sample=48):
@@ -424,6 +436,7 @@ def test_full_size_properties_c3(orb, oracle):
         h = ((h ^ int(rng[i][1])) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
     assert h == 0xD4F00F38C84CA6F5
     _check_build_properties(orb, oracle, x, y, z, d, heap, rng, gx, gy, gz, st.n_levels)
+    _check_known_answers("c3_r1", heap, st, rng, gx, gy, gz)
 
 
 @pytest.mark.parametrize("kind", ["gaussian", "plummer"])
@@ -441,6 +454,8 @@ def test_full_size_properties_c4_clustered(orb, oracle, kind):
     # the reference's |difference| < 3 rule balances every split to within a few particles unless a cell hit the cap
     if sum(st.not_found[:13]) == 0:
         assert sizes.max() - sizes.min() <= 64
+    # ... and bit for bit what the CPU oracle builds from the same 2^26 clustered particles
+    _check_known_answers("c4g_r1" if kind == "gaussian" else "c4p_r1", heap, st, rng, gx, gy, gz)
 
 
 def tie_columns(n, seed=17):
