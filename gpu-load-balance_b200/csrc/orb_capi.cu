@@ -80,6 +80,8 @@ struct NcclApi {
     } while (0)
 
 constexpr int kMaxLevels = 40;
+constexpr uint32_t kSelCellCapMax = 40960;   // candidates k_sel_percell keeps in shared memory at most (176 KB with its histogram)
+constexpr uint32_t kVisitRecs = 4096;     // COMPACT blocks that may leave visit records (>= resident blocks of any supported device)
 constexpr uint32_t kSelValsCap = 49152;   // values one block of the selection search stages in shared memory (192 KB)
 constexpr uint32_t kSelMrMaxCells = 2048; // several ranks: levels up to this many cells use the selection search
 constexpr size_t kSelSlotWordsTotal = (size_t)1 << 20;   // candidate slots of one rank and level (4 MB; v2 arena: at least this)
@@ -156,6 +158,22 @@ struct orb_ctx {
                                    // candidates and the finish kernel searches an over-full list in global memory
     int selBinAvg = 8192;          // ORB_SELECT_BIN_AVG: HIST bins per cell are doubled (512..8192) until a bin holds at most this many particles on average
     int selT512MinAvg = 32768;     // ORB_SELECT_T512_MIN: cells of at least this many particles get 512-thread blocks
+    // Sampled rows (single rank, orb_select.cuh SelSampleEst): HIST bins every sampleS-th tile (piece) only, RESOLVE widens the
+    // candidate bins by sampleZ standard deviations, the gathering pass proves the bracket with exact counts.
+    int sampleS = 8;               // ORB_SAMPLE_STRIDE (1: exact rows everywhere)
+    float sampleZ = 5.f;           // ORB_SAMPLE_Z
+    // Where it pays (measured, profiles/r02k_*): the HIST pass must be bandwidth-bound for a sample to save anything - from
+    // 2^25 particles per GPU, like the partition-built rows it replaces - and the candidates of a cell must not swamp the
+    // one block that finishes it: streaming cells of at most 2^25 particles (the margin of a 2^27-particle cell is
+    // 160 000 candidates), block-searched cells of at least 2^16 (kSelSampleMinCell).
+    uint64_t sampleMinLocal = 1ull << 25;   // ORB_SAMPLE_MIN_LOCAL
+    uint64_t sampleMaxAvg = 1ull << 25;     // ORB_SAMPLE_MAX_AVG
+    int chunkOcc = 2;              // ORB_CHUNK_OCC: blocks per SM of the chunking the search's last pass and the cooperative partition share
+                                   // (measured: the partition streams 10 % faster with 2 x 148 chunks than with 3 x 148)
+    bool selLowOcc = false;        // ORB_SELECT_LOW_OCC=1: k_sel_percell with 64 registers per thread (4 x 256 / 2 x 512 threads per SM, no spills)
+    bool levelSampled = false;     // the level being searched uses sampled rows
+    bool sampleOff = false;        // this build: a level's brackets failed (particle order correlates with position) - exact rows from there on
+    orb::SelVisitRec *d_visits = nullptr;   // [kVisitRecs] COMPACT with private candidate regions: one record per block
     bool pdl = true;               // programmatic dependent launch between the small kernels of a level
     // partition without its phase-1 read (PreLeft, orb_kernels.cuh): the search's last pass and the partition share one
     // chunk per block; ORB_PRELEFT=0 disables
@@ -171,7 +189,7 @@ struct orb_ctx {
     orb::SelState sel{};
     size_t selHistWords = 0;
     uint32_t *d_sel_nflag = nullptr;   // [kMaxLevels] cells left to the iterative path per level
-    int occSelStream[2] = {1, 1};
+    int occSelStream[3] = {1, 1, 1};   // HIST, COMPACT, COMPACT without a row buffer (cells resolved by k_sel_resolve)
     bool profile = false;
     struct LabelledEvent { const char *label; int level; cudaEvent_t e0, e1; };
     std::vector<LabelledEvent> evAux;      // profile mode: per-kernel times of the selection search
@@ -326,6 +344,11 @@ orb::XArena no_arena() {
     return xa;
 }
 
+orb::SelPriv no_priv() {
+    orb::SelPriv sp;
+    memset(&sp, 0, sizeof(sp));
+    return sp;
+}
 orb::FuseCtl no_fuse() {
     orb::FuseCtl fc;
     memset(&fc, 0, sizeof(fc));
@@ -584,7 +607,19 @@ struct SelPlan {
     int nb1, rep;
     size_t histWords;     // nCells * nb1 (cleared by k_tile_map during level preparation)
     uint32_t candCap;
+    int sampleS;          // > 1: rows from a sample (streaming: private candidate regions + visit records as well)
 };
+// single rank, default trial depth: the search may work from sampled rows
+// (not with ORB_PREFUSE=1, which asks for the partition-built rows)
+inline bool sampling_on(const orb_ctx *c) {
+    return c->sampleS > 1 && !c->sampleOff && c->nRanks == 1 && !c->mrSelf && c->d_visits != nullptr && c->prefuseHist != 1 &&
+           c->nLocal >= c->sampleMinLocal;
+}
+// candidates a cell of `avg` particles is expected to have with sampled rows of nb bins: the z-sigma margin of the
+// sample's rank estimate on either side plus the two bins that hold the bracket's ends
+inline uint64_t sampled_cand_estimate(const orb_ctx *c, uint64_t avg, int nb) {
+    return (uint64_t)(c->sampleZ * std::sqrt((double)c->sampleS * (double)avg)) + 2 * (avg / (uint64_t)nb) + 64;
+}
 SelPlan sel_plan(const orb_ctx *c, uint32_t nCells, int forcedNb = 0 /* rows already built by the partition with this many bins */) {
     SelPlan p{};
     const uint64_t avg = c->nLocal / nCells;
@@ -600,10 +635,25 @@ SelPlan sel_plan(const orb_ctx *c, uint32_t nCells, int forcedNb = 0 /* rows alr
     p.nb1 = orb::kSelBinsMin;
     while (p.nb1 < orb::kSelBinsMax && avg / (uint64_t)p.nb1 > (uint64_t)c->selBinAvg) p.nb1 <<= 1;
     if (forcedNb) p.nb1 = forcedNb;
+    p.sampleS = (sampling_on(c) && !forcedNb && (p.cellsInSmem || avg <= c->sampleMaxAvg)) ? c->sampleS : 1;
+    if (p.sampleS > 1 && !p.cellsInSmem) {
+        // sampled rows: the margin dominates the candidates, finer bins cost nothing (few atomics) - bins of <= 1024 particles
+        while (p.nb1 < orb::kSelBinsMax && avg / (uint64_t)p.nb1 > 1024) p.nb1 <<= 1;
+        if ((size_t)nCells * (size_t)p.nb1 > c->selHistWords) p.sampleS = 1;
+    }
     p.rep = p.nb1 <= 512 ? 4 : (p.nb1 <= 1024 ? 2 : 1);
     p.histWords = (p.cellsInSmem && !forcedNb) ? 0 : (size_t)nCells * (size_t)p.nb1;
     // candidates one block will stage per cell: a few bins' worth; cells beyond it go to the iterative search
     p.candCap = (uint32_t)std::min<uint64_t>(kSelValsCap, 4 * (avg / (uint64_t)p.nb1) + 4096);
+    if (p.sampleS > 1) {
+        if (p.cellsInSmem) {
+            const uint64_t want = (sampled_cand_estimate(c, avg, avg > 4096 ? orb::kSelBins2 : 256) * 5 / 4 + 1023) & ~(uint64_t)1023;
+            p.cellCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(p.cellCap, want), kSelCellCapMax);
+        } else {
+            // (more than this is searched in global memory by k_sel_finish, not flagged)
+            p.candCap = (uint32_t)std::min<uint64_t>(kSelValsCap, (sampled_cand_estimate(c, avg, p.nb1) * 5 / 4 + 4095) & ~(uint64_t)1023);
+        }
+    }
     return p;
 }
 
@@ -617,7 +667,10 @@ inline bool partition_is_coop(const orb_ctx *c, uint32_t nCells) {
 uint32_t level_chunk_tiles(const orb_ctx *c, uint32_t nCells) {
     if (!c->preLeft || c->tieMode == 1 || !c->nLocal || !partition_is_coop(c, nCells)) return 0u;
     const uint32_t nTiles = ceil_div(c->nLocal, orb::kCountTile);
-    const uint32_t G = (uint32_t)c->nSM * (uint32_t)std::max(1, std::min(std::min(c->occPartStream, c->occSelStream[1]), 3));
+    // (a sampled level's COMPACT carries no row buffer: k_sel_resolve has resolved the cells)
+    const SelPlan pl = sel_plan(c, nCells);
+    const int occCompact = (pl.sampleS > 1 && !pl.cellsInSmem) ? c->occSelStream[2] : c->occSelStream[1];
+    const uint32_t G = (uint32_t)c->nSM * (uint32_t)std::max(1, std::min(std::min(c->occPartStream, occCompact), c->chunkOcc));
     return std::max<uint32_t>(1u, ceil_div(nTiles, G));
 }
 
@@ -643,17 +696,26 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
     const uint32_t preTag = ++c->preTagSeq;
     // block size of the per-cell search kernels: big blocks when shared memory allows one block per SM anyway
     auto search_threads = [](size_t smem) { return smem > 112 * 1024 ? 1024 : (smem > 56 * 1024 ? 512 : 256); };
+    c->levelSampled = pl.sampleS > 1;
     if (pl.cellsInSmem) {
         // ---- many cells: one block runs the whole search of a cell ----
         const size_t smem = sel_percell_smem_bytes(pl.cellCap);
         int occ = 1;
-        auto kern = pl.variant == 2 ? k_sel_percell<1024, 1, 8> : (pl.variant == 1 ? k_sel_percell<512, 2, 8>
-                    : (pl.threads == 512 ? k_sel_percell<512, 3> : k_sel_percell<256, 6>));
+        // (the sampled first attempt is a separate instantiation: cells below kSelSampleMinCell and builds without sampling
+        //  run the plain one)
+        const int percellS = (c->nLocal / nCells >= (uint64_t)kSelSampleMinCell) ? pl.sampleS : 1;
+        auto kern = percellS > 1
+                        ? (pl.variant == 2 ? k_sel_percell<1024, 1, 8, true> : (pl.variant == 1 ? k_sel_percell<512, 2, 8, true>
+                           : (pl.threads == 512 ? k_sel_percell<512, 3, 4, true> : k_sel_percell<256, 6, 4, true>)))
+                        : (pl.variant == 2 ? k_sel_percell<1024, 1, 8> : (pl.variant == 1 ? k_sel_percell<512, 2, 8>
+                           : (pl.threads == 512 ? (c->selLowOcc ? k_sel_percell<512, 2> : k_sel_percell<512, 3>)
+                                                : (c->selLowOcc ? k_sel_percell<256, 4> : k_sel_percell<256, 6>))));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, pl.threads, smem));
         const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
         if ((rc = count_event_begin(c))) return rc;
         CK(launch_pdl(c, kern, dim3(grid), dim3(pl.threads), smem, x, y, z, c->lv, ss, sc, nCells, pl.cellCap, preNb, dn, pre, preTag,
-                      c->chunkTiles * (uint32_t)kCountTile, (uint32_t)c->nLocal));
+                      c->chunkTiles * (uint32_t)kCountTile, (uint32_t)c->nLocal,
+                      percellS, c->sampleZ));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     } else {
@@ -666,40 +728,67 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
         const uint32_t nTiles = ceil_div(c->nLocal, kCountTile);
         const size_t ringBytes = (size_t)kCountStages * kCountTile * sizeof(float);
         const uint32_t nL = (uint32_t)c->nLocal;
+        // sampled rows: COMPACT appends to block-private regions and leaves visit records, FINISH gathers (orb_select.cuh SelPriv)
+        SelPriv sp;
+        memset(&sp, 0, sizeof(sp));
+        uint32_t compactTiles = c->chunkTiles;      // count tiles per COMPACT block
+        if (pl.sampleS > 1) {
+            if (!compactTiles) compactTiles = std::max<uint32_t>(1u, ceil_div(nTiles, (uint32_t)c->nSM * (uint32_t)std::max(1, std::min(c->occSelStream[2], 3))));
+            if (ceil_div(nTiles, compactTiles) <= kVisitRecs) {
+                sp.sampleS = pl.sampleS;
+                sp.z = c->sampleZ;
+                sp.visits = c->d_visits;
+                sp.chunk = compactTiles * (uint32_t)kCountTile;
+                sp.useBounds = 1;
+            }
+        }
+        c->levelSampled = sp.sampleS > 1;
         if (!preNb) {      // (preNb: the rows were built by the previous level's partition)
             const size_t smem = ringBytes + (size_t)nb1 * rep * 4;
             int occ = 1;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelHist>, kThreads, smem));
-            const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 4));
+            const uint32_t nVisit = sp.sampleS > 1 ? ceil_div(nTiles, (uint32_t)sp.sampleS) : nTiles;      // tiles the pass reads
+            const uint32_t grid = std::min<uint32_t>(nVisit, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 4));
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                          nCells, nL, nTiles, nb1, rep, candCap, dbgBase, (float *)nullptr, 0u, 0, no_arena(), (PreLeft *)nullptr, 0u, 0u));
+                          nCells, nL, nTiles, nb1, rep, candCap, dbgBase, (float *)nullptr, 0u, 0, no_arena(), (PreLeft *)nullptr, 0u, 0u, sp));
             if ((rc = count_event_end(c))) return rc;
             c->nCountLaunch++;
         }
+        if (sp.useBounds) {     // RESOLVE as its own kernel: candidate bins and value bounds of every cell
+            if ((rc = aux_begin(c, "resolve", levelIdx))) return rc;
+            CK(launch_pdl(c, k_sel_resolve, dim3(std::min<uint32_t>(nCells, 4u * (uint32_t)c->nSM)), dim3(kThreads), (size_t)nb1 * 4, c->lv, ss, nCells, nb1,
+                          0x7fffffffu, sp.sampleS, sp.z));
+            if ((rc = aux_end(c))) return rc;
+            c->nOtherLaunch++;
+        }
         {
-            const size_t smem = ringBytes + (size_t)kWarps * kSelWarpStage * 4 + (size_t)nb1 * 4;
+            const size_t smem = ringBytes + (size_t)kWarps * kSelWarpStage * 4 + (sp.useBounds ? 0 : (size_t)nb1 * 4);
             int occ = 1;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_stream<kSelCompact>, kThreads, smem));
-            const uint32_t grid = c->chunkTiles ? ceil_div(nTiles, c->chunkTiles)
-                                                : std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 3));
+            auto kcomp = sp.visits ? k_sel_stream<kSelCompact, true> : k_sel_stream<kSelCompact, false>;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kcomp, kThreads, smem));
+            const uint32_t grid = compactTiles ? ceil_div(nTiles, compactTiles)
+                                               : std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 3));
             if ((rc = count_event_begin(c))) return rc;
-            CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                          nCells, nL, nTiles, nb1, 1, c->selBigFinish ? 0x7fffffffu : candCap,
+            CK(launch_pdl(c, kcomp, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
+                          nCells, nL, nTiles, nb1, 1, (c->selBigFinish || sp.visits) ? 0x7fffffffu : candCap,
                           dbgBase ? dbgBase + (size_t)kDbgBlocks * 4 : (unsigned long long *)nullptr,
-                          (float *)nullptr, 0u, 0, no_arena(), pre, preTag, c->chunkTiles));
+                          (float *)nullptr, 0u, sp.useBounds ? 1 : 0, no_arena(), pre, preTag, compactTiles, sp));
             if ((rc = count_event_end(c))) return rc;
         }
         {
-            const size_t smem = sel_search_smem_bytes(candCap);
-            const int threads = nCells <= 2u * (uint32_t)c->nSM ? 1024 : search_threads(smem);
+            // (private regions: the search reads the pieces in place - no staging area, three piece tables instead)
+            const uint32_t finishCap = sp.visits ? 0u : candCap;
+            const size_t smem = sel_search_smem_bytes(finishCap) + (sp.visits ? (size_t)3 * kSelMaxPieces * 4 : 0);
+            const int threads = (nCells <= 2u * (uint32_t)c->nSM || sp.visits) ? 1024 : search_threads(smem);
             int occ = 1;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sel_finish, threads, smem));
+            auto kfin = sp.visits ? k_sel_finish<true> : k_sel_finish<false>;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfin, threads, smem));
             const uint32_t grid = std::min<uint32_t>(nCells, (uint32_t)c->nSM * (uint32_t)std::max(occ, 1));
             if ((rc = aux_begin(c, "finish", levelIdx))) return rc;
-            CK(launch_pdl(c, k_sel_finish, dim3(grid), dim3(threads), smem, (const float *)cand, c->lv, ss, sc, nCells, nb1, candCap, c->d_err,
-                          dbgBase ? dbgBase + (size_t)2 * kDbgBlocks * 4 : (unsigned long long *)nullptr, preNb ? 1 : 2,
-                          c->selBigFinish ? 1 : 0, dn));
+            CK(launch_pdl(c, kfin, dim3(grid), dim3(threads), smem, (const float *)cand, c->lv, ss, sc, nCells, nb1, finishCap, c->d_err,
+                          dbgBase ? dbgBase + (size_t)2 * kDbgBlocks * 4 : (unsigned long long *)nullptr, (preNb || sp.sampleS > 1) ? 1 : 2,
+                          c->selBigFinish ? 1 : 0, dn, sp));
             if ((rc = aux_end(c))) return rc;
         }
         c->nCountLaunch += 1;
@@ -840,6 +929,8 @@ SelMrPlan sel_plan_mr(const orb_ctx *c, uint32_t nCells, int M, int forcedNb = 0
 // fit.  Decided from rank-invariant numbers only (it shapes the multi-rank exchanges).
 int prefuse_nb(const orb_ctx *c, uint32_t nNext, int M) {
     if (c->prefuseHist == 0) return 0;
+    // sampled rows (single rank) replace the HIST pass for a fraction of its cost without touching the partition
+    if (c->prefuseHist < 0 && sampling_on(c)) return 0;
     // Measured (profiles/r01x_*, r01z_*): binning in the partition costs ~10 us per level at 2^24 particles - as much as
     // the HIST pass it replaces, whose column is still half in L2 at that size - but pays from ~2^25 particles per GPU
     // (HIST is then a full HBM pass: -9 % build time at 2^27) and whenever ranks have to agree on the rows anyway.
@@ -912,7 +1003,7 @@ int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int
         const uint32_t grid = std::min<uint32_t>(nTiles, (uint32_t)c->nSM * (uint32_t)std::min(std::max(occ, 1), 4));
         if ((rc = count_event_begin(c))) return rc;
         CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                      nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u, 0, no_arena(), (PreLeft *)nullptr, 0u, 0u));
+                      nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u, 0, no_arena(), (PreLeft *)nullptr, 0u, 0u, no_priv()));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     }
@@ -936,7 +1027,7 @@ int launch_level_select_mr(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, int
         if ((rc = count_event_begin(c))) return rc;
         CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, peer ? ss : sg,
                       (const uint32_t *)c->d_tile_first, nCells, nL, nTiles, nb1, 1, pl.candCap, (unsigned long long *)nullptr,
-                      c->d_slots_l, pl.slotWords, peer ? 1 : 0, no_arena(), (PreLeft *)nullptr, 0u, 0u));
+                      c->d_slots_l, pl.slotWords, peer ? 1 : 0, no_arena(), (PreLeft *)nullptr, 0u, 0u, no_priv()));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     }
@@ -1024,7 +1115,7 @@ int launch_level_select_mr2(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, in
             const uint32_t grid = std::min<uint32_t>(nTiles, nSM * (uint32_t)std::min(std::max(occ, 1), 4));
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelHist>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, ss, (const uint32_t *)c->d_tile_first,
-                          nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u, 0, no_arena(), (PreLeft *)nullptr, 0u, 0u));
+                          nCells, nL, nTiles, nb1, pl.rep, pl.candCap, (unsigned long long *)nullptr, (float *)nullptr, 0u, 0, no_arena(), (PreLeft *)nullptr, 0u, 0u, no_priv()));
             if ((rc = count_event_end(c))) return rc;
             c->nCountLaunch++;
         }
@@ -1062,7 +1153,7 @@ int launch_level_select_mr2(orb_ctx *c, uint32_t nCells, const SelMrPlan &pl, in
             if ((rc = count_event_begin(c))) return rc;
             CK(launch_pdl(c, k_sel_stream<kSelCompact>, dim3(grid), dim3(kThreads), smem, x, y, z, cand, c->lv, sg,
                           (const uint32_t *)c->d_tile_first, nCells, nL, nTiles, nb1, 1, resolveCap, (unsigned long long *)nullptr,
-                          c->d_slots_l, pl.slotWords, 0, xa, c->preValid ? c->d_pre : (PreLeft *)nullptr, c->preTagSeq, c->chunkTiles));
+                          c->d_slots_l, pl.slotWords, 0, xa, c->preValid ? c->d_pre : (PreLeft *)nullptr, c->preTagSeq, c->chunkTiles, no_priv()));
             if ((rc = count_event_end(c))) return rc;
             c->nCountLaunch++;
         }
@@ -1430,6 +1521,8 @@ static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_l
     CK(cudaMalloc(&c->d_blk_left, sizeof(uint32_t) * 64 * (size_t)c->nSM));
     CK(cudaMalloc(&c->d_blk_restart, sizeof(uint32_t) * 64 * (size_t)c->nSM));
     CK(cudaMalloc(&c->d_blk_le, sizeof(uint32_t) * 64 * (size_t)c->nSM));
+    CK(cudaMalloc(&c->d_visits, sizeof(orb::SelVisitRec) * kVisitRecs));
+    CK(cudaMemset(c->d_visits, 0, sizeof(orb::SelVisitRec) * kVisitRecs));
     CK(cudaMalloc(&c->d_pre, sizeof(orb::PreLeft) * 64 * (size_t)c->nSM));
     CK(cudaMemset(c->d_pre, 0, sizeof(orb::PreLeft) * 64 * (size_t)c->nSM));
     CK(cudaMalloc(&c->d_nGE, (size_t)std::max<uint32_t>(1u, n_leaf_cells) * 4));
@@ -1456,22 +1549,35 @@ static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_l
         CK(cudaMalloc(&c->sel.ncand, L * 4));
         CK(cudaMalloc(&c->sel.flag, L * 4));
         CK(cudaMemset(c->sel.flag, 0, L * 4));
+        CK(cudaMalloc(&c->sel.vlo, L * 4));
+        CK(cudaMalloc(&c->sel.vhi, L * 4));
         CK(cudaMalloc(&c->d_sel_nflag, sizeof(uint32_t) * kMaxLevels));
         CK(cudaMemset(c->d_sel_nflag, 0, sizeof(uint32_t) * kMaxLevels));
         const int ringBytes = orb::kCountStages * orb::kCountTile * (int)sizeof(float);
         const int histBytes = ringBytes + orb::kSelBinsMax * 4 /* >= nb1 * rep * 4 for every level */, compBytes = ringBytes + orb::kWarps * orb::kSelWarpStage * 4 + orb::kSelBinsMax * 4;
         CK(cudaFuncSetAttribute(orb::k_sel_stream<orb::kSelHist>, cudaFuncAttributeMaxDynamicSharedMemorySize, histBytes));
         CK(cudaFuncSetAttribute(orb::k_sel_stream<orb::kSelCompact>, cudaFuncAttributeMaxDynamicSharedMemorySize, compBytes));
+        CK(cudaFuncSetAttribute(orb::k_sel_stream<orb::kSelCompact, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, compBytes));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occSelStream[0], orb::k_sel_stream<orb::kSelHist>, orb::kThreads, histBytes));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occSelStream[1], orb::k_sel_stream<orb::kSelCompact>, orb::kThreads, compBytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occSelStream[2], orb::k_sel_stream<orb::kSelCompact, true>, orb::kThreads,
+                                                         ringBytes + orb::kWarps * orb::kSelWarpStage * 4));
+        CK(cudaFuncSetAttribute(orb::k_sel_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, orb::kSelBinsMax * 4));
         const int searchBytes = (int)orb::sel_search_smem_bytes(kSelValsCap);
-        CK(cudaFuncSetAttribute(orb::k_sel_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
+        CK(cudaFuncSetAttribute(orb::k_sel_finish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
+        CK(cudaFuncSetAttribute(orb::k_sel_finish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
         CK(cudaFuncSetAttribute(orb::k_selmr_finish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
         CK(cudaFuncSetAttribute(orb::k_selmr_finish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, searchBytes));
-        CK(cudaFuncSetAttribute(orb::k_sel_percell<512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
-        CK(cudaFuncSetAttribute(orb::k_sel_percell<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
-        CK(cudaFuncSetAttribute(orb::k_sel_percell<512, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
-        CK(cudaFuncSetAttribute(orb::k_sel_percell<1024, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(8192)));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(kSelCellCapMax)));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(kSelCellCapMax)));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(kSelCellCapMax)));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<1024, 1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(kSelCellCapMax)));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<512, 2, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(kSelCellCapMax)));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<512, 3, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(kSelCellCapMax)));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<256, 6, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(kSelCellCapMax)));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(kSelCellCapMax)));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<512, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(kSelCellCapMax)));
+        CK(cudaFuncSetAttribute(orb::k_sel_percell<1024, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_percell_smem_bytes(kSelCellCapMax)));
     }
     CK(cudaFuncSetAttribute(orb::k_xf_finish_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::sel_search_smem_bytes(kSelValsCap)));
     CK(cudaFuncSetAttribute(orb::k_xd_compact_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orb::xd_compact_warp_smem(512)));
@@ -1510,6 +1616,18 @@ static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_l
     if (c->occPartStream < 1 || c->occPartCells < 1) return fail(ORB_ERR_CUDA, "partition kernels do not fit on this device");
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occHoare, orb::k_hoare_scan, orb::kThreads, 0));
     if (c->occHoare < 1) c->occHoare = 1;
+    const char *sml = getenv("ORB_SAMPLE_MIN_LOCAL");
+    if (sml && atoll(sml) >= 0) c->sampleMinLocal = (uint64_t)atoll(sml);
+    const char *sma = getenv("ORB_SAMPLE_MAX_AVG");
+    if (sma && atoll(sma) >= 1) c->sampleMaxAvg = (uint64_t)atoll(sma);
+    const char *cko = getenv("ORB_CHUNK_OCC");
+    if (cko && atoi(cko) >= 1 && atoi(cko) <= 3) c->chunkOcc = atoi(cko);
+    const char *slo = getenv("ORB_SELECT_LOW_OCC");
+    if (slo) c->selLowOcc = atoi(slo) != 0;
+    const char *sst = getenv("ORB_SAMPLE_STRIDE");
+    if (sst && atoi(sst) >= 1 && atoi(sst) <= 64) c->sampleS = atoi(sst);
+    const char *ssz = getenv("ORB_SAMPLE_Z");
+    if (ssz && atof(ssz) >= 0.0) c->sampleZ = (float)atof(ssz);
     const char *tm = getenv("ORB_TIES");
     if (tm && std::string(tm) == "hoare") c->tieMode = 1;
     const char *p = getenv("ORB_PROFILE");
@@ -1598,7 +1716,7 @@ int orb_destroy(orb_ctx *c) {
     if (c->d_cnt_g_buf) cudaFree(c->d_cnt_g_buf);
     cudaFree(c->d_dbg); cudaFree(c->d_dbg_blocks);
     cudaFree(c->sel.bfirst); cudaFree(c->sel.blast); cudaFree(c->sel.base); cudaFree(c->sel.ncand);
-    cudaFree(c->sel.flag); cudaFree(c->d_sel_nflag);
+    cudaFree(c->sel.flag); cudaFree(c->d_sel_nflag); cudaFree(c->d_visits); cudaFree(c->sel.vlo); cudaFree(c->sel.vhi);
     cudaFree(c->d_sel_hist_g); cudaFree(c->d_sel_locbase); cudaFree(c->d_slots_g);
     for (int r = 0; r < orb::kMaxPeers; ++r)
         if (c->peerIpc[r] && c->peerX[r]) cudaIpcCloseMemHandle(c->peerX[r]);
@@ -2077,6 +2195,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
     }
 
     const int M = c->trialDepth;
+    c->sampleOff = false;
     c->extraPasses.assign(kMaxLevels, 0);
     std::vector<int> passes;
     std::vector<uint32_t> unfound;
@@ -2184,6 +2303,9 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             uint32_t nf = 0;
             if ((rc = select_mr_flagged(c, slot, &nf))) return rc;
             if (nf == 0u) break;
+            // sampled rows whose brackets fail on more than a stray cell: the particle order is not independent of the
+            // coordinates (a pre-sorted snapshot) - exact rows for the rest of this build
+            if (c->levelSampled && nf > std::max<uint32_t>(1u, nCells / 64u)) c->sampleOff = true;
             c->cur ^= 1;                  // the gated partition did nothing: undo the ping-pong flip
             rc = mrPlan.ok ? select_mr_fallback(c, nCells, slot, l - 1) : select_fallback(c, nCells, slot, l - 1);
             if (rc) return rc;

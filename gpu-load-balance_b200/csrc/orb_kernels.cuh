@@ -1434,8 +1434,8 @@ __global__ void k_ranges_from_level(const orb_cell *__restrict__ cells, uint32_t
 struct PreLeft {
     uint32_t tag;        // level tag (stale records of earlier levels never match)
     uint32_t cell;       // level-local index of the chunk's trailing cell
-    uint32_t below;      // kind 0: particles of the segment below the candidate bins; kind 1: its left particles
-    uint32_t gbase, tot; // kind 0: the segment's candidates are list[gbase .. gbase + tot)
+    uint32_t below;      // kind 0 / 2: particles of the segment below the candidate bins; kind 1: its left particles
+    uint32_t gbase, tot; // kind 0: the segment's candidates are list[gbase .. gbase + tot) of the cell's list; kind 2: of the whole column
     uint32_t kind;
     uint32_t pad_[2];
 };
@@ -1850,9 +1850,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_partition_coop(const float *__r
                 const PreLeft P = pre[blockIdx.x];
                 if (P.tag == preTag && P.cell == c) {
                     if (tid == 0) cnt = P.below;
-                    if (P.kind == 0u) {
-                        const float *list = preList + (preListStride ? (size_t)c * preListStride : (size_t)cb) + P.gbase;
-                        for (uint32_t i = tid; i < P.tot; i += kThreads) cnt += (__ldcg(list + i) < cutv) ? 1u : 0u;
+                    if (P.kind == 0u || P.kind == 2u) {      // kind 2: gbase is an absolute index (the search block's private region)
+                        const float *list = P.kind == 2u ? preList + P.gbase : preList + (preListStride ? (size_t)c * preListStride : (size_t)cb) + P.gbase;
+                        uint32_t i = tid;
+                        for (; i + 3u * kThreads < P.tot; i += 4u * kThreads) {      // four loads in flight per thread
+                            const float a0 = __ldcg(list + i), a1 = __ldcg(list + i + kThreads), a2 = __ldcg(list + i + 2 * kThreads), a3 = __ldcg(list + i + 3 * kThreads);
+                            cnt += (uint32_t)(a0 < cutv) + (uint32_t)(a1 < cutv) + (uint32_t)(a2 < cutv) + (uint32_t)(a3 < cutv);
+                        }
+                        for (; i < P.tot; i += kThreads) cnt += (__ldcg(list + i) < cutv) ? 1u : 0u;
                     }
                     e = b;      // nothing left to read
                 }

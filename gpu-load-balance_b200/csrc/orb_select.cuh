@@ -41,6 +41,7 @@ struct SelState {
     uint32_t *cursor;     // [nCells] COMPACT: fill level of the cell's candidate list; FINISH leaves it zero
     uint32_t *flag;       // [nCells] 1: left to the iterative path
     uint32_t *n_flagged;  // this level's count of flagged cells (gate of the iterative fallback)
+    float *vlo, *vhi;     // [nCells] value bounds of the candidate bins (sel_value_bounds), published by k_sel_resolve; may be null
 };
 
 struct SelCtl {           // statistics of the level (same meaning as PassCtl / LevelCtl)
@@ -65,6 +66,76 @@ struct SelTarget {
         prod = __fmul_rn(__uint2float_rn(total), ratio);
     }
     __device__ __forceinline__ int diff(uint32_t cnt) const { return __float2int_rz(__fsub_rn(__uint2float_rn(cnt), prod)); }
+};
+
+// ---- sampled rows (single rank) ----
+// The HIST pass may bin only a SAMPLE of a cell (every S-th tile, or every S-th 512-byte piece of a cell that one block
+// searches): the rows then only ESTIMATE the prefix counts.  RESOLVE widens the candidate bins by z standard deviations
+// of the estimate; the pass that gathers the candidates (which reads every particle anyway) counts the particles below
+// the candidate bins EXACTLY, and the search is entered only if the exact numbers prove the bracket:
+//     (first == 0 || diff(base) <= -3)  &&  (last == nb - 1 || diff(base + K) >= 3)
+// - the same two facts the exact rows establish (sel_resolve_cell).  The result therefore never depends on the sample;
+// a bracket that fails is searched again with exact rows (k_sel_percell) or left to the iterative search (k_sel_finish).
+struct SelSampleEst {
+    float ns, sc, z, nTot;
+    __device__ __forceinline__ void init(uint32_t sampleTotal, uint32_t cellTotal, float zIn) {
+        ns = (float)sampleTotal; nTot = (float)cellTotal; z = zIn;
+        sc = sampleTotal ? __fdiv_rn(nTot, ns) : 0.f;
+    }
+    // bound on the cell's exact prefix count, given the sample's prefix count p
+    __device__ __forceinline__ uint32_t bound(uint32_t p, bool upper) const {
+        if (!(ns > 0.f)) return upper ? (uint32_t)nTot : 0u;
+        const float pf = (float)p;
+        const float sd = sc * sqrtf(fmaxf(pf * (ns - pf), 0.f) / ns);
+        const float m = z * sd + 2.f * sc + 8.f;
+        const float v = fminf(fmaxf(upper ? pf * sc + m : pf * sc - m, 0.f), nTot);
+        return (uint32_t)v;
+    }
+};
+
+// smallest x in (lo, hi] with pred(x), for a monotone predicate with pred(hi) true and pred(lo) false (or lo outside the
+// domain); called by a whole warp, 32 probes per round
+template <typename P>
+__device__ __forceinline__ uint32_t sel_warp_first_true(uint32_t lo, uint32_t hi, P pred) {
+    const uint32_t lane = threadIdx.x & 31u;
+    while (hi - lo > 1u) {
+        const uint32_t span = hi - lo, step = (span + 31u) / 32u;
+        const uint64_t xx = (uint64_t)lo + (uint64_t)step * (lane + 1u);
+        const uint32_t x = xx >= (uint64_t)hi ? hi : (uint32_t)xx;
+        const unsigned m = __ballot_sync(0xffffffffu, x == hi || pred(x));
+        const int j = __ffs(m) - 1;                           // (lane 31 probes hi: m != 0)
+        const uint32_t hj = __shfl_sync(0xffffffffu, x, j);
+        const uint32_t lj = j ? __shfl_sync(0xffffffffu, x, j - 1) : lo;
+        hi = hj; lo = lj;
+    }
+    return hi;
+}
+// The sampled RESOLVE without a square root and a division per bin: the two bounds are monotone in the sample prefix
+// where it matters (away from the very ends), so "upper bound reaches the target" / "lower bound still below it" turn
+// into two critical sample prefixes pA, pB, found once per cell by a warp.  A bin then costs two integer compares.
+// (Where the bounds are not monotone the candidate bins may come out differently - the bracket is proven afterwards
+// with exact counts whatever they are.)
+__device__ __forceinline__ void sel_sample_crit(const SelSampleEst &se, const SelTarget &tg, uint32_t sampleTotal, uint32_t &pA, uint32_t &pB) {
+    // pA = smallest p in [0, ns] with diff(upper(p)) > -3   (search over y = p + 1 so that "none below" is y = 0)
+    pA = sel_warp_first_true(0u, sampleTotal + 1u, [&](uint32_t y) { return tg.diff(se.bound(y - 1u, true)) > -3; }) - 1u;
+    // pB = largest p in [0, ns] with diff(lower(p)) < 3 = (smallest p in (0, ns + 1] where it fails) - 1
+    pB = sel_warp_first_true(0u, sampleTotal + 1u, [&](uint32_t x) { return !(tg.diff(se.bound(x, false)) < 3); }) - 1u;
+}
+
+// COMPACT with private regions (single rank): block b appends the candidates it meets to ITS OWN region of the idle
+// column (the particles [chunkStart, chunkEnd) it streams - always room, no global atomic, contiguous per visited cell)
+// and leaves one record per visited cell.  FINISH gathers a cell's pieces from the blocks whose chunks overlap it; the
+// exact count below the candidate bins is the sum of the records' `below`.
+constexpr int kSelMaxVisit = 4;
+constexpr int kSelMaxPieces = 1024;    // chunks one cell may overlap (pieces FINISH gathers)
+struct SelVisit { uint32_t cell, off, cnt, below; };       // off: absolute index of the piece in the idle column
+struct SelVisitRec { uint32_t n, pad_[3]; SelVisit v[kSelMaxVisit]; };
+struct SelPriv {
+    int sampleS;            // HIST: bin every sampleS-th tile only; COMPACT / FINISH: the rows are sampled (> 1)
+    float z;
+    SelVisitRec *visits;    // != null: private regions + visit records (one per COMPACT block)
+    uint32_t chunk;         // particles per COMPACT block (FINISH: to find the blocks that overlap a cell)
+    int useBounds;          // COMPACT with preResolved: ss.vlo / ss.vhi hold the cells' value bounds (k_sel_resolve ran)
 };
 
 // block-wide exclusive scan of one value per thread (any block size up to 1024); total in `total`
@@ -124,11 +195,13 @@ struct SelResolveSmem {
     uint32_t w[32];
     int first, last;
     uint32_t base, end;
+    uint32_t pA, pB;          // sampled rows: critical sample prefixes (sel_sample_crit)
 };
 __device__ __forceinline__ void sel_resolve_cell(const LevelState &lv, const SelState &ss, uint32_t c, int nb1, uint32_t candCap,
                                                  bool publish, uint32_t *hbuf, SelResolveSmem &rs, uint32_t &bfOut, uint32_t &blOut,
                                                  bool preloaded = false /* hbuf already holds the row (barrier done by the caller) */,
-                                                 bool countFlag = true /* false: the caller counts flagged cells elsewhere */) {
+                                                 bool countFlag = true /* false: the caller counts flagged cells elsewhere */,
+                                                 int sampleS = 1 /* > 1: the row is a sample (see SelSampleEst) */, float sampleZ = 0.f) {
     const int tid = threadIdx.x;
     const int per = nb1 / kThreads;          // 2 .. 32
     if (!preloaded) __syncthreads();
@@ -147,12 +220,32 @@ __device__ __forceinline__ void sel_resolve_cell(const LevelState &lv, const Sel
     const uint32_t excl = sel_block_scan(sum, rs.w, total);
     int myFirst = nb1, myLast = -1;
     uint32_t p = excl;
-    for (int j = 0; j < per; ++j) {
-        const uint32_t pn = p + h[j];
-        const int b = tid * per + j;
-        if (tg.diff(pn) > -3) myFirst = min(myFirst, b);
-        if (tg.diff(p) < 3) myLast = max(myLast, b);
-        p = pn;
+    const bool sampled = sampleS > 1;
+    if (sampled) {      // block-uniform
+        if (tid < 32) {
+            SelSampleEst se;
+            se.init(total, lv.total[c], sampleZ);
+            uint32_t pA, pB;
+            sel_sample_crit(se, tg, total, pA, pB);
+            if (tid == 0) { rs.pA = pA; rs.pB = pB; }
+        }
+        __syncthreads();
+        const uint32_t pA = rs.pA, pB = rs.pB;
+        for (int j = 0; j < per; ++j) {
+            const uint32_t pn = p + h[j];
+            const int b = tid * per + j;
+            if (pn >= pA) myFirst = min(myFirst, b);
+            if (p <= pB) myLast = max(myLast, b);
+            p = pn;
+        }
+    } else {
+        for (int j = 0; j < per; ++j) {
+            const uint32_t pn = p + h[j];
+            const int b = tid * per + j;
+            if (tg.diff(pn) > -3) myFirst = min(myFirst, b);
+            if (tg.diff(p) < 3) myLast = max(myLast, b);
+            p = pn;
+        }
     }
     if (myFirst < nb1) atomicMin(&rs.first, myFirst);
     if (myLast >= 0) atomicMax(&rs.last, myLast);
@@ -168,7 +261,8 @@ __device__ __forceinline__ void sel_resolve_cell(const LevelState &lv, const Sel
     __syncthreads();
     // bf <= bl always (tests/test_select_model.py::ambiguous_range); guarded anyway.  More candidates than one block
     // can stage: the cell is left to the iterative search.
-    const bool ok = bf <= bl && bf < nb1 && bl >= 0 && (rs.end - rs.base) <= candCap;
+    // (sampled rows: base / ncand published below are sample counts - FINISH takes the exact ones from the visit records)
+    const bool ok = bf <= bl && bf < nb1 && bl >= 0 && (sampled || (rs.end - rs.base) <= candCap);
     bfOut = ok ? (uint32_t)bf : 1u;
     blOut = ok ? (uint32_t)bl : 0u;
     if (publish && tid == 0) {
@@ -195,6 +289,9 @@ struct SelStreamSmem {
     uint32_t wN[kWarps];                          // COMPACT: staged candidates per warp
     uint32_t gbase;
     uint32_t below, spilled;                      // COMPACT: PreLeft bookkeeping of the running cell
+    uint32_t blkCur, visitStart, nVis;            // COMPACT with private regions: fill level of the block's region, start of the running visit
+    SelVisit vis[kSelMaxVisit];
+    float vLo, vHi;                               // COMPACT: value bounds of the running cell's candidate bins
     SelResolveSmem rs;
 };
 
@@ -204,6 +301,94 @@ __device__ __forceinline__ void sel_bin_bounds(uint32_t first, uint32_t last, in
     fHi = (last + 1u >= (uint32_t)nb) ? __int_as_float(0x7f800000) : (float)(last + 1u);
     if (first > last) { fLo = 1.f; fHi = 0.f; }     // empty
 }
+
+// The same membership test on the VALUE instead of the bin coordinate: sel_bin is monotone, so
+//     first <= sel_bin(v) <= last   <=>   vLo <= v < vHi
+// for vLo = the smallest float whose bin is >= first and vHi = the smallest float whose bin is > last, found by bisection
+// over the floats in their total order (32 evaluations of sel_bin, once per cell).  Two compares per particle instead
+// of subtract, multiply, clamp and three compares.  vHi = NaN stands for "no upper limit" (the tests below are written
+// so that NaN passes everything); an empty range gives vLo = +inf, vHi = -inf.  (NaN coordinates are not supported
+// by the search: they would be binned low here and never counted left by the reference.)
+__device__ __forceinline__ uint32_t sel_f2key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float sel_key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+// smallest float v in [-inf, +inf] with sel_bin(v, lo, scale, nb) >= b (b >= 1; +inf if even +inf falls short)
+__device__ __forceinline__ float sel_bin_threshold(int b, float lo, float scale, int nb) {
+    const float inf = __int_as_float(0x7f800000);
+    uint32_t a = sel_f2key(-inf), e = sel_f2key(inf);        // answer in [a, e]
+    if (sel_bin(-inf, lo, scale, nb) >= b) return -inf;
+    // invariant: bin(key a) < b; bin(key e) >= b or e = key(+inf): if even +inf falls short the loop ends at e.
+    // The bin edge lo + b / scale is within a few ulps of the answer: bracket it first (18 evaluations instead of 32)
+    if (scale > 0.f) {
+        const float g = __fadd_rn(lo, __fdiv_rn((float)b, scale));
+        if (fabsf(g) < inf) {
+            const uint32_t kg = sel_f2key(g);
+            if (kg - a > 256u) { const uint32_t a2 = kg - 256u; if (sel_bin(sel_key2f(a2), lo, scale, nb) < b) a = a2; }
+            if (e - kg > 256u) { const uint32_t e2 = kg + 256u; if (sel_bin(sel_key2f(e2), lo, scale, nb) >= b) e = e2; }
+        }
+    }
+    while (e - a > 1u) {
+        const uint32_t m = a + ((e - a) >> 1);
+        if (sel_bin(sel_key2f(m), lo, scale, nb) >= b) e = m; else a = m;
+    }
+    return sel_key2f(e);
+}
+// The same by a whole warp (all 32 lanes call it with the same arguments and get the same result): 32 keys of the
+// bracket are tried at once, so the bisection takes 2 dependent evaluations near the bin edge (7 from the full range)
+// instead of 18 (32) - it sits on the critical path of every cell that one block searches.
+__device__ __forceinline__ float sel_bin_threshold_warp(int b, float lo, float scale, int nb) {
+    const float inf = __int_as_float(0x7f800000);
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t a = sel_f2key(-inf), e = sel_f2key(inf);
+    if (sel_bin(-inf, lo, scale, nb) >= b) return -inf;
+    if (scale > 0.f) {
+        const float g = __fadd_rn(lo, __fdiv_rn((float)b, scale));
+        if (fabsf(g) < inf) {
+            const uint32_t kg = sel_f2key(g);
+            // lane 0 tries kg - 256 as the new lower end, lane 1 kg + 256 as the new upper end
+            const bool canA = kg - a > 256u, canE = e - kg > 256u;
+            const uint32_t kt = lane == 0u ? kg - 256u : kg + 256u;
+            const bool ge = sel_bin(sel_key2f(kt), lo, scale, nb) >= b;
+            const unsigned m = __ballot_sync(0xffffffffu, ge);
+            if (canA && !(m & 1u)) a = kg - 256u;
+            if (canE && (m & 2u)) e = kg + 256u;
+        }
+    }
+    // invariant: bin(key a) < b; bin(key e) >= b, or e = key(+inf)
+    while (e - a > 1u) {
+        const uint32_t span = e - a;                                   // >= 2
+        const uint32_t step = (span + 31u) / 32u;                      // lanes try a + step, a + 2 step, ... (clamped to e)
+        const uint64_t kk = (uint64_t)a + (uint64_t)step * (lane + 1u);
+        const uint32_t kt = kk >= (uint64_t)e ? e : (uint32_t)kk;
+        const bool ge = sel_bin(sel_key2f(kt), lo, scale, nb) >= b;
+        const unsigned m = __ballot_sync(0xffffffffu, ge);
+        if (!m) return sel_key2f(e);                                   // even e falls short (e = key(+inf)): +inf
+        const int j = __ffs(m) - 1;                                    // first lane at or above the threshold
+        const uint32_t ej = __shfl_sync(0xffffffffu, kt, j);
+        const uint32_t aj = j ? __shfl_sync(0xffffffffu, kt, j - 1) : a;
+        if (ej - aj >= span) return sel_key2f(e);                      // (cannot happen: the bracket always shrinks)
+        e = ej; a = aj;
+    }
+    return sel_key2f(e);
+}
+// value bounds by one warp (block-uniform results must be broadcast by the caller)
+__device__ __forceinline__ void sel_value_bounds_warp(uint32_t first, uint32_t last, float lo, float scale, int nb, float &vLo, float &vHi) {
+    const float inf = __int_as_float(0x7f800000);
+    if (first > last) { vLo = inf; vHi = -inf; return; }
+    vLo = first == 0u ? -inf : sel_bin_threshold_warp((int)first, lo, scale, nb);
+    vHi = (last + 1u >= (uint32_t)nb) ? __int_as_float(0x7fc00000) : sel_bin_threshold_warp((int)last + 1, lo, scale, nb);
+}
+__device__ __forceinline__ void sel_value_bounds(uint32_t first, uint32_t last, float lo, float scale, int nb, float &vLo, float &vHi) {
+    const float inf = __int_as_float(0x7f800000);
+    if (first > last) { vLo = inf; vHi = -inf; return; }
+    vLo = first == 0u ? -inf : sel_bin_threshold((int)first, lo, scale, nb);
+    vHi = (last + 1u >= (uint32_t)nb) ? __int_as_float(0x7fc00000) : sel_bin_threshold((int)last + 1, lo, scale, nb);
+}
+// membership tests (vHi may be NaN = no upper limit)
+__device__ __forceinline__ bool sel_is_low(float v, float vLo) { return v < vLo; }
+__device__ __forceinline__ bool sel_is_cand(float v, float vLo, float vHi) { return v >= vLo && !(v >= vHi); }
 
 // Exchange arenas of all ranks (protocol of orb_exchange.cuh) and the cross-rank barrier at the start of a kernel:
 // block 0 stores the exchange's sequence number into every peer's flag word (this rank's preceding kernel has
@@ -236,7 +421,10 @@ __device__ __forceinline__ void x_barrier(const XArena &xa) {
     __syncthreads();
 }
 
-template <int MODE>
+// (PRIV: COMPACT with private candidate regions + cells resolved by k_sel_resolve - a separate instantiation, so that the
+//  plain pass does not carry its code: these kernels run for 20-30 us on 2^24 particles and an instruction-cache
+//  miss at every phase change shows)
+template <int MODE, bool PRIV = false>
 __global__ void __launch_bounds__(kThreads, MODE == kSelHist ? 4 : 3)
 k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z, float *__restrict__ cand,
              LevelState lv, SelState ss, const uint32_t *__restrict__ tile_first, uint32_t nCells, uint32_t nLocal,
@@ -244,7 +432,8 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
              uint32_t slotWords, int preResolved, XArena xa /* n > 1: cross-rank barrier before the pass (the rows it
              resolves from are the all-reduced ones) */,
              PreLeft *__restrict__ pre /* COMPACT: records for the partition's phase 1 (may be null) */, uint32_t preTag,
-             uint32_t tilesPerBlockIn /* != 0: chunk per block in count tiles, shared with the partition */) {
+             uint32_t tilesPerBlockIn /* != 0: chunk per block in count tiles, shared with the partition */,
+             SelPriv sp /* single rank: sampled rows, private candidate regions (zero: neither) */) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     pdl_enter();
     x_barrier(xa);
@@ -261,14 +450,20 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
 
     if (MODE == kSelHist) for (int i = tid; i < nb1 * rep; i += kThreads) s_hist[i] = 0u;
     if (MODE == kSelCompact && tid < kWarps) sm.wN[tid] = 0u;
-    if (tid == 0) { sm.below = 0u; sm.spilled = 0u; }
+    if (tid == 0) { sm.below = 0u; sm.spilled = 0u; sm.blkCur = 0u; sm.visitStart = 0u; sm.nVis = 0u; }
     __syncthreads();
 
-    // block b owns the contiguous tiles [tb0, tb1)
-    const uint32_t tilesPerBlock = tilesPerBlockIn ? tilesPerBlockIn : (nTiles + gridDim.x - 1) / gridDim.x;
-    const uint32_t tb0 = min(blockIdx.x * tilesPerBlock, nTiles), tb1 = min(tb0 + tilesPerBlock, nTiles);
+    // block b owns the contiguous tiles [tb0, tb1) - of the tiles the pass visits: a sampled HIST pass (sampled rows)
+    // visits the tiles 0, S, 2S, ... only, and counts in those
+    const uint32_t tileStep = (MODE == kSelHist && sp.sampleS > 1) ? (uint32_t)sp.sampleS : 1u;
+    const uint32_t nVisit = (nTiles + tileStep - 1u) / tileStep;
+    const uint32_t tilesPerBlock = tilesPerBlockIn ? tilesPerBlockIn : (nVisit + gridDim.x - 1) / gridDim.x;
+    const uint32_t tb0 = min(blockIdx.x * tilesPerBlock, nVisit), tb1 = min(tb0 + tilesPerBlock, nVisit);
+    constexpr bool priv = MODE == kSelCompact && PRIV;
+    const uint32_t chunkStart = tb0 * (uint32_t)kCountTile;
     int cur = -1;
-    float lo = 0.f, scale = 0.f, fLo = 1.f, fHi = 0.f;
+    float lo = 0.f, scale = 0.f;
+    float vLo = __int_as_float(0x7f800000), vHi = __int_as_float(0xff800000);      // empty
     const float nbm1 = (float)(nb1 - 1);
     unsigned below = 0u;          // COMPACT: this thread's particles of the running cell below the candidate bins
     bool curOk = false;           // ... the running cell has candidate bins (not flagged by the resolve)
@@ -287,10 +482,41 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
             uint32_t tot = 0, off = 0;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) { const uint32_t n = sm.wN[w]; if (w < warp) off += n; tot += n; }
-            if (pre) {      // block-uniform
+            if (pre || priv) {      // block-uniform
                 const unsigned wb = __reduce_add_sync(0xffffffffu, below);
                 if (lane == 0 && wb) atomicAdd(&sm.below, wb);
                 below = 0u;
+            }
+            if (priv) {
+                // the visit's candidates are [visitStart, blkCur) of the block's region, whatever the warps spilled before
+                if (tid == 0) { sm.gbase = sm.blkCur; sm.blkCur += tot; }
+                __syncthreads();
+                if (tid == 0) {
+                    const uint32_t v0 = sm.visitStart, cnt = sm.blkCur - v0;
+                    if (sm.nVis < (uint32_t)kSelMaxVisit) {
+                        SelVisit V;
+                        V.cell = (uint32_t)cur; V.off = chunkStart + v0; V.cnt = cnt; V.below = sm.below;
+                        sm.vis[sm.nVis] = V;
+                    }
+                    sm.nVis++;          // beyond kSelMaxVisit: FINISH sees the overflow and flags the cells this block touched
+                    if (pre) {
+                        PreLeft P;
+                        P.tag = curOk ? preTag : ~preTag;
+                        P.cell = (uint32_t)cur; P.below = sm.below; P.gbase = chunkStart + v0; P.tot = cnt; P.kind = 2u; P.pad_[0] = P.pad_[1] = 0u;
+                        pre[blockIdx.x] = P;
+                    }
+                    sm.visitStart = sm.blkCur;
+                    sm.below = 0u;
+                }
+                if (tot) {
+                    float *dst = cand + chunkStart + sm.gbase + off;
+                    const uint32_t n = sm.wN[warp];
+                    for (uint32_t i = lane; i < n; i += 32u) dst[i] = s_stage[warp * kSelWarpStage + i];
+                }
+                __syncthreads();
+                if (tid < kWarps) sm.wN[tid] = 0u;
+                __syncthreads();
+                return;
             }
             if (tid == 0) sm.gbase = tot ? atomicAdd(&ss.cursor[cur], tot) : 0u;
             __syncthreads();
@@ -324,9 +550,12 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
         const uint32_t n = sm.wN[warp];
         if (n + 512u <= (uint32_t)kSelWarpStage) return;
         uint32_t g = 0;
-        if (lane == 0) { g = atomicAdd(&ss.cursor[cur], n); sm.spilled = 1u; }
+        if (lane == 0) {
+            if (priv) g = atomicAdd(&sm.blkCur, n);
+            else { g = atomicAdd(&ss.cursor[cur], n); sm.spilled = 1u; }
+        }
         g = __shfl_sync(0xffffffffu, g, 0);
-        float *dst = slotWords ? slots + (size_t)cur * slotWords : cand + lv.bnd[cur];
+        float *dst = priv ? cand + chunkStart : (slotWords ? slots + (size_t)cur * slotWords : cand + lv.bnd[cur]);
         const uint32_t lim = slotWords ? slotWords - 1u : 0xffffffffu;
         for (uint32_t i = lane; i < n; i += 32u)
             if (g + i < lim) dst[g + i] = s_stage[warp * kSelWarpStage + i];
@@ -345,9 +574,19 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
             // (several ranks: k_selmr_prep resolves and publishes every cell, also those without local particles)
             const bool publish = slotWords == 0u && cb >= tb0 * (uint32_t)kCountTile && cb < tb1 * (uint32_t)kCountTile;
             uint32_t bf, bl;
-            if (preResolved) { bf = __ldcg(&ss.bfirst[c]); bl = __ldcg(&ss.blast[c]); }     // k_selx_resolve did it for the level
+            if (PRIV || preResolved) { bf = __ldcg(&ss.bfirst[c]); bl = __ldcg(&ss.blast[c]); }     // k_selx_resolve / k_sel_resolve did it for the level
             else sel_resolve_cell(lv, ss, c, nb1, candCap, publish, s_hbuf, sm.rs, bf, bl);
-            sel_bin_bounds(bf, bl, nb1, fLo, fHi);
+            if (PRIV) { vLo = __ldcg(&ss.vlo[c]); vHi = __ldcg(&ss.vhi[c]); }
+            else {
+                __syncthreads();
+                if (warp == 0) {
+                    float a, b;
+                    sel_value_bounds_warp(bf, bl, cLo, cScale, nb1, a, b);
+                    if (lane == 0) { sm.vLo = a; sm.vHi = b; }
+                }
+                __syncthreads();
+                vLo = sm.vLo; vHi = sm.vHi;
+            }
             curOk = bf <= bl;
         }
     };
@@ -357,10 +596,11 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
 
     for (uint32_t base = tb0; base < tb1; base += (uint32_t)kMaxUnits) {
         // ---- phase 1: classify up to kMaxUnits tiles ----
-        const uint32_t t = base + (uint32_t)tid;
+        const uint32_t tv = base + (uint32_t)tid;
+        const uint32_t t = tv * tileStep;
         int kind = 0;   // 0 skip, 1 stream, 2 fragmented
         uint32_t c = 0;
-        if (tid < kMaxUnits && t < tb1) {
+        if (tid < kMaxUnits && tv < tb1) {
             const uint32_t t0 = t * (uint32_t)kCountTile, t1 = min(t0 + (uint32_t)kCountTile, nLocal);
             c = tile_first[t * (kCountTile / kMapTile)];
             const uint32_t cb = lv.bnd[c], ce = lv.bnd[c + 1];
@@ -421,9 +661,8 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
                         unsigned keep = 0u, lows = 0u;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float tc = coord(v[j]);
-                            keep |= (unsigned)(tc >= fLo && tc < fHi) << j;
-                            lows |= (unsigned)(tc < fLo) << j;
+                            keep |= (unsigned)sel_is_cand(v[j], vLo, vHi) << j;
+                            lows |= (unsigned)sel_is_low(v[j], vLo) << j;
                         }
                         keep &= inMask;
                         below += __popc(lows & inMask);
@@ -464,16 +703,37 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
                         atomicAdd(&s_hist[b * rep + repSel], 1u);
                     }
                 } else {
-                    unsigned keep = 0u, lows = 0u;
+                    // two compares and two predicated adds per particle: #{v >= vLo} and #{v >= vHi}; the thread holds a
+                    // candidate iff the two differ (vHi = NaN, "no upper limit", compares false)
+                    unsigned nGeLo = 0u, nGeHi = 0u;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float tc = coord(v[j]);
-                        keep |= (unsigned)(tc >= fLo && tc < fHi) << j;
-                        lows |= (unsigned)(tc < fLo) << j;
+                        nGeLo += (v[j] >= vLo) ? 1u : 0u;
+                        nGeHi += (v[j] >= vHi) ? 1u : 0u;
                     }
-                    below += __popc(lows);
-                    warp_spill();
-                    sel_warp_append<16>(v, keep, s_stage + warp * kSelWarpStage, &sm.wN[warp]);
+                    below += 16u - nGeLo;
+                    const bool has = nGeLo != nGeHi;
+                    // Candidates are sparse (a thread rarely has one): only warps that hold any take this path, only the
+                    // lanes that hold one work in it - a shared-memory atomic on the warp's fill level, the values
+                    // re-read from the tile in shared memory (no register array indexed by a run-time bit position).
+                    if (__any_sync(0xffffffffu, has)) {
+                        warp_spill();
+                        unsigned keep = 0u;
+                        if (has) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) keep |= (unsigned)sel_is_cand(v[j], vLo, vHi) << j;
+                        }
+                        if (keep) {
+                            uint32_t pos = atomicAdd(&sm.wN[warp], (uint32_t)__popc(keep));
+                            float *dstw = s_stage + warp * kSelWarpStage;
+                            while (keep) {
+                                const int j = __ffs(keep) - 1;
+                                keep &= keep - 1u;
+                                dstw[pos++] = reinterpret_cast<const float *>(src + (j >> 2) * kThreads)[j & 3];
+                            }
+                        }
+                        __syncwarp();
+                    }
                 }
             }
             cp_async_wait<0>();
@@ -483,7 +743,34 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
     }
     if (bs && tid == 0) bs[2] = gtimer();
     flush();
+    if (priv) {
+        __syncthreads();
+        if (tid == 0) sp.visits[blockIdx.x].n = sm.nVis;
+        if (tid < kSelMaxVisit && (uint32_t)tid < sm.nVis) sp.visits[blockIdx.x].v[tid] = sm.vis[tid];
+    }
     if (bs && tid == 0) bs[3] = gtimer();
+}
+
+// RESOLVE of every cell of a streaming level as a kernel of its own (single rank, between HIST and COMPACT): one block
+// per cell publishes the candidate bins and their value bounds.  COMPACT then enters a cell with four loads instead of
+// a 32 KB row, a scan and a bisection per block and cell, and needs no row buffer in shared memory.
+__global__ void __launch_bounds__(kThreads) k_sel_resolve(LevelState lv, SelState ss, uint32_t nCells, int nb1, uint32_t candCap,
+                                                           int sampleS, float sampleZ) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    uint32_t *hbuf = reinterpret_cast<uint32_t *>(sel_smem);
+    __shared__ SelResolveSmem rs;
+    pdl_enter();
+    for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
+        if (!lv.active[c]) continue;          // block-uniform
+        uint32_t bf, bl;
+        sel_resolve_cell(lv, ss, c, nb1, candCap, true, hbuf, rs, bf, bl, false, true, sampleS, sampleZ);
+        if (threadIdx.x < 32) {
+            const float L = lv.mL[c];
+            float vLo, vHi;
+            sel_value_bounds_warp(bf, bl, L, sel_scale(L, lv.mR[c], nb1), nb1, vLo, vHi);
+            if (threadIdx.x == 0) { ss.vlo[c] = vLo; ss.vhi[c] = vHi; }
+        }
+    }
 }
 
 // =====================================================================================
@@ -494,6 +781,67 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
 // Writes the cell's result (margins, iter, found, nleft) and returns true, or flags it and returns false (block-
 // uniform); nothing else is written for a flagged cell.
 // =====================================================================================
+// f(v) for every staged value; `glob`: vals lies in global memory (a cell with more candidates than shared memory holds)
+// - eight loads in flight per thread instead of one dependent load per iteration
+template <typename F>
+__device__ __forceinline__ void sel_vals_for_each(const float *vals, uint32_t K, bool glob, F f) {
+    const uint32_t nT = blockDim.x;
+    uint32_t i = threadIdx.x;
+    if (glob) {
+        for (; i + 7u * nT < K; i += 8u * nT) {
+            float q[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) q[u] = __ldcg(vals + i + (uint32_t)u * nT);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f(q[u]);
+        }
+        for (; i < K; i += nT) f(__ldcg(vals + i));
+    } else {
+        for (; i < K; i += nT) f(vals[i]);
+    }
+}
+
+// where the block search reads its values from: an array (shared or global memory), or the pieces the COMPACT blocks
+// left in their private regions (piece i: cand[pOff[i] .. pOff[i] + pCnt[i]), pPos[i] = values in the pieces before it)
+struct SelSrcArray {
+    const float *vals;
+    uint32_t K;
+    bool glob;
+    template <typename F>
+    __device__ __forceinline__ void for_each(F f) const { sel_vals_for_each(vals, K, glob, f); }
+    __device__ __forceinline__ const float *shared_ptr() const { return glob ? nullptr : vals; }      // the values, if they lie in shared memory
+};
+struct SelSrcPieces {
+    const float *cand;
+    const uint32_t *pOff, *pCnt, *pPos;      // shared memory
+    uint32_t K;
+    __device__ __forceinline__ const float *shared_ptr() const { return nullptr; }
+    // thread t takes the values t, t + nT, ... of the concatenation; its piece index only ever advances.  Eight loads
+    // in flight per thread (the pieces lie in L2: the pass is a few latencies, not bandwidth).
+    template <typename F>
+    __device__ __forceinline__ void for_each(F f) const {
+        const uint32_t nT = blockDim.x;
+        uint32_t p = 0;
+        for (uint32_t i = threadIdx.x; i < K; i += 8u * nT) {
+            float q[8];
+            bool in[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t ii = i + (uint32_t)u * nT;
+                in[u] = ii < K;
+                q[u] = 0.f;
+                if (in[u]) {
+                    while (ii >= pPos[p] + pCnt[p]) ++p;       // (ii < K: ends at the last non-empty piece at the latest)
+                    q[u] = __ldcg(cand + pOff[p] + (ii - pPos[p]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (in[u]) f(q[u]);
+        }
+    }
+};
+
 struct SelSearchSmem {
     float wmin[32], wmax[32];
     uint32_t w[32];
@@ -508,24 +856,38 @@ struct SelSearchSmem {
 
 // Core of the search: computes the cell's result into sm.res* (valid for every thread on return) and returns true, or
 // returns false when the cell has to be left to the iterative path (block-uniform).  Writes no global memory.
-__device__ __forceinline__ bool sel_block_search_core(const float *vals, uint32_t K, uint32_t base, int hasOuter, float lo1,
-                                                      float scale1, int nb1, int bfirst, int blast, uint32_t *hist2, float *amb,
-                                                      const LevelState &lv, uint32_t c, SelSearchSmem &sm,
-                                                      unsigned long long *dbg = nullptr) {
+template <typename SRC>
+__device__ __forceinline__ bool sel_block_search_core_src(const SRC &src, uint32_t K, uint32_t base, int hasOuter, float lo1,
+                                                          float scale1, int nb1, int bfirst, int blast, uint32_t *hist2, float *amb,
+                                                          const LevelState &lv, uint32_t c, SelSearchSmem &sm,
+                                                          unsigned long long *dbg = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nThreads = (int)blockDim.x, nWarps = nThreads >> 5;
     const float inf = __int_as_float(0x7f800000);
     SelTarget tg;
     tg.init(lv.total[c], lv.nleaf[c]);
     const float L0 = lv.mL[c], R0 = lv.mR[c];
+    // Few values in shared memory (the candidates of a small cell searched with exact rows): no refinement - every value
+    // takes part in the replay's counts.  Two barriers instead of a dozen, no second histogram.
+    constexpr uint32_t kTiny = 256;
     const int nb2 = K > 4096u ? kSelBins2 : max(256, nThreads);
     const int per = nb2 / nThreads;          // 1, 2 or 8
+    const float *ambp = amb;
+    float lo2 = 0.f, scale2 = 0.f;
+    int first = 0, last = -1;
+    uint32_t base2 = base, K2 = K;
+    const bool tiny = K <= kTiny && src.shared_ptr() != nullptr;      // block-uniform
+    if (tiny) {
+        ambp = src.shared_ptr();
+        __syncthreads();                    // (sm.* may still be read from the previous cell)
+        if (tid == 0) { sm.finalCnt = 0u; sm.needFinal = 0; sm.cutf = 0.f; }
+    } else {
 
     // ---- range of the staged values: the candidate bins' interval when there is an outer histogram, else min / max
     //      (any range gives a valid monotone bin function; a tight one just resolves better) ----
     const bool fromBins = hasOuter && scale1 > 0.f;
     float mn = inf, mx = -inf;
     if (!fromBins) {
-        for (uint32_t i = tid; i < K; i += nThreads) { const float v = vals[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+        src.for_each([&](float v) { mn = fminf(mn, v); mx = fmaxf(mx, v); });
 #pragma unroll
         for (int o = 16; o; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
     }
@@ -546,9 +908,9 @@ __device__ __forceinline__ bool sel_block_search_core(const float *vals, uint32_
         sm.first = nb2; sm.last = -1; sm.base2 = 0u; sm.end2 = 0u; sm.namb = 0u; sm.finalCnt = 0u; sm.needFinal = 0; sm.cutf = 0.f;
     }
     __syncthreads();
-    const float lo2 = sm.lo2, scale2 = sm.scale2;
+    lo2 = sm.lo2; scale2 = sm.scale2;
     if (dbg && tid == 0) dbg[2] = gtimer();
-    for (uint32_t i = tid; i < K; i += nThreads) atomicAdd(&hist2[sel_bin(vals[i], lo2, scale2, nb2)], 1u);
+    src.for_each([&](float v) { atomicAdd(&hist2[sel_bin(v, lo2, scale2, nb2)], 1u); });
     __syncthreads();
     if (dbg && tid == 0) dbg[3] = gtimer();
 
@@ -576,7 +938,7 @@ __device__ __forceinline__ bool sel_block_search_core(const float *vals, uint32_
     if (myFirst < nb2) atomicMin(&sm.first, myFirst);
     if (myLast >= 0) atomicMax(&sm.last, myLast);
     __syncthreads();
-    const int first = sm.first, last = sm.last;
+    first = sm.first; last = sm.last;
     {
         uint32_t p = base + excl;
 #pragma unroll
@@ -591,17 +953,17 @@ __device__ __forceinline__ bool sel_block_search_core(const float *vals, uint32_
     }
     __syncthreads();
     if (dbg && tid == 0) dbg[4] = gtimer();
-    const uint32_t base2 = sm.base2;
-    const uint32_t K2 = sm.end2 - base2;
+    base2 = sm.base2;
+    K2 = sm.end2 - base2;
     const bool tooMany = !(first <= last) || K2 > (uint32_t)kSelAmbCap;
     if (tooMany) return false;   // massive ties: leave the cell to the iterative path
-    for (uint32_t i = tid; i < K; i += nThreads) {
-        const float v = vals[i];
+    src.for_each([&](float v) {
         const int b = sel_bin(v, lo2, scale2, nb2);
         if (b >= first && b <= last) amb[atomicAdd(&sm.namb, 1u)] = v;
-    }
+    });
     __syncthreads();
 
+    }
     if (dbg && tid == 0) dbg[5] = gtimer();
     // ---- replay of orbit.cpp:149-232 by warp 0 (every lane computes the same scalars) ----
     float L = L0, R = R0;
@@ -616,14 +978,14 @@ __device__ __forceinline__ bool sel_block_search_core(const float *vals, uint32_
                 const int b1 = sel_bin(cut, lo1, scale1, nb1);
                 dec = b1 < bfirst ? -1 : (b1 > blast ? 1 : 0);
             }
-            if (dec == 0) {
+            if (dec == 0 && !tiny) {
                 const int b2 = sel_bin(cut, lo2, scale2, nb2);
                 dec = b2 < first ? -1 : (b2 > last ? 1 : 0);
             }
             ++it;
             if (dec == 0) {
                 uint32_t n = 0;
-                for (uint32_t i = lane; i < K2; i += 32u) n += (amb[i] < cut) ? 1u : 0u;
+                for (uint32_t i = lane; i < K2; i += 32u) n += (ambp[i] < cut) ? 1u : 0u;
                 n = __reduce_add_sync(0xffffffffu, n);
                 const uint32_t cnt = base2 + n;
                 const int d = tg.diff(cnt);
@@ -648,7 +1010,7 @@ __device__ __forceinline__ bool sel_block_search_core(const float *vals, uint32_
     if (needFinal == 1) {
         const float cutf = sm.cutf;
         uint32_t n = 0;
-        for (uint32_t i = tid; i < K; i += nThreads) n += (vals[i] < cutf) ? 1u : 0u;
+        src.for_each([&](float v) { n += (v < cutf) ? 1u : 0u; });
         n = __reduce_add_sync(0xffffffffu, n);
         if (lane == 0 && n) atomicAdd(&sm.finalCnt, n);
         __syncthreads();
@@ -659,13 +1021,23 @@ __device__ __forceinline__ bool sel_block_search_core(const float *vals, uint32_
     return true;
 }
 
+__device__ __forceinline__ bool sel_block_search_core(const float *vals, uint32_t K, uint32_t base, int hasOuter, float lo1,
+                                                      float scale1, int nb1, int bfirst, int blast, uint32_t *hist2, float *amb,
+                                                      const LevelState &lv, uint32_t c, SelSearchSmem &sm,
+                                                      unsigned long long *dbg = nullptr, bool glob = false /* vals in global memory */) {
+    SelSrcArray src;
+    src.vals = vals; src.K = K; src.glob = glob;
+    return sel_block_search_core_src(src, K, base, hasOuter, lo1, scale1, nb1, bfirst, blast, hist2, amb, lv, c, sm, dbg);
+}
+
 // Search + commit: writes the cell's result (margins, iter, found, nleft) and the level statistics and returns true, or
 // flags the cell and returns false (block-uniform); nothing else is written for a flagged cell.
-__device__ __forceinline__ bool sel_block_search(const float *vals, uint32_t K, uint32_t base, int hasOuter, float lo1,
-                                                 float scale1, int nb1, int bfirst, int blast, uint32_t *hist2, float *amb,
-                                                 const LevelState &lv, const SelState &ss, const SelCtl &sc, uint32_t c,
-                                                 int hbmPasses, SelSearchSmem &sm, unsigned long long *dbg = nullptr) {
-    const bool ok = sel_block_search_core(vals, K, base, hasOuter, lo1, scale1, nb1, bfirst, blast, hist2, amb, lv, c, sm, dbg);
+template <typename SRC>
+__device__ __forceinline__ bool sel_block_search_src(const SRC &src, uint32_t K, uint32_t base, int hasOuter, float lo1,
+                                                     float scale1, int nb1, int bfirst, int blast, uint32_t *hist2, float *amb,
+                                                     const LevelState &lv, const SelState &ss, const SelCtl &sc, uint32_t c,
+                                                     int hbmPasses, SelSearchSmem &sm, unsigned long long *dbg = nullptr) {
+    const bool ok = sel_block_search_core_src(src, K, base, hasOuter, lo1, scale1, nb1, bfirst, blast, hist2, amb, lv, c, sm, dbg);
     if (threadIdx.x == 0) {
         if (!ok) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
         else {
@@ -685,6 +1057,14 @@ __device__ __forceinline__ bool sel_block_search(const float *vals, uint32_t K, 
         }
     }
     return ok;
+}
+__device__ __forceinline__ bool sel_block_search(const float *vals, uint32_t K, uint32_t base, int hasOuter, float lo1,
+                                                 float scale1, int nb1, int bfirst, int blast, uint32_t *hist2, float *amb,
+                                                 const LevelState &lv, const SelState &ss, const SelCtl &sc, uint32_t c,
+                                                 int hbmPasses, SelSearchSmem &sm, unsigned long long *dbg = nullptr, bool glob = false) {
+    SelSrcArray src;
+    src.vals = vals; src.K = K; src.glob = glob;
+    return sel_block_search_src(src, K, base, hasOuter, lo1, scale1, nb1, bfirst, blast, hist2, amb, lv, ss, sc, c, hbmPasses, sm, dbg);
 }
 
 // dynamic shared memory of the two search kernels: vals[cap + 4] | hist2[kSelBins2] | amb[kSelAmbCap]
@@ -728,26 +1108,32 @@ __device__ __forceinline__ void sel_report_done(const SelDone &dn, const uint32_
     }
 }
 
-// FINISH (streaming regime): one block per cell, candidates from the dense list written by COMPACT
+// FINISH (streaming regime): one block per cell, candidates from the dense list written by COMPACT - or, with private
+// regions (sp.visits: cap = 0, dynamic shared memory hist2 | amb | piece tables), read from the pieces the COMPACT blocks
+// left in their own regions
+template <bool PRIV>
 __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ cand, LevelState lv, SelState ss, SelCtl sc,
                                                      uint32_t nCells, int nb1, uint32_t cap, int *__restrict__ err,
                                                      unsigned long long *dbg, int hbmPasses /* reads of the column: 2, or 1 when the partition built the rows */,
                                                      int allowGlobal /* more candidates than `cap`: search them where they lie instead of failing */,
-                                                     SelDone dn) {
+                                                     SelDone dn, SelPriv sp) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     float *sbuf = reinterpret_cast<float *>(sel_smem);
     uint32_t *hist2 = reinterpret_cast<uint32_t *>(sbuf + cap + 4);
     float *amb = reinterpret_cast<float *>(hist2 + kSelBins2);
     __shared__ SelSearchSmem sm;
+    __shared__ uint32_t s_below, s_bad;
     pdl_enter();
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(sc.passes_out, hbmPasses);
     unsigned long long *bs = (dbg && blockIdx.x == 0) ? dbg : nullptr;    // ORB_DEBUG_TIMES=2: phases of block 0's first cell
     if (bs && threadIdx.x == 0) bs[0] = gtimer();
+    const int tid = threadIdx.x, lane = tid & 31, nThreads = (int)blockDim.x;
     for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
         __syncthreads();
         // independent loads of the cell's parameters, issued together
         const uint32_t act = lv.active[c], b0 = lv.bnd[c], b1 = lv.bnd[c + 1];
-        const uint32_t flg = __ldcg(&ss.flag[c]), K = __ldcg(&ss.ncand[c]), cur = __ldcg(&ss.cursor[c]), bs_ = __ldcg(&ss.base[c]);
+        const uint32_t flg = __ldcg(&ss.flag[c]), cur = __ldcg(&ss.cursor[c]), bs_ = __ldcg(&ss.base[c]);
+        uint32_t K = __ldcg(&ss.ncand[c]);
         const uint32_t bf = __ldcg(&ss.bfirst[c]), bl = __ldcg(&ss.blast[c]);
         const float L = lv.mL[c], R = lv.mR[c];
         if (!act) continue;
@@ -757,6 +1143,61 @@ __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ c
             continue;
         }
         if (flg) continue;
+        if (PRIV) {
+            // ---- the cell's pieces: chunks k0..k1 overlap it; each chunk's block left at most one record for the cell.
+            //      The search reads the pieces where they lie (L2), nothing is staged. ----
+            uint32_t *pOff = reinterpret_cast<uint32_t *>(amb + kSelAmbCap), *pCnt = pOff + kSelMaxPieces, *pPos = pCnt + kSelMaxPieces;
+            const uint32_t k0 = b0 / sp.chunk, k1 = (b1 - 1u) / sp.chunk, nP = k1 - k0 + 1u;
+            if (tid == 0) { s_below = 0u; s_bad = nP > (uint32_t)kSelMaxPieces ? 1u : 0u; }
+            __syncthreads();
+            uint32_t myBelow = 0;
+            if (!s_bad) {
+                for (uint32_t i = tid; i < nP; i += nThreads) {
+                    const SelVisitRec *r = sp.visits + (k0 + i);
+                    const uint32_t n = __ldcg(&r->n);
+                    uint32_t off = 0, cnt = 0;
+                    if (n > (uint32_t)kSelMaxVisit) s_bad = 1u;      // the block dropped a record: this cell's may be the one
+                    for (uint32_t j = 0; j < min(n, (uint32_t)kSelMaxVisit); ++j) {
+                        if (__ldcg(&r->v[j].cell) == c) { off = __ldcg(&r->v[j].off); cnt = __ldcg(&r->v[j].cnt); myBelow += __ldcg(&r->v[j].below); }
+                    }
+                    pOff[i] = off; pCnt[i] = cnt;
+                }
+            }
+            myBelow = __reduce_add_sync(0xffffffffu, myBelow);
+            if (lane == 0 && myBelow) atomicAdd(&s_below, myBelow);
+            __syncthreads();
+            if (s_bad) {        // block-uniform
+                if (tid == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
+                continue;
+            }
+            uint32_t carry = 0;
+            for (uint32_t r0 = 0; r0 < nP; r0 += (uint32_t)nThreads) {       // exclusive scan of the piece sizes
+                const uint32_t i = r0 + (uint32_t)tid;
+                const uint32_t v = i < nP ? pCnt[i] : 0u;
+                uint32_t tot;
+                const uint32_t ex = sel_block_scan(v, sm.w, tot);
+                if (i < nP) pPos[i] = carry + ex;
+                carry += tot;
+            }
+            __syncthreads();
+            K = carry;
+            const uint32_t base = s_below;
+            // the exact numbers must prove the bracket the (sampled) rows suggested - see SelSampleEst
+            SelTarget tg;
+            tg.init(lv.total[c], lv.nleaf[c]);
+            const bool proven = (bf == 0u || tg.diff(base) <= -3) && (bl + 1u >= (uint32_t)nb1 || tg.diff(base + K) >= 3);
+            if (!proven || bf > bl) {
+                if (tid == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
+                continue;
+            }
+            SelSrcPieces src;
+            src.cand = cand; src.pOff = pOff; src.pCnt = pCnt; src.pPos = pPos; src.K = K;
+            if (bs && threadIdx.x == 0) bs[1] = gtimer();
+            sel_block_search_src(src, K, base, 1, L, sel_scale(L, R, nb1), nb1, (int)bf, (int)bl, hist2, amb, lv, ss, sc, c, hbmPasses, sm,
+                                 c == blockIdx.x ? bs : nullptr);
+            if (bs && threadIdx.x == 0 && c == blockIdx.x) bs[7] = gtimer();
+            continue;
+        }
         if (cur != K || (K > cap && !allowGlobal)) {   // cannot happen: HIST and COMPACT use the same bin function
             if (threadIdx.x == 0) atomicExch(err, ORB_ERR_STATE);
             continue;
@@ -768,7 +1209,7 @@ __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ c
         if (threadIdx.x == 0) ss.cursor[c] = 0u;      // zero between levels (HIST counts into it)
         if (bs && threadIdx.x == 0) bs[1] = gtimer();
         sel_block_search(vals, K, bs_, 1, L, sel_scale(L, R, nb1), nb1, (int)bf, (int)bl, hist2, amb, lv, ss, sc, c, hbmPasses, sm,
-                         c == blockIdx.x ? bs : nullptr);
+                         c == blockIdx.x ? bs : nullptr, K > cap);
         if (bs && threadIdx.x == 0 && c == blockIdx.x) bs[7] = gtimer();
     }
     sel_report_done(dn, ss.n_flagged);
@@ -787,7 +1228,8 @@ struct SelPerCellSmem {
     SelSearchSmem search;
     uint32_t w[32];
     int first, last;
-    uint32_t base, end, nlist;
+    uint32_t base, end, nlist, lowTot, pA, pB;
+    float vLo, vHi;
     uint32_t segBelow[kSelMaxSeg], segListEnd[kSelMaxSeg], segLeft[kSelMaxSeg];
 };
 
@@ -814,13 +1256,101 @@ __device__ __forceinline__ void sel_for_each(const float *__restrict__ src, uint
     if (tail0 + threadIdx.x < K) f(__ldg(src + tail0 + threadIdx.x));
 }
 
-template <int THREADS, int MINBLOCKS, int U = 4>
+// COMPACT of a cell one block searches: counts the values below vLo (returned per thread) and appends those in
+// [vLo, vHi) to `list` (fill level *nlist; values beyond cap are counted but not stored).  One shared-memory atomic per
+// float4 that holds candidates, not per candidate.
+template <int U>
+__device__ __forceinline__ unsigned sel_compact_pass(const float *__restrict__ src, uint32_t K, float vLo, float vHi, float *list,
+                                                     uint32_t *nlist, uint32_t cap) {
+    unsigned lows = 0u;
+    auto one = [&](float v) {
+        lows += sel_is_low(v, vLo) ? 1u : 0u;
+        if (sel_is_cand(v, vLo, vHi)) {
+            const uint32_t idx = atomicAdd(nlist, 1u);
+            if (idx < cap) list[idx] = v;
+        }
+    };
+    auto four = [&](const float4 q) {
+        const float v[4] = {q.x, q.y, q.z, q.w};
+        // #{v >= vLo} and #{v >= vHi}: they differ iff the float4 holds a candidate (vHi = NaN compares false)
+        unsigned nGeLo = 0u, nGeHi = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            nGeLo += (v[k] >= vLo) ? 1u : 0u;
+            nGeHi += (v[k] >= vHi) ? 1u : 0u;
+        }
+        lows += 4u - nGeLo;
+        if (nGeLo != nGeHi) {
+            unsigned keep = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) keep |= (unsigned)sel_is_cand(v[k], vLo, vHi) << k;
+            uint32_t idx = atomicAdd(nlist, (uint32_t)__popc(keep));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (keep & (1u << k)) { if (idx < cap) list[idx] = v[k]; ++idx; }
+        }
+    };
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
+    const uint32_t head = mis ? min(4u - mis, K) : 0u;
+    const uint32_t body4 = (K - head) / 4u;
+    const float4 *g4 = reinterpret_cast<const float4 *>(src + head);
+    const uint32_t nT = blockDim.x;
+    uint32_t i = threadIdx.x;
+    for (; i + (uint32_t)(U - 1) * nT < body4; i += (uint32_t)U * nT) {
+        float4 q[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) q[u] = __ldg(g4 + i + (uint32_t)u * nT);
+#pragma unroll
+        for (int u = 0; u < U; ++u) four(q[u]);
+    }
+    for (; i < body4; i += nT) four(__ldg(g4 + i));
+    if (threadIdx.x < head) one(__ldg(src + threadIdx.x));
+    const uint32_t tail0 = head + body4 * 4u;
+    if (tail0 + threadIdx.x < K) one(__ldg(src + tail0 + threadIdx.x));
+    return lows;
+}
+
+// sampled variant of sel_for_each: every S-th 512-byte piece (32 float4) of the 16-byte aligned body of src[0..K)
+template <int U, typename F>
+__device__ __forceinline__ void sel_for_each_sampled(const float *__restrict__ src, uint32_t K, uint32_t S, F f) {
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
+    const uint32_t head = mis ? min(4u - mis, K) : 0u;
+    const uint32_t nPieces = ((K - head) / 4u) >> 5;                // whole pieces
+    const uint32_t nSamp = (nPieces + S - 1u) / S;                  // pieces 0, S, 2S, ...
+    const float4 *g4 = reinterpret_cast<const float4 *>(src + head);
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nW = blockDim.x >> 5;
+    for (uint32_t j = wid; j < nSamp; j += nW * (uint32_t)U) {
+        float4 q[U];
+        bool in[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t jj = j + (uint32_t)u * nW;
+            in[u] = jj < nSamp;
+            q[u] = in[u] ? __ldg(g4 + (size_t)jj * S * 32u + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (in[u]) { f(q[u].x); f(q[u].y); f(q[u].z); f(q[u].w); }
+    }
+}
+
+// Smaller cells are searched with exact rows: the sample's margin would make a tenth or more of such a cell a
+// candidate, and its second read comes from L2 anyway.
+constexpr uint32_t kSelSampleMinCell = 65536;
+// bins of a block's own histogram of a cell of K particles: about 64 particles per bin, at least one bin per thread
+__device__ __forceinline__ int sel_percell_bins(uint32_t K, int nThreads) {
+    const int nb = K > 131072u ? kSelBins2 : (K > 32768u ? 1024 : (K > 8192u ? 512 : 256));
+    return max(nb, nThreads);
+}
+
+template <int THREADS, int MINBLOCKS, int U = 4, bool SMP = false /* first attempt with sampled rows compiled in */>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float *__restrict__ x, const float *__restrict__ y,
                                                                     const float *__restrict__ z, LevelState lv, SelState ss,
                                                                     SelCtl sc, uint32_t nCells, uint32_t candCap, int preNb, SelDone dn,
                                                                     PreLeft *__restrict__ pre, uint32_t preTag,
                                                                     uint32_t chunk /* particles per partition block; 0: no records */,
-                                                                    uint32_t nLocal) {
+                                                                    uint32_t nLocal, int sampleS /* > 1: first attempt with sampled rows */,
+                                                                    float sampleZ) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     uint32_t *hist = reinterpret_cast<uint32_t *>(sel_smem);
     float *list = reinterpret_cast<float *>(hist + kSelBins2);
@@ -828,7 +1358,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float 
     __shared__ SelPerCellSmem sm;
     pdl_enter();
     const int tid = threadIdx.x, nThreads = (int)blockDim.x;
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(sc.passes_out, preNb ? 1 : 2);
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(sc.passes_out, preNb ? 1 : (sampleS > 1 ? 1 : 2));
     for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
         __syncthreads();
         const uint32_t act = lv.active[c], b = lv.bnd[c], K = lv.bnd[c + 1] - b;
@@ -836,160 +1366,196 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float 
         const float L = lv.mL[c], R = lv.mR[c];
         if (tid == 0) ss.flag[c] = 0u;
         if (!act) continue;
-        // Rounds: HIST (bins over [lo, lo + nb/scale)), RESOLVE; if the candidate bins hold more particles than the
-        // block stages (a dense clump inside a wide cell), zoom the bin function onto them and go again - any monotone
-        // bin function over the whole cell is valid, so a round needs nothing from the previous one but the interval.
-        // Round 0 with preNb != 0: the cell's row (preNb bins over the margins) was built by the partition of the
-        // previous level (NextHist) and is loaded instead of read from the particles.  The scan runs over
-        // nbScan >= nb bins; bins beyond nb are empty (an empty trailing bin never becomes the first candidate bin;
-        // as the last one it only means "up to the end", which sel_bin_bounds and the search treat the same way).
         const float *col = pick_col(ax, x, y, z) + b;
-        int nb = preNb ? preNb : max(K > 4096u ? kSelBins2 : 256, nThreads);
-        float lo = L, scale = sel_scale(L, R, nb);
-        int first = 0, last = -1;
-        uint32_t base = 0, K2 = 0;
-        bool ok = false;
-        int reads = 1;                                        // of the cell: HIST rounds + COMPACT
-        for (int round = 0; round < 3; ++round) {
-            const int nbScan = max(nb, nThreads);
-            const int per = nbScan / nThreads;                // 1, 2 or 8
-            const float nbm1 = (float)(nb - 1);
+        SelTarget tg;
+        tg.init(lv.total[c], lv.nleaf[c]);
+        // Attempt 0 (sampleS > 1): rows from a sample of the cell - one read of 1/S of it; the gathering read then counts
+        // the particles below the candidate bins exactly and the bracket must be proven by those numbers (SelSampleEst).
+        // Attempt 1: exact rows, as many zoom rounds as it takes.
+        for (int attempt = (SMP && sampleS > 1 && !preNb && K >= kSelSampleMinCell) ? 0 : 1; attempt < 2; ++attempt) {
+            const bool smp = SMP && attempt == 0;
+            // Rounds: HIST (bins over [lo, lo + nb/scale)), RESOLVE; if the candidate bins hold more particles than the
+            // block stages (a dense clump inside a wide cell), zoom the bin function onto them and go again - any monotone
+            // bin function over the whole cell is valid, so a round needs nothing from the previous one but the interval.
+            // Round 0 with preNb != 0: the cell's row (preNb bins over the margins) was built by the partition of the
+            // previous level (NextHist) and is loaded instead of read from the particles.  The scan runs over
+            // nbScan >= nb bins; bins beyond nb are empty (an empty trailing bin never becomes the first candidate bin;
+            // as the last one it only means "up to the end", which sel_bin_bounds and the search treat the same way).
+            int nb = preNb ? preNb : sel_percell_bins(K, nThreads);
+            float lo = L, scale = sel_scale(L, R, nb);
+            int first = 0, last = -1;
+            uint32_t base = 0, K2 = 0;
+            bool ok = false;
+            int reads = 1;                                        // of the cell: HIST rounds + COMPACT
+            for (int round = 0; round < (smp ? 1 : 3); ++round) {
+                const int nbScan = max(nb, nThreads);
+                const int per = nbScan / nThreads;                // 1, 2 or 8
+                const float nbm1 = (float)(nb - 1);
+                __syncthreads();
+                if (preNb && round == 0) for (int i = tid; i < nbScan; i += nThreads) hist[i] = i < nb ? __ldcg(ss.hist + (size_t)c * nb + i) : 0u;
+                else for (int i = tid; i < nbScan; i += nThreads) hist[i] = 0u;
+                if (tid == 0) { sm.first = nbScan; sm.last = -1; sm.base = 0u; sm.end = 0u; sm.nlist = 0u; sm.lowTot = 0u; }
+                __syncthreads();
+                // ---- HIST ----
+                if (!(preNb && round == 0)) {
+                    auto bin = [&](float v) {
+                        const float t = fminf(fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f), nbm1);      // == sel_bin(v, lo, scale, nb)
+                        atomicAdd(&hist[__float2int_rz(t)], 1u);
+                    };
+                    if (smp) sel_for_each_sampled<U>(col, K, (uint32_t)sampleS, bin);
+                    else { ++reads; sel_for_each<U>(col, K, bin); }
+                    __syncthreads();
+                }
+                // ---- RESOLVE ----
+                uint32_t h[8];
+                uint32_t sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { h[j] = (j < per) ? hist[tid * per + j] : 0u; sum += h[j]; }
+                uint32_t total;
+                const uint32_t excl = sel_block_scan(sum, sm.w, total);
+                SelSampleEst se;
+                se.init(total, K, sampleZ);
+                uint32_t pA = 0u, pB = 0u;
+                if (smp) {      // block-uniform: critical sample prefixes by one warp
+                    if (tid < 32) {
+                        sel_sample_crit(se, tg, total, pA, pB);
+                        if (tid == 0) { sm.pA = pA; sm.pB = pB; }
+                    }
+                    __syncthreads();
+                    pA = sm.pA; pB = sm.pB;
+                }
+                int myFirst = nbScan, myLast = -1;
+                {
+                    uint32_t p = excl;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < per) {
+                            const uint32_t pn = p + h[j];
+                            const int bb = tid * per + j;
+                            if (smp ? (pn >= pA) : (tg.diff(pn) > -3)) myFirst = min(myFirst, bb);
+                            if (smp ? (p <= pB) : (tg.diff(p) < 3)) myLast = max(myLast, bb);
+                            p = pn;
+                        }
+                    }
+                }
+                if (myFirst < nbScan) atomicMin(&sm.first, myFirst);
+                if (myLast >= 0) atomicMax(&sm.last, myLast);
+                __syncthreads();
+                first = sm.first; last = sm.last;
+                {
+                    uint32_t p = excl;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < per) {
+                            const int bb = tid * per + j;
+                            if (bb == first) sm.base = p;
+                            p += h[j];
+                            if (bb == last) sm.end = p;
+                        }
+                    }
+                }
+                __syncthreads();
+                base = sm.base; K2 = sm.end - base;
+                if (!(first <= last)) break;                    // cannot happen (tests/test_select_model.py::ambiguous_range)
+                if (smp) {      // estimated number of candidates, with headroom: the list must not overflow
+                    const float est = (float)K2 * se.sc;
+                    ok = est * 1.125f + 64.f <= (float)candCap;
+                    break;
+                }
+                if (K2 <= candCap) { ok = true; break; }
+                // ---- zoom onto the candidate bins (widened by 1/16 of their width on either side) ----
+                const float a = __fadd_rn(lo, __fdiv_rn((float)first, scale));
+                const float e = __fadd_rn(lo, __fdiv_rn((float)min(last + 1, nb), scale));
+                const float w = __fsub_rn(e, a);
+                const int nbNew = max(kSelBins2, nThreads);
+                const float loNew = __fsub_rn(a, w * 0.0625f);
+                const float scNew = sel_scale(loNew, __fadd_rn(e, w * 0.0625f), nbNew);
+                if (!(scale > 0.f) || !(w > 0.f) || !(scNew > scale)) break;     // degenerate box / no resolution left: ties
+                lo = loNew; scale = scNew; nb = nbNew;
+            }
+            if (!ok) {
+                if (smp) continue;       // the sample's candidate bins are too wide for the block: exact rows
+                // too many candidates for one block even after zooming (massive ties): the iterative search takes the cell
+                if (tid == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
+                break;
+            }
+            // ---- COMPACT: another read (L2), candidates into shared memory ----
+            if (tid < 32) {
+                float a, bb;
+                sel_value_bounds_warp((uint32_t)first, (uint32_t)last, lo, scale, nb, a, bb);
+                if (tid == 0) { sm.vLo = a; sm.vHi = bb; }
+            }
             __syncthreads();
-            if (preNb && round == 0) for (int i = tid; i < nbScan; i += nThreads) hist[i] = i < nb ? __ldcg(ss.hist + (size_t)c * nb + i) : 0u;
-            else for (int i = tid; i < nbScan; i += nThreads) hist[i] = 0u;
-            if (tid == 0) { sm.first = nbScan; sm.last = -1; sm.base = 0u; sm.end = 0u; sm.nlist = 0u; }
-            __syncthreads();
-            // ---- HIST ----
-            if (!(preNb && round == 0)) {
-                ++reads;
-                sel_for_each<U>(col, K, [&](float v) {
-                    const float t = fminf(fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f), nbm1);      // == sel_bin(v, lo, scale, nb)
-                    atomicAdd(&hist[__float2int_rz(t)], 1u);
-                });
+            const float vLo = sm.vLo, vHi = sm.vHi;
+            // With `pre`: the cell is read segment by segment (pieces between the partition's chunk boundaries), so that the
+            // left count of every chunk that ends inside this cell is known afterwards: particles below the candidate bins
+            // + the segment's candidates left of the cut.
+            const uint32_t e = b + K;
+            int nSeg = 1;
+            if (pre && chunk) {
+                const uint32_t k0 = b / chunk, k1 = (e - 1u) / chunk;      // chunks of the first / last particle (K > 0 here)
+                nSeg = (int)(k1 - k0 + 1u);
+            }
+            const bool segs = pre && chunk && nSeg <= kSelMaxSeg && K > 0u;
+            if (!segs) nSeg = 1;
+            if (segs) {
+                if (tid < kSelMaxSeg) sm.segBelow[tid] = 0u;
                 __syncthreads();
             }
-            // ---- RESOLVE ----
-            SelTarget tg;
-            tg.init(lv.total[c], lv.nleaf[c]);
-            uint32_t h[8];
-            uint32_t sum = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { h[j] = (j < per) ? hist[tid * per + j] : 0u; sum += h[j]; }
-            uint32_t total;
-            const uint32_t excl = sel_block_scan(sum, sm.w, total);
-            int myFirst = nbScan, myLast = -1;
-            {
-                uint32_t p = excl;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (j < per) {
-                        const uint32_t pn = p + h[j];
-                        const int bb = tid * per + j;
-                        if (tg.diff(pn) > -3) myFirst = min(myFirst, bb);
-                        if (tg.diff(p) < 3) myLast = max(myLast, bb);
-                        p = pn;
-                    }
-                }
-            }
-            if (myFirst < nbScan) atomicMin(&sm.first, myFirst);
-            if (myLast >= 0) atomicMax(&sm.last, myLast);
-            __syncthreads();
-            first = sm.first; last = sm.last;
-            {
-                uint32_t p = excl;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (j < per) {
-                        const int bb = tid * per + j;
-                        if (bb == first) sm.base = p;
-                        p += h[j];
-                        if (bb == last) sm.end = p;
-                    }
-                }
-            }
-            __syncthreads();
-            base = sm.base; K2 = sm.end - base;
-            if (!(first <= last)) break;                    // cannot happen (tests/test_select_model.py::ambiguous_range)
-            if (K2 <= candCap) { ok = true; break; }
-            // ---- zoom onto the candidate bins (widened by 1/16 of their width on either side) ----
-            const float a = __fadd_rn(lo, __fdiv_rn((float)first, scale));
-            const float e = __fadd_rn(lo, __fdiv_rn((float)min(last + 1, nb), scale));
-            const float w = __fsub_rn(e, a);
-            const int nbNew = max(kSelBins2, nThreads);
-            const float loNew = __fsub_rn(a, w * 0.0625f);
-            const float scNew = sel_scale(loNew, __fadd_rn(e, w * 0.0625f), nbNew);
-            if (!(scale > 0.f) || !(w > 0.f) || !(scNew > scale)) break;     // degenerate box / no resolution left: ties
-            lo = loNew; scale = scNew; nb = nbNew;
-        }
-        if (!ok) {       // too many candidates for one block even after zooming (massive ties): the iterative search takes the cell
-            if (tid == 0) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
-            continue;
-        }
-        // ---- COMPACT: another read (L2), candidates into shared memory ----
-        float fLo, fHi;
-        sel_bin_bounds((uint32_t)first, (uint32_t)last, nb, fLo, fHi);
-        // With `pre`: the cell is read segment by segment (pieces between the partition's chunk boundaries), so that the
-        // left count of every chunk that ends inside this cell is known afterwards: particles below the candidate bins
-        // + the segment's candidates left of the cut.
-        const uint32_t e = b + K;
-        int nSeg = 1;
-        if (pre && chunk) {
-            const uint32_t k0 = b / chunk, k1 = (e - 1u) / chunk;      // chunks of the first / last particle (K > 0 here)
-            nSeg = (int)(k1 - k0 + 1u);
-        }
-        const bool segs = pre && chunk && nSeg <= kSelMaxSeg && K > 0u;
-        if (!segs) nSeg = 1;
-        if (segs) {
-            if (tid < kSelMaxSeg) sm.segBelow[tid] = 0u;
-            __syncthreads();
-        }
-        for (int sgi = 0; sgi < nSeg; ++sgi) {
-            uint32_t s0 = b, s1 = e;
-            if (segs) {
-                const uint32_t k = b / chunk + (uint32_t)sgi;
-                s0 = max(b, k * chunk);
-                s1 = min(e, (k + 1u) * chunk);
-            }
-            unsigned lows = 0u;
-            sel_for_each<U>(col + (s0 - b), s1 - s0, [&](float v) {
-                const float t = fmaxf(__fmul_rn(__fsub_rn(v, lo), scale), 0.f);
-                if (t >= fLo && t < fHi) list[atomicAdd(&sm.nlist, 1u)] = v;
-                lows += (t < fLo) ? 1u : 0u;
-            });
-            if (segs) {
-                lows = __reduce_add_sync(0xffffffffu, lows);
-                __syncthreads();                                  // the segment's candidates are all in the list
-                if ((tid & 31) == 0 && lows) atomicAdd(&sm.segBelow[sgi], lows);
-                if (tid == 0) sm.segListEnd[sgi] = sm.nlist;
-                __syncthreads();                                  // ... before anyone appends the next segment's
-            }
-        }
-        __syncthreads();
-        // ---- FINISH ----
-        const bool done = sel_block_search(list, K2, base, 1, lo, scale, nb, first, last, hist, amb, lv, ss, sc, c, reads, sm.search);
-        if (segs && done) {       // block-uniform
-            const float cutf = mid_cut(sm.search.resL, sm.search.resR);
-            if (tid < kSelMaxSeg) sm.segLeft[tid] = 0u;
-            __syncthreads();
             for (int sgi = 0; sgi < nSeg; ++sgi) {
-                const uint32_t l0 = sgi ? sm.segListEnd[sgi - 1] : 0u, l1 = sm.segListEnd[sgi];
-                uint32_t m = 0;
-                for (uint32_t i = l0 + tid; i < l1; i += nThreads) m += (list[i] < cutf) ? 1u : 0u;
-                m = __reduce_add_sync(0xffffffffu, m);
-                if ((tid & 31) == 0 && m) atomicAdd(&sm.segLeft[sgi], m);
-            }
-            __syncthreads();
-            if (tid < nSeg) {
-                const uint32_t k = b / chunk + (uint32_t)tid;
-                const uint32_t segEnd = min(e, (k + 1u) * chunk);
-                // the segment is chunk k's trailing segment iff it reaches the chunk's end (the last chunk ends at nLocal)
-                if (segEnd == (k + 1u) * chunk || segEnd == nLocal) {
-                    PreLeft P;
-                    P.tag = preTag; P.cell = c; P.below = sm.segBelow[tid] + sm.segLeft[tid]; P.gbase = 0u; P.tot = 0u; P.kind = 1u;
-                    P.pad_[0] = P.pad_[1] = 0u;
-                    pre[k] = P;
+                uint32_t s0 = b, s1 = e;
+                if (segs) {
+                    const uint32_t k = b / chunk + (uint32_t)sgi;
+                    s0 = max(b, k * chunk);
+                    s1 = min(e, (k + 1u) * chunk);
+                }
+                // (exact rows never overfill the list; a sampled estimate may)
+                unsigned lows = sel_compact_pass<U>(col + (s0 - b), s1 - s0, vLo, vHi, list, &sm.nlist, candCap);
+                if (segs || smp) {
+                    lows = __reduce_add_sync(0xffffffffu, lows);
+                    if (smp && (tid & 31) == 0 && lows) atomicAdd(&sm.lowTot, lows);
+                }
+                if (segs) {
+                    __syncthreads();                                  // the segment's candidates are all in the list
+                    if ((tid & 31) == 0 && lows) atomicAdd(&sm.segBelow[sgi], lows);
+                    if (tid == 0) sm.segListEnd[sgi] = sm.nlist;
+                    __syncthreads();                                  // ... before anyone appends the next segment's
                 }
             }
+            __syncthreads();
+            if (smp) {
+                // exact numbers of the gathering read: they must fit the list and prove the bracket, else exact rows
+                base = sm.lowTot; K2 = sm.nlist;
+                const bool proven = (first == 0 || tg.diff(base) <= -3) && (last + 1 >= nb || tg.diff(base + K2) >= 3);
+                if (K2 > candCap || !proven) continue;
+            }
+            // ---- FINISH ----
+            const bool done = sel_block_search(list, K2, base, 1, lo, scale, nb, first, last, hist, amb, lv, ss, sc, c, reads, sm.search);
+            if (segs && done) {       // block-uniform
+                const float cutf = mid_cut(sm.search.resL, sm.search.resR);
+                if (tid < kSelMaxSeg) sm.segLeft[tid] = 0u;
+                __syncthreads();
+                for (int sgi = 0; sgi < nSeg; ++sgi) {
+                    const uint32_t l0 = sgi ? sm.segListEnd[sgi - 1] : 0u, l1 = sm.segListEnd[sgi];
+                    uint32_t m = 0;
+                    for (uint32_t i = l0 + tid; i < l1; i += nThreads) m += (list[i] < cutf) ? 1u : 0u;
+                    m = __reduce_add_sync(0xffffffffu, m);
+                    if ((tid & 31) == 0 && m) atomicAdd(&sm.segLeft[sgi], m);
+                }
+                __syncthreads();
+                if (tid < nSeg) {
+                    const uint32_t k = b / chunk + (uint32_t)tid;
+                    const uint32_t segEnd = min(e, (k + 1u) * chunk);
+                    // the segment is chunk k's trailing segment iff it reaches the chunk's end (the last chunk ends at nLocal)
+                    if (segEnd == (k + 1u) * chunk || segEnd == nLocal) {
+                        PreLeft P;
+                        P.tag = preTag; P.cell = c; P.below = sm.segBelow[tid] + sm.segLeft[tid]; P.gbase = 0u; P.tot = 0u; P.kind = 1u;
+                        P.pad_[0] = P.pad_[1] = 0u;
+                        pre[k] = P;
+                    }
+                }
+            }
+            break;
         }
     }
     sel_report_done(dn, ss.n_flagged);

@@ -178,6 +178,61 @@ def test_signed_zero_coordinates(orb, oracle):
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+@pytest.mark.parametrize("stride,z", [("1", "6"), ("8", "6"), ("4", "5"), ("8", "0.25"), ("16", "0")])
+@pytest.mark.parametrize("n,d,gen", [(1 << 22, 1 << 11, "uniform"), (1 << 21, 1 << 6, "uniform"), (1 << 22, 1 << 10, "gaussian"),
+                                     (1 << 21, 1 << 9, "plummer"), (3_000_017, 1 << 7, "uniform"), (1 << 23, 1 << 8, "uniform")])
+def test_build_bit_exact_with_sampled_rows(orb, oracle, n, d, gen, stride, z, monkeypatch):
+    """Sampled histogram rows (ORB_SAMPLE_STRIDE > 1, the default): HIST bins a sample, RESOLVE widens the candidate bins by
+    z standard deviations, the gathering pass counts exactly and the bracket must be proven by the exact numbers.  The
+    tree never depends on the sample: stride 1 (exact rows), the default, and margins far too small (z = 0.25, z = 0:
+    brackets fail, k_sel_percell searches again with exact rows, k_sel_finish leaves the cell to the iterative search)
+    all give the oracle's tree, ranges and particle order - streaming levels (private candidate regions + gather) and
+    one-block-per-cell levels."""
+    monkeypatch.setenv("ORB_SAMPLE_STRIDE", stride)
+    monkeypatch.setenv("ORB_SAMPLE_Z", z)
+    monkeypatch.setenv("ORB_SAMPLE_MIN_LOCAL", "0")          # (by default only builds of >= 2^25 particles per GPU sample,
+    monkeypatch.setenv("ORB_SAMPLE_MAX_AVG", str(1 << 30))   #  and only cells of <= 2^25 particles)
+    x, y, z_ = orb.generate_uniform(n) if gen == "uniform" else orb.generate_clustered(n, gen)
+    ref = oracle.build(x, y, z_, d, ties=oracle.TIES_CANONICAL)
+    with orb.Orb(n, d) as ctx:
+        ctx.upload(x, y, z_)
+        heap, st = ctx.build()
+        gx, gy, gz = ctx.download()
+        rng = ctx.ranges()
+    print(f"stride={stride} z={z}: passes {list(st.passes[:st.n_levels])} fallback cells {st.search_fallback_cells} ms {st.ms_total:.3f}")
+    assert list(st.iters[:st.n_levels]) == list(ref["stats"].iters[:st.n_levels])
+    assert list(st.not_found[:st.n_levels]) == list(ref["stats"].not_found[:st.n_levels])
+    assert heap.tobytes() == ref["heap"].tobytes()
+    assert np.array_equal(rng, ref["ranges"][0])
+    for a, b in ((gx, ref["x"]), (gy, ref["y"]), (gz, ref["z"])):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    if float(z) >= 5 and gen == "uniform":
+        assert st.search_fallback_cells == 0
+
+
+def test_sampled_rows_on_presorted_particles(orb, oracle, monkeypatch):
+    """Particles sorted along x: a positional sample of a cell is no random sample of its coordinates, the brackets
+    fail, the level falls back and the build switches to exact rows - same tree as the oracle's."""
+    n, d = 1 << 21, 1 << 8
+    monkeypatch.setenv("ORB_SAMPLE_MIN_LOCAL", "0")
+    monkeypatch.setenv("ORB_SAMPLE_MAX_AVG", str(1 << 30))
+    x, y, z = orb.generate_uniform(n)
+    o = np.argsort(x, kind="stable")
+    x, y, z = (np.ascontiguousarray(a[o]) for a in (x, y, z))
+    ref = oracle.build(x, y, z, d, ties=oracle.TIES_CANONICAL)
+    with orb.Orb(n, d) as ctx:
+        ctx.upload(x, y, z)
+        heap, st = ctx.build()
+        gx, gy, gz = ctx.download()
+        rng = ctx.ranges()
+    print(f"presorted: passes {list(st.passes[:st.n_levels])} fallback cells {st.search_fallback_cells}")
+    assert list(st.iters[:st.n_levels]) == list(ref["stats"].iters[:st.n_levels])
+    assert heap.tobytes() == ref["heap"].tobytes()
+    assert np.array_equal(rng, ref["ranges"][0])
+    for a, b in ((gx, ref["x"]), (gy, ref["y"]), (gz, ref["z"])):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 @pytest.mark.parametrize("n,d", [(1 << 20, 8), (1 << 16, 32)])
 def test_search_fallback_on_massive_ties(orb, oracle, n, d):
     """Thousands of particles tie exactly where the cut has to go: the selection-based search cannot isolate the

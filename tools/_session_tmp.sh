@@ -1,8 +1,12 @@
-out=gpurun_out; tag=r02h
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > $out/${tag}_parity.txt 2>&1; echo "parity rc=$?"; tail -3 $out/${tag}_parity.txt
-for b in 1 0 1 0; do echo "== C3 bulk=$b"; ORB_PART_BULK=$b timeout 300 python tools/build_once.py 27 16 7 2>&1 | tail -1; done
-for b in 1 0; do echo "== C3 bulk=$b prefuse0"; ORB_PREFUSE=0 ORB_PART_BULK=$b timeout 300 python tools/build_once.py 27 16 7 2>&1 | tail -1; done
-for b in 1 0; do echo "== C2 bulk=$b"; ORB_PART_BULK=$b timeout 300 python tools/build_once.py 24 12 9 2>&1 | tail -1; done
-for b in 1 0; do ORB_PART_BULK=$b ORB_PROFILE=1 ORB_DEBUG_SELECT=1 timeout 300 python tools/build_once.py 27 16 2 > $out/${tag}_c3_levels_bulk$b.txt 2>&1; done
-echo "== 27/20 self-mode"; ORB_MR_SELF=1 timeout 300 python tools/build_once.py 27 20 3 2>&1 | tail -1
-ORB_MR_SELF=1 ORB_PROFILE=1 ORB_DEBUG_SELECT=1 timeout 300 python tools/build_once.py 27 20 2 > $out/${tag}_2720_self_levels.txt 2>&1
+out=gpurun_out; tag=r02p
+timeout 1200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 300 --durations=3 > $out/${tag}_parity.txt 2>&1; echo "parity rc=$?"; tail -6 $out/${tag}_parity.txt | cut -c1-300
+run() { echo "== $1 $2 [$3]"; env $3 timeout 300 python tools/build_once.py $1 $2 9 2>&1 | tail -1; }
+run 27 16 "ORB_X=0"
+run 24 12 "ORB_X=0"
+run 27 16 "ORB_SAMPLE_Z=4"
+run 27 16 "ORB_SAMPLE_Z=6"
+echo "== C4g"; timeout 300 python tools/build_once.py 26 14 5 gaussian 2>&1 | tail -1
+echo "== C4p"; timeout 300 python tools/build_once.py 26 14 5 plummer 2>&1 | tail -1
+ORB_PROFILE=1 ORB_DEBUG_SELECT=1 timeout 300 python tools/build_once.py 27 16 2 > $out/${tag}_c3_levels.txt 2>&1
+ORB_PROFILE=1 ORB_DEBUG_SELECT=1 timeout 300 python tools/build_once.py 24 12 2 > $out/${tag}_c2_levels.txt 2>&1
+timeout 900 python -m pytest tests -q -m gpu --deselect tests/test_gpu_parity.py --timeout 600 --durations=3 > $out/${tag}_gpu_rest.txt 2>&1; echo "rest rc=$?"; tail -6 $out/${tag}_gpu_rest.txt | cut -c1-300

@@ -17,5 +17,5 @@ for rep in range(1 + reps):
     heap, st = ctx.build()
     if rep:
         ms.append(st.ms_total)
-print("ms median %.4f min %.4f" % (float(np.median(ms)), min(ms)), "passes", list(st.passes[:st.n_levels]),
+print("ms median %.4f min %.4f" % ((float(np.median(ms)), min(ms)) if ms else (0.0, 0.0)), "passes", list(st.passes[:st.n_levels]),
       "fallback_cells", st.search_fallback_cells)
