@@ -119,7 +119,7 @@ class LevelPlan(C.Structure):
         ("slot_words", C.c_uint32),
         ("hist_words", C.c_uint64),
         ("prefuse_bins", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("sample_stride", C.c_int32),
     ]
 
 

@@ -168,6 +168,7 @@ struct orb_ctx {
     // 160 000 candidates), block-searched cells of at least 2^16 (kSelSampleMinCell).
     uint64_t sampleMinLocal = 1ull << 25;   // ORB_SAMPLE_MIN_LOCAL
     uint64_t sampleMaxAvg = 1ull << 25;     // ORB_SAMPLE_MAX_AVG
+    uint32_t sampleMinCell = orb::kSelSampleMinCell;   // ORB_SAMPLE_MIN_CELL: block-searched cells of fewer particles use exact rows
     int chunkOcc = 2;              // ORB_CHUNK_OCC: blocks per SM of the chunking the search's last pass and the cooperative partition share
                                    // (measured: the partition streams 10 % faster with 2 x 148 chunks than with 3 x 148)
     bool selLowOcc = false;        // ORB_SELECT_LOW_OCC=1: k_sel_percell with 64 registers per thread (4 x 256 / 2 x 512 threads per SM, no spills)
@@ -703,7 +704,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
         int occ = 1;
         // (the sampled first attempt is a separate instantiation: cells below kSelSampleMinCell and builds without sampling
         //  run the plain one)
-        const int percellS = (c->nLocal / nCells >= (uint64_t)kSelSampleMinCell) ? pl.sampleS : 1;
+        const int percellS = (c->nLocal / nCells >= (uint64_t)c->sampleMinCell) ? pl.sampleS : 1;
         auto kern = percellS > 1
                         ? (pl.variant == 2 ? k_sel_percell<1024, 1, 8, true> : (pl.variant == 1 ? k_sel_percell<512, 2, 8, true>
                            : (pl.threads == 512 ? k_sel_percell<512, 3, 4, true> : k_sel_percell<256, 6, 4, true>)))
@@ -715,7 +716,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
         if ((rc = count_event_begin(c))) return rc;
         CK(launch_pdl(c, kern, dim3(grid), dim3(pl.threads), smem, x, y, z, c->lv, ss, sc, nCells, pl.cellCap, preNb, dn, pre, preTag,
                       c->chunkTiles * (uint32_t)kCountTile, (uint32_t)c->nLocal,
-                      percellS, c->sampleZ));
+                      percellS, c->sampleZ, c->sampleMinCell));
         if ((rc = count_event_end(c))) return rc;
         c->nCountLaunch++;
     } else {
@@ -1620,6 +1621,8 @@ static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_l
     if (sml && atoll(sml) >= 0) c->sampleMinLocal = (uint64_t)atoll(sml);
     const char *sma = getenv("ORB_SAMPLE_MAX_AVG");
     if (sma && atoll(sma) >= 1) c->sampleMaxAvg = (uint64_t)atoll(sma);
+    const char *smc = getenv("ORB_SAMPLE_MIN_CELL");
+    if (smc && atoll(smc) >= 4096) c->sampleMinCell = (uint32_t)atoll(smc);
     const char *cko = getenv("ORB_CHUNK_OCC");
     if (cko && atoi(cko) >= 1 && atoi(cko) <= 3) c->chunkOcc = atoi(cko);
     const char *slo = getenv("ORB_SELECT_LOW_OCC");
@@ -1768,6 +1771,9 @@ int orb_plan_level(uint64_t n_local, uint64_t n_global, uint64_t n_local_min, in
     c->occPersist[3] = 1;
     c->prefuseHist = prefuse_mode < 0 ? -1 : (prefuse_mode ? 1 : 0);
     c->d_slots_g = reinterpret_cast<float *>(uintptr_t(16));     // "allocated" (sel_plan_mr only tests the pointer)
+    c->d_visits = reinterpret_cast<orb::SelVisitRec *>(uintptr_t(16));      // (likewise sampling_on)
+    const char *sst = getenv("ORB_SAMPLE_STRIDE");
+    if (sst && atoi(sst) >= 1 && atoi(sst) <= 64) c->sampleS = atoi(sst);
     c->nLocalMax = c->nLocalMin;      // (the plan never reads it: buffers are sized from it, decisions use the minimum)
     c->peerEnabled = n_ranks > 1;     // plan of the peer-memory protocol (orb_exchange.cuh)
     c->slotTotal = std::max<size_t>(std::max<size_t>(kSelSlotWordsTotal, 64 * (size_t)c->maxLevelCells), (((size_t)n_local_min / 8) + 63) & ~(size_t)63);
@@ -1786,12 +1792,14 @@ int orb_plan_level(uint64_t n_local, uint64_t n_global, uint64_t n_local_min, in
         out->hist_words = mr.histWords;
     } else if (level_can_select(c.get(), n_cells, M)) {
         const SelPlan p = sel_plan(c.get(), n_cells, pre);
+        out->sample_stride = (p.sampleS > 1 && (!p.cellsInSmem || n_local / n_cells >= (uint64_t)c->sampleMinCell)) ? p.sampleS : 1;
         out->search = p.cellsInSmem ? 2 : 1;
         out->hist_bins = (p.cellsInSmem && !pre) ? 0 : p.nb1;
         out->cand_cap = p.cellsInSmem ? p.cellCap : p.candCap;
         out->hist_words = p.histWords;
     }
     c->d_slots_g = nullptr;
+    c->d_visits = nullptr;
     return ORB_OK;
 }
 

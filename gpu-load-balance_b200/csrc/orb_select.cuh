@@ -816,17 +816,18 @@ struct SelSrcPieces {
     const uint32_t *pOff, *pCnt, *pPos;      // shared memory
     uint32_t K;
     __device__ __forceinline__ const float *shared_ptr() const { return nullptr; }
-    // thread t takes the values t, t + nT, ... of the concatenation; its piece index only ever advances.  Eight loads
+    // thread t takes the values t, t + nT, ... of the concatenation; its piece index only ever advances.  kFly loads
     // in flight per thread (the pieces lie in L2: the pass is a few latencies, not bandwidth).
+    static constexpr int kFly = 16;
     template <typename F>
     __device__ __forceinline__ void for_each(F f) const {
         const uint32_t nT = blockDim.x;
         uint32_t p = 0;
-        for (uint32_t i = threadIdx.x; i < K; i += 8u * nT) {
-            float q[8];
-            bool in[8];
+        for (uint32_t i = threadIdx.x; i < K; i += (uint32_t)kFly * nT) {
+            float q[kFly];
+            bool in[kFly];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < kFly; ++u) {
                 const uint32_t ii = i + (uint32_t)u * nT;
                 in[u] = ii < K;
                 q[u] = 0.f;
@@ -836,7 +837,7 @@ struct SelSrcPieces {
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < kFly; ++u)
                 if (in[u]) f(q[u]);
         }
     }
@@ -1336,7 +1337,7 @@ __device__ __forceinline__ void sel_for_each_sampled(const float *__restrict__ s
 
 // Smaller cells are searched with exact rows: the sample's margin would make a tenth or more of such a cell a
 // candidate, and its second read comes from L2 anyway.
-constexpr uint32_t kSelSampleMinCell = 65536;
+constexpr uint32_t kSelSampleMinCell = 65536;      // (default of ORB_SAMPLE_MIN_CELL)
 // bins of a block's own histogram of a cell of K particles: about 64 particles per bin, at least one bin per thread
 __device__ __forceinline__ int sel_percell_bins(uint32_t K, int nThreads) {
     const int nb = K > 131072u ? kSelBins2 : (K > 32768u ? 1024 : (K > 8192u ? 512 : 256));
@@ -1350,7 +1351,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float 
                                                                     PreLeft *__restrict__ pre, uint32_t preTag,
                                                                     uint32_t chunk /* particles per partition block; 0: no records */,
                                                                     uint32_t nLocal, int sampleS /* > 1: first attempt with sampled rows */,
-                                                                    float sampleZ) {
+                                                                    float sampleZ, uint32_t sampleMinCell) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     uint32_t *hist = reinterpret_cast<uint32_t *>(sel_smem);
     float *list = reinterpret_cast<float *>(hist + kSelBins2);
@@ -1372,7 +1373,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_sel_percell(const float 
         // Attempt 0 (sampleS > 1): rows from a sample of the cell - one read of 1/S of it; the gathering read then counts
         // the particles below the candidate bins exactly and the bracket must be proven by those numbers (SelSampleEst).
         // Attempt 1: exact rows, as many zoom rounds as it takes.
-        for (int attempt = (SMP && sampleS > 1 && !preNb && K >= kSelSampleMinCell) ? 0 : 1; attempt < 2; ++attempt) {
+        for (int attempt = (SMP && sampleS > 1 && !preNb && K >= sampleMinCell) ? 0 : 1; attempt < 2; ++attempt) {
             const bool smp = SMP && attempt == 0;
             // Rounds: HIST (bins over [lo, lo + nb/scale)), RESOLVE; if the candidate bins hold more particles than the
             // block stages (a dense clump inside a wide cell), zoom the bin function onto them and go again - any monotone

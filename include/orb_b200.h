@@ -103,7 +103,8 @@ typedef struct orb_level_plan {
     uint32_t slot_words;   /* several ranks: words of one rank's candidate slot per cell (last word = count) */
     uint64_t hist_words;   /* words of histogram rows the level needs in global memory */
     int32_t prefuse_bins;  /* != 0: the previous level's partition builds this level's rows with this many bins */
-    int32_t reserved_;
+    int32_t sample_stride; /* > 1: the rows come from a sample (every sample_stride-th tile / piece of a cell), the gathering
+                            * pass proves the bracket with exact counts (one rank, >= 2^25 particles per GPU) */
 } orb_level_plan;
 int orb_plan_level(uint64_t n_local, uint64_t n_global, uint64_t n_local_min, int n_ranks, uint32_t n_leaf_cells,
                    uint32_t n_cells, int prefuse_mode, orb_level_plan *out);

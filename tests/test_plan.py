@@ -79,14 +79,35 @@ def test_single_rank_plan_bounds(orb, x):
 
 
 def test_automatic_prefuse_policy(orb):
-    """One rank: the partition pre-builds the next level's rows from 2^25 particles on; several ranks: always."""
+    """Several ranks: the partition pre-builds the next level's rows wherever the level streams.  One rank: never by
+    default - below 2^25 particles per GPU a HIST pass is cheaper than binning in the partition, from 2^25 on the rows
+    come from a sample instead (test_sampled_rows_policy); ORB_PREFUSE=1 still forces it."""
     small = [orb.plan_level(1 << 24, 1 << l, 1 << 12).prefuse_bins for l in range(1, 11)]
     big = [orb.plan_level(1 << 27, 1 << l, 1 << 16).prefuse_bins for l in range(1, 15)]
     forced = [orb.plan_level(1 << 24, 1 << l, 1 << 12, prefuse=1).prefuse_bins for l in range(1, 11)]
+    forced_big = [orb.plan_level(1 << 27, 1 << l, 1 << 16, prefuse=1).prefuse_bins for l in range(1, 15)]
     multi = [orb.plan_level(1 << 24, 1 << l, 1 << 12, n_ranks=2).prefuse_bins for l in range(1, 11)]
-    assert not any(small)
-    assert big[:2] == [0, 0] and all(big[3:])          # 2^26 / 2^25-particle cells want more than 1024 bins: separate pass
+    assert not any(small) and not any(big)
     assert all(forced)
+    assert forced_big[:2] == [0, 0] and all(forced_big[3:])   # 2^26 / 2^25-particle cells want more than 1024 bins: separate pass
     # 2 x 2^24 in 2 cells: 2048 bins wanted, more than the partition holds; from 512 cells on the cells are searched by
     # one block each (their rows come from k_xd_hist, not from the partition)
     assert multi[0] == 0 and all(multi[1:8]) and not any(multi[8:])
+
+
+def test_sampled_rows_policy(orb):
+    """Sampled histogram rows: one rank, builds of at least 2^25 particles per GPU; streaming levels
+    whose cells hold at most 2^25 particles, block-searched cells of at least 2^16; never with several ranks, never
+    where the partition-built rows are forced."""
+    c3 = [orb.plan_level(1 << 27, 1 << l, 1 << 16) for l in range(0, 15)]
+    assert [p.sample_stride for p in c3] == [1, 1] + [8] * 10 + [1, 1, 1]
+    assert [p.search for p in c3] == [1] * 7 + [2] * 8
+    # the sampled streaming levels bin finely (the margin, not the bin width, sets the number of candidates)
+    assert all(p.hist_bins == 8192 for p in c3[2:5]) and all(p.hist_words == (1 << l) * p.hist_bins for l, p in enumerate(c3[:7]))
+    assert all(p.cand_cap <= 49152 for p in c3)
+    c2 = [orb.plan_level(1 << 24, 1 << l, 1 << 12) for l in range(0, 11)]
+    assert all(p.sample_stride == 1 for p in c2)
+    c4 = [orb.plan_level(1 << 26, 1 << l, 1 << 14) for l in range(0, 13)]
+    assert [p.sample_stride for p in c4] == [1] + [8] * 10 + [1, 1]
+    assert all(orb.plan_level(1 << 27, 1 << l, 1 << 16, n_ranks=2).sample_stride <= 1 for l in range(0, 15))
+    assert all(orb.plan_level(1 << 27, 1 << l, 1 << 16, prefuse=1).sample_stride <= 1 for l in range(0, 15))
