@@ -296,3 +296,166 @@ def test_randomised_inputs_and_capacities():
                 answered += 1
                 assert same(got, want), ("zoom", kind, n, nleaf, nb1, got, want)
     assert answered > 150
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Sampled rows (csrc/orb_select.cuh: SelSampleEst, sel_sample_crit, the proof in k_sel_finish / k_sel_percell) and the
+# value bounds that replace the bin test in the gathering pass (sel_bin_threshold, sel_value_bounds).
+# ---------------------------------------------------------------------------------------------------------------
+def sample_bound(p, ns, n_tot, z, upper):
+    """SelSampleEst::bound: bound on the cell's exact prefix count given the sample's prefix count p."""
+    if ns <= 0:
+        return n_tot if upper else 0
+    sc = f32(n_tot) / f32(ns)
+    pf = f32(p)
+    sd = sc * f32(math.sqrt(max(float(pf * (f32(ns) - pf)), 0.0) / float(ns)))
+    m = f32(z) * sd + f32(2) * sc + f32(8)
+    val = pf * sc + m if upper else pf * sc - m
+    return int(min(max(float(val), 0.0), float(n_tot)))
+
+
+def sampled_select(v, L, R, nleaf, stride, z, nb1=1024, piece=128):
+    """HIST on every stride-th piece of the cell, RESOLVE with margins, exact counts from the gathering pass, proof,
+    search on the candidates.  Returns (result or None, proven)."""
+    n = v.size
+    prod = make_prod(n, nleaf)
+    lo1, s1 = bin_params(L, R, nb1)
+    idx = np.arange(n)
+    smp = v[(idx // piece) % stride == 0]
+    ns = smp.size
+    bs = sel_bin(smp, lo1, s1, nb1) if ns else np.zeros(0, np.int64)
+    ps = np.concatenate([[0], np.cumsum(np.bincount(bs, minlength=nb1))])
+    # critical sample prefixes (sel_sample_crit), then two integer compares per bin
+    pA = next(p for p in range(ns + 1) if diff_of(sample_bound(p, ns, n, z, True), prod) > -3)
+    pB = next(p for p in range(ns, -1, -1) if diff_of(sample_bound(p, ns, n, z, False), prod) < 3)
+    firsts = [b for b in range(nb1) if ps[b + 1] >= pA]
+    lasts = [b for b in range(nb1) if ps[b] <= pB]
+    if not firsts or not lasts or firsts[0] > lasts[-1]:
+        return None, False
+    f1, l1 = firsts[0], lasts[-1]
+    # the gathering pass reads every particle: exact count below the candidate bins, exact candidates
+    b = sel_bin(v, lo1, s1, nb1)
+    base = int(np.count_nonzero(b < f1))
+    cand = v[(b >= f1) & (b <= l1)]
+    proven = (f1 == 0 or diff_of(base, prod) <= -3) and (l1 == nb1 - 1 or diff_of(base + cand.size, prod) >= 3)
+    if not proven:
+        return None, False
+    # replay with exact counts base + #{cand < cut}; cuts outside the candidate bins are decided by the bins
+    Lc, Rc, it, found, nleft = L, R, 0, False, None
+    while it < MAX_ITER:
+        cut = mid_cut(Lc, Rc)
+        c1 = int(sel_bin(cut, lo1, s1, nb1))
+        dec = -1 if c1 < f1 else (1 if c1 > l1 else 0)
+        it += 1
+        if dec == 0:
+            cnt = base + int(np.count_nonzero(cand < cut))
+            d = diff_of(cnt, prod)
+            if abs(d) < 3:
+                found, nleft = True, cnt
+                break
+            dec = 1 if d > 0 else -1
+        if dec > 0:
+            Rc = cut
+        else:
+            Lc = cut
+    if not found:
+        cut = mid_cut(Lc, Rc)
+        c1 = int(sel_bin(cut, lo1, s1, nb1))
+        if c1 < f1 or c1 > l1:
+            return None, True
+        nleft = base + int(np.count_nonzero(cand < cut))
+    return (Lc, Rc, it, found, nleft), True
+
+
+@pytest.mark.parametrize("stride,z", [(8, 5.0), (4, 5.0), (16, 6.0), (8, 1.0), (8, 0.0)])
+def test_sampled_rows_never_change_the_result(stride, z):
+    """Whatever the sample suggests, a PROVEN bracket gives the literal loop's result; an unproven one is reported (the
+    GPU then searches again with exact rows).  With the default margin random-order cells are always proven."""
+    rng = np.random.default_rng(23)
+    proven_n = total_n = 0
+    for trial in range(12):
+        n = int(rng.integers(20_000, 200_000))
+        kind = trial % 3
+        if kind == 0:
+            v = rng.random(n, dtype=f32) - f32(0.5)
+        elif kind == 1:
+            v = rng.normal(0.1, 0.03, n).clip(-0.5, 0.5).astype(f32)
+        else:
+            v = np.concatenate([rng.normal(-0.3, 0.001, n // 2), rng.random(n - n // 2) - 0.5]).astype(f32)
+            rng.shuffle(v)
+        nleaf = int(rng.choice([2, 3, 7, 64]))
+        want = literal_bisection(v, f32(-0.5), f32(0.5), v.size, nleaf)
+        got, proven = sampled_select(v, f32(-0.5), f32(0.5), nleaf, stride, z)
+        total_n += 1
+        proven_n += bool(proven)
+        if got is not None:
+            assert same(got, want), (trial, got, want)
+    if z >= 5.0:
+        assert proven_n == total_n
+
+
+def test_sampled_rows_on_sorted_cell_are_rejected_not_wrong():
+    """Positional sample of a sorted cell: the estimate is biased, the proof fails (or holds by luck) - never a wrong tree."""
+    rng = np.random.default_rng(3)
+    v = np.sort(rng.random(100_000, dtype=f32) - f32(0.5))
+    want = literal_bisection(v, f32(-0.5), f32(0.5), v.size, 2)
+    for piece in (128, 4096):
+        got, proven = sampled_select(v, f32(-0.5), f32(0.5), 2, 8, 5.0, piece=piece)
+        assert got is None or same(got, want)
+
+
+def _key(x):
+    u = np.asarray(x, f32).view(np.uint32).astype(np.uint64)
+    return np.where(u & 0x80000000, (~u) & 0xFFFFFFFF, u | 0x80000000).astype(np.uint64)
+
+
+def _unkey(k):
+    k = np.uint64(k)
+    u = (k & np.uint64(0x7FFFFFFF)) if (k & np.uint64(0x80000000)) else ((~k) & np.uint64(0xFFFFFFFF))
+    return np.array([u], np.uint64).astype(np.uint32).view(f32)[0]
+
+
+def bin_threshold(b, lo, scale, nb):
+    """sel_bin_threshold: smallest float (in the total order) whose bin is >= b, by bisection over the ordered keys."""
+    ninf, pinf = f32(-np.inf), f32(np.inf)
+    if int(sel_bin(ninf, lo, scale, nb)) >= b:
+        return ninf
+    a, e = int(_key(ninf)), int(_key(pinf))
+    while e - a > 1:
+        m = a + ((e - a) >> 1)
+        if int(sel_bin(_unkey(m), lo, scale, nb)) >= b:
+            e = m
+        else:
+            a = m
+    return _unkey(e)
+
+
+def test_value_bounds_equal_the_bin_test():
+    """first <= sel_bin(v) <= last  <=>  vLo <= v < vHi for the bisected thresholds - on values around every bin edge,
+    signed zeros, denormals, particles outside the box and a degenerate box."""
+    rng = np.random.default_rng(11)
+    for trial in range(60):
+        nb = int(rng.choice([256, 512, 2048, 8192]))
+        L = f32(rng.uniform(-0.5, 0.4))
+        R = f32(L + f32(rng.choice([1e-6, 1e-3, 0.05, 0.9])))
+        if trial % 10 == 9:
+            R = L
+        lo, scale = bin_params(L, R, nb)
+        first = int(rng.integers(0, nb))
+        last = int(rng.integers(first, nb))
+        v_lo = f32(-np.inf) if first == 0 else bin_threshold(first, lo, scale, nb)
+        v_hi = None if last + 1 >= nb else bin_threshold(last + 1, lo, scale, nb)
+        edges = (lo + (np.arange(nb + 1, dtype=f32) / max(scale, f32(1e-30)))).astype(f32) if scale > 0 else np.array([L], f32)
+        pts = np.concatenate([edges, np.nextafter(edges, f32(-np.inf)), np.nextafter(edges, f32(np.inf)),
+                              rng.uniform(float(L) - 0.2, float(R) + 0.2, 4000).astype(f32),
+                              np.array([0.0, -0.0, 1e-42, -1e-42, np.inf, -np.inf, 1e30, -1e30], f32)])
+        b = sel_bin(pts, lo, scale, nb)
+        by_bin = (b >= first) & (b <= last)
+        by_val = pts >= v_lo
+        if v_hi is not None:
+            by_val &= ~(pts >= v_hi)
+        assert np.array_equal(by_bin, by_val), (trial, nb, L, R, first, last)
+        # (a bin that not even +inf reaches gets the threshold +inf: a particle AT +inf would then be neither low nor a
+        #  candidate - such a bin is empty and never becomes `first`, sel_resolve_cell only picks occupied prefixes)
+        fin = np.isfinite(pts)
+        assert np.array_equal((b < first)[fin], (pts < v_lo)[fin])
