@@ -2295,6 +2295,7 @@ int orb_build(orb_ctx *c, uint32_t flags, orb_cell *heap_out, orb_build_stats *s
             nx.n_active0 = c->d_nactive + l * kPassSlots;
             nx.nMapTiles = ceil_div(c->nLocal, kMapTile);
             nx.tile_first = c->d_tile_first_alt;
+            nx.tile_first_cur = c->d_tile_first;
             nx.zero = c->sel.hist;
             nx.nZero = std::min(hwNext, c->selHistWords);
             splitBlocks = std::max(splitBlocks, std::max(ceil_div(nx.nMapTiles, 256), std::min<uint32_t>(ceil_div(nx.nZero, 2048), 4u * (uint32_t)c->nSM)));

@@ -1329,6 +1329,7 @@ struct NextLevel {
     uint32_t *n_active0;          // gate of the next level's first count pass
     uint32_t nMapTiles;
     uint32_t *tile_first;         // the other buffer
+    const uint32_t *tile_first_cur;   // this level's map: the parent of a tile's first particle without a search
     uint32_t *zero;               // histogram rows of the next level
     size_t nZero;
 };
@@ -1357,13 +1358,19 @@ __global__ void k_split(orb_cell *__restrict__ heap, uint32_t first, uint32_t nC
         for (size_t i = c; i < nx.nZero; i += (size_t)gridDim.x * blockDim.x) nx.zero[i] = 0u;
         if (c == 0 && nx.n_active0) *nx.n_active0 = 1u;
         if (c < nx.nMapTiles) {
-            // smallest child whose range extends beyond the tile's first particle: the parent by binary search on
-            // this level's boundaries, then left or right of its split position
+            // smallest child whose range extends beyond the tile's first particle: its parent is this level's entry of
+            // the same tile (one load instead of a binary search over the boundaries: log2(nCells) dependent loads
+            // were most of this kernel's time at the deep levels), then left or right of the split position
             const uint32_t start = c * (uint32_t)kMapTile;
-            uint32_t lo = 0, hi = nCells - 1;
-            while (lo < hi) {
-                const uint32_t m = (lo + hi) >> 1;
-                if (lv.bnd[m + 1] > start) hi = m; else lo = m + 1;
+            uint32_t lo;
+            if (nx.tile_first_cur) lo = nx.tile_first_cur[c];
+            else {
+                lo = 0;
+                uint32_t hi = nCells - 1;
+                while (lo < hi) {
+                    const uint32_t m = (lo + hi) >> 1;
+                    if (lv.bnd[m + 1] > start) hi = m; else lo = m + 1;
+                }
             }
             nx.tile_first[c] = 2u * lo + ((lv.bnd[lo] + lv.nleft_l[lo] > start) ? 0u : 1u);
         }
