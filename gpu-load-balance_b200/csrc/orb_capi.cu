@@ -81,6 +81,7 @@ struct NcclApi {
 
 constexpr int kMaxLevels = 40;
 constexpr uint32_t kSelCellCapMax = 40960;   // candidates k_sel_percell keeps in shared memory at most (176 KB with its histogram)
+constexpr uint32_t kParMaxCells = 256;    // cells of a level the parallel FINISH holds fine histograms / lists for (streaming levels have fewer)
 constexpr uint32_t kVisitRecs = 4096;     // COMPACT blocks that may leave visit records (>= resident blocks of any supported device)
 constexpr uint32_t kSelValsCap = 49152;   // values one block of the selection search stages in shared memory (192 KB)
 constexpr uint32_t kSelMrMaxCells = 2048; // several ranks: levels up to this many cells use the selection search
@@ -168,7 +169,12 @@ struct orb_ctx {
     // 160 000 candidates), block-searched cells of at least 2^16 (kSelSampleMinCell).
     uint64_t sampleMinLocal = 1ull << 25;   // ORB_SAMPLE_MIN_LOCAL
     uint64_t sampleMaxAvg = 1ull << 25;     // ORB_SAMPLE_MAX_AVG
+    bool sampleMaxAvgDefault = true;        // (not set by the environment)
     uint32_t sampleMinCell = orb::kSelSampleMinCell;   // ORB_SAMPLE_MIN_CELL: block-searched cells of fewer particles use exact rows
+    // parallel FINISH of the sampled streaming levels (orb_select.cuh SelPar): fine histogram filled by COMPACT, then
+    // k_sel_fin_a / k_sel_gather / k_sel_fin_b instead of one block walking all candidates of its cell twice
+    bool parFinish = true;         // ORB_PAR_FINISH=0: k_sel_finish<true>
+    orb::SelPar par{};
     int chunkOcc = 2;              // ORB_CHUNK_OCC: blocks per SM of the chunking the search's last pass and the cooperative partition share
                                    // (measured: the partition streams 10 % faster with 2 x 148 chunks than with 3 x 148)
     bool selLowOcc = false;        // ORB_SELECT_LOW_OCC=1: k_sel_percell with 64 registers per thread (4 x 256 / 2 x 512 threads per SM, no spills)
@@ -636,7 +642,9 @@ SelPlan sel_plan(const orb_ctx *c, uint32_t nCells, int forcedNb = 0 /* rows alr
     p.nb1 = orb::kSelBinsMin;
     while (p.nb1 < orb::kSelBinsMax && avg / (uint64_t)p.nb1 > (uint64_t)c->selBinAvg) p.nb1 <<= 1;
     if (forcedNb) p.nb1 = forcedNb;
-    p.sampleS = (sampling_on(c) && !forcedNb && (p.cellsInSmem || avg <= c->sampleMaxAvg)) ? c->sampleS : 1;
+    // (cells beyond sampleMaxAvg: their candidates would swamp a one-block FINISH; the parallel FINISH has no such limit)
+    p.sampleS = (sampling_on(c) && !forcedNb && (p.cellsInSmem || avg <= c->sampleMaxAvg || (c->parFinish && c->sampleMaxAvgDefault && nCells <= kParMaxCells)))
+                    ? c->sampleS : 1;
     if (p.sampleS > 1 && !p.cellsInSmem) {
         // sampled rows: the margin dominates the candidates, finer bins cost nothing (few atomics) - bins of <= 1024 particles
         while (p.nb1 < orb::kSelBinsMax && avg / (uint64_t)p.nb1 > 1024) p.nb1 <<= 1;
@@ -741,6 +749,7 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
                 sp.visits = c->d_visits;
                 sp.chunk = compactTiles * (uint32_t)kCountTile;
                 sp.useBounds = 1;
+                if (c->parFinish && nCells <= kParMaxCells) { sp.fine = c->par.fine; sp.lo2 = c->par.lo2; sp.sc2 = c->par.sc2; }
             }
         }
         c->levelSampled = sp.sampleS > 1;
@@ -758,8 +767,10 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
         }
         if (sp.useBounds) {     // RESOLVE as its own kernel: candidate bins and value bounds of every cell
             if ((rc = aux_begin(c, "resolve", levelIdx))) return rc;
+            SelPar prr = c->par;
+            if (!sp.fine) prr.fine = nullptr;
             CK(launch_pdl(c, k_sel_resolve, dim3(std::min<uint32_t>(nCells, 4u * (uint32_t)c->nSM)), dim3(kThreads), (size_t)nb1 * 4, c->lv, ss, nCells, nb1,
-                          0x7fffffffu, sp.sampleS, sp.z));
+                          0x7fffffffu, sp.sampleS, sp.z, prr));
             if ((rc = aux_end(c))) return rc;
             c->nOtherLaunch++;
         }
@@ -777,7 +788,17 @@ int launch_level_select(orb_ctx *c, uint32_t nCells, int slotBase, int levelIdx,
                           (float *)nullptr, 0u, sp.useBounds ? 1 : 0, no_arena(), pre, preTag, compactTiles, sp));
             if ((rc = count_event_end(c))) return rc;
         }
-        {
+        if (sp.fine) {
+            // ---- parallel FINISH: proof + scan of the fine histogram, gather of the ambiguous values, search on the short lists ----
+            const uint32_t nCompact = ceil_div(nTiles, compactTiles);
+            if ((rc = aux_begin(c, "finish", levelIdx))) return rc;
+            CK(launch_pdl(c, k_sel_fine, dim3(nCompact), dim3(kThreads), 0, (const float *)cand, sp, c->par, nCompact));
+            CK(launch_pdl(c, k_sel_fin_a, dim3(nCells), dim3(kThreads), 0, c->lv, ss, sp, c->par, nCells, nb1));
+            CK(launch_pdl(c, k_sel_gather, dim3(nCompact), dim3(kThreads), 0, (const float *)cand, sp, c->par, nCompact));
+            CK(launch_pdl(c, k_sel_fin_b, dim3(nCells), dim3(kThreads), 0, c->lv, ss, sc, c->par, nCells, c->d_err, 1, dn));
+            if ((rc = aux_end(c))) return rc;
+            c->nOtherLaunch += 3;
+        } else {
             // (private regions: the search reads the pieces in place - no staging area, three piece tables instead)
             const uint32_t finishCap = sp.visits ? 0u : candCap;
             const size_t smem = sel_search_smem_bytes(finishCap) + (sp.visits ? (size_t)3 * kSelMaxPieces * 4 : 0);
@@ -1522,6 +1543,17 @@ static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_l
     CK(cudaMalloc(&c->d_blk_left, sizeof(uint32_t) * 64 * (size_t)c->nSM));
     CK(cudaMalloc(&c->d_blk_restart, sizeof(uint32_t) * 64 * (size_t)c->nSM));
     CK(cudaMalloc(&c->d_blk_le, sizeof(uint32_t) * 64 * (size_t)c->nSM));
+    {
+        orb::SelPar &pr = c->par;
+        CK(cudaMalloc(&pr.fine, sizeof(uint32_t) * kParMaxCells * orb::kSelBins2));
+        CK(cudaMalloc(&pr.amb, sizeof(float) * kParMaxCells * orb::kSelAmbCap));
+        CK(cudaMalloc(&pr.lo2, 4 * kParMaxCells)); CK(cudaMalloc(&pr.sc2, 4 * kParMaxCells));
+        CK(cudaMalloc(&pr.f2, 4 * kParMaxCells)); CK(cudaMalloc(&pr.l2, 4 * kParMaxCells));
+        CK(cudaMalloc(&pr.base2, 4 * kParMaxCells)); CK(cudaMalloc(&pr.k2, 4 * kParMaxCells));
+        CK(cudaMalloc(&pr.v2lo, 4 * kParMaxCells)); CK(cudaMalloc(&pr.v2hi, 4 * kParMaxCells));
+        CK(cudaMalloc(&pr.ambCnt, 4 * kParMaxCells));
+        CK(cudaMemset(pr.ambCnt, 0, 4 * kParMaxCells));
+    }
     CK(cudaMalloc(&c->d_visits, sizeof(orb::SelVisitRec) * kVisitRecs));
     CK(cudaMemset(c->d_visits, 0, sizeof(orb::SelVisitRec) * kVisitRecs));
     CK(cudaMalloc(&c->d_pre, sizeof(orb::PreLeft) * 64 * (size_t)c->nSM));
@@ -1620,7 +1652,9 @@ static int create_impl(orb_ctx **out, int device, uint64_t n_local, uint32_t n_l
     const char *sml = getenv("ORB_SAMPLE_MIN_LOCAL");
     if (sml && atoll(sml) >= 0) c->sampleMinLocal = (uint64_t)atoll(sml);
     const char *sma = getenv("ORB_SAMPLE_MAX_AVG");
-    if (sma && atoll(sma) >= 1) c->sampleMaxAvg = (uint64_t)atoll(sma);
+    if (sma && atoll(sma) >= 1) { c->sampleMaxAvg = (uint64_t)atoll(sma); c->sampleMaxAvgDefault = false; }
+    const char *pfn = getenv("ORB_PAR_FINISH");
+    if (pfn) c->parFinish = atoi(pfn) != 0;
     const char *smc = getenv("ORB_SAMPLE_MIN_CELL");
     if (smc && atoll(smc) >= 4096) c->sampleMinCell = (uint32_t)atoll(smc);
     const char *cko = getenv("ORB_CHUNK_OCC");
@@ -1720,6 +1754,8 @@ int orb_destroy(orb_ctx *c) {
     cudaFree(c->d_dbg); cudaFree(c->d_dbg_blocks);
     cudaFree(c->sel.bfirst); cudaFree(c->sel.blast); cudaFree(c->sel.base); cudaFree(c->sel.ncand);
     cudaFree(c->sel.flag); cudaFree(c->d_sel_nflag); cudaFree(c->d_visits); cudaFree(c->sel.vlo); cudaFree(c->sel.vhi);
+    cudaFree(c->par.fine); cudaFree(c->par.amb); cudaFree(c->par.lo2); cudaFree(c->par.sc2); cudaFree(c->par.f2); cudaFree(c->par.l2);
+    cudaFree(c->par.base2); cudaFree(c->par.k2); cudaFree(c->par.v2lo); cudaFree(c->par.v2hi); cudaFree(c->par.ambCnt);
     cudaFree(c->d_sel_hist_g); cudaFree(c->d_sel_locbase); cudaFree(c->d_slots_g);
     for (int r = 0; r < orb::kMaxPeers; ++r)
         if (c->peerIpc[r] && c->peerX[r]) cudaIpcCloseMemHandle(c->peerX[r]);

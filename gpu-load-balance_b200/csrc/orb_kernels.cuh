@@ -2333,6 +2333,25 @@ __global__ void __launch_bounds__(kThreads) k_bbox(const float *__restrict__ x, 
                                                    const uint32_t *__restrict__ tile_first, uint32_t nCells,
                                                    uint32_t nLocal, uint32_t nTiles, uint32_t *__restrict__ bb) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Every lane keeps the running min / max of the cell its warp is in; the warp reduces and touches the cell's six
+    // words only when it moves on to another cell or runs out of tiles.  (Reducing per 128-particle piece - the first
+    // version - is 6 global atomics per piece on the SAME six words while a level has few cells: 4.8 ms for one cell
+    // of 2^27 particles, profiles/r02v_bbox.txt.)
+    uint32_t accCell = 0xffffffffu;
+    uint32_t amn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, amx[3] = {0u, 0u, 0u};
+    auto flush = [&]() {      // warp-uniform
+        if (accCell == 0xffffffffu) return;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const uint32_t wmn = __reduce_min_sync(0xffffffffu, amn[a]);
+            const uint32_t wmx = __reduce_max_sync(0xffffffffu, amx[a]);
+            if (lane == 0) {
+                if (wmn != 0xffffffffu) atomicMin(&bb[accCell * 8u + a], wmn);
+                if (wmx != 0u) atomicMax(&bb[accCell * 8u + 3 + a], wmx);
+            }
+            amn[a] = 0xffffffffu; amx[a] = 0u;
+        }
+    };
     for (uint32_t t = blockIdx.x; t < nTiles; t += gridDim.x) {
         const uint32_t t0 = t * (uint32_t)kMapTile, t1 = min(t0 + (uint32_t)kMapTile, nLocal);
         const uint32_t c = tile_first[t];
@@ -2346,7 +2365,7 @@ __global__ void __launch_bounds__(kThreads) k_bbox(const float *__restrict__ x, 
                 if (b >= cend) break;
                 const uint32_t lo = max(b, chunk), hi = min(e, cend);
                 if (hi > lo) {
-                    uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+                    if (cc != accCell) { flush(); accCell = cc; }
                     if (e0 >= lo && e0 + 4u <= hi) {
                         const float4 q[3] = {__ldg(reinterpret_cast<const float4 *>(x + e0)),
                                              __ldg(reinterpret_cast<const float4 *>(y + e0)),
@@ -2355,7 +2374,7 @@ __global__ void __launch_bounds__(kThreads) k_bbox(const float *__restrict__ x, 
                         for (int a = 0; a < 3; ++a) {
                             const float lo4 = fminf(fminf(q[a].x, q[a].y), fminf(q[a].z, q[a].w));
                             const float hi4 = fmaxf(fmaxf(q[a].x, q[a].y), fmaxf(q[a].z, q[a].w));
-                            mn[a] = f2ord(lo4); mx[a] = f2ord(hi4);
+                            amn[a] = min(amn[a], f2ord(lo4)); amx[a] = max(amx[a], f2ord(hi4));
                         }
                     } else {
 #pragma unroll
@@ -2363,19 +2382,10 @@ __global__ void __launch_bounds__(kThreads) k_bbox(const float *__restrict__ x, 
                             const uint32_t ee = e0 + j;
                             if (ee >= lo && ee < hi) {
                                 const uint32_t ux = f2ord(__ldg(x + ee)), uy = f2ord(__ldg(y + ee)), uz = f2ord(__ldg(z + ee));
-                                mn[0] = min(mn[0], ux); mx[0] = max(mx[0], ux);
-                                mn[1] = min(mn[1], uy); mx[1] = max(mx[1], uy);
-                                mn[2] = min(mn[2], uz); mx[2] = max(mx[2], uz);
+                                amn[0] = min(amn[0], ux); amx[0] = max(amx[0], ux);
+                                amn[1] = min(amn[1], uy); amx[1] = max(amx[1], uy);
+                                amn[2] = min(amn[2], uz); amx[2] = max(amx[2], uz);
                             }
-                        }
-                    }
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const uint32_t wmn = __reduce_min_sync(0xffffffffu, mn[a]);
-                        const uint32_t wmx = __reduce_max_sync(0xffffffffu, mx[a]);
-                        if (lane == 0) {
-                            atomicMin(&bb[cc * 8u + a], wmn);
-                            atomicMax(&bb[cc * 8u + 3 + a], wmx);
                         }
                     }
                 }
@@ -2384,6 +2394,7 @@ __global__ void __launch_bounds__(kThreads) k_bbox(const float *__restrict__ x, 
             }
         }
     }
+    flush();
 }
 
 __global__ void k_bbox_decode(const uint32_t *__restrict__ bb, uint32_t nCells, float *__restrict__ out6) {

@@ -136,6 +136,10 @@ struct SelPriv {
     SelVisitRec *visits;    // != null: private regions + visit records (one per COMPACT block)
     uint32_t chunk;         // particles per COMPACT block (FINISH: to find the blocks that overlap a cell)
     int useBounds;          // COMPACT with preResolved: ss.vlo / ss.vhi hold the cells' value bounds (k_sel_resolve ran)
+    // parallel FINISH (k_sel_fine / k_sel_fin_a / k_sel_gather / k_sel_fin_b): the cells' FINE histograms (kSelBins2 bins
+    // over the candidate range, bin function lo2 / sc2 published by k_sel_resolve)
+    uint32_t *fine;         // [nCells][kSelBins2], null: one-block FINISH (k_sel_finish)
+    float *lo2, *sc2;       // [nCells]
 };
 
 // block-wide exclusive scan of one value per thread (any block size up to 1024); total in `total`
@@ -576,7 +580,9 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
             uint32_t bf, bl;
             if (PRIV || preResolved) { bf = __ldcg(&ss.bfirst[c]); bl = __ldcg(&ss.blast[c]); }     // k_selx_resolve / k_sel_resolve did it for the level
             else sel_resolve_cell(lv, ss, c, nb1, candCap, publish, s_hbuf, sm.rs, bf, bl);
-            if (PRIV) { vLo = __ldcg(&ss.vlo[c]); vHi = __ldcg(&ss.vhi[c]); }
+            if (PRIV) {
+                vLo = __ldcg(&ss.vlo[c]); vHi = __ldcg(&ss.vhi[c]);
+            }
             else {
                 __syncthreads();
                 if (warp == 0) {
@@ -668,6 +674,7 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
                         below += __popc(lows & inMask);
                         warp_spill();
                         sel_warp_append<16>(v, keep, s_stage + warp * kSelWarpStage, &sm.wN[warp]);
+
                     }
                 }
                 if (ce >= t1) break;
@@ -751,11 +758,31 @@ k_sel_stream(const float *__restrict__ x, const float *__restrict__ y, const flo
     if (bs && tid == 0) bs[3] = gtimer();
 }
 
+// State of the parallel FINISH (sampled streaming levels).  One block finishing a cell walks all its candidates twice
+// (refinement histogram, then the few ambiguous values): with sampled rows that is 60 000 - 160 000 values on ONE SM,
+// 60 - 135 us.  Instead, four small kernels (binning inside COMPACT's append path was measured too: +10...35 us per pass):
+//   k_sel_fine    every COMPACT block's region again (L2), by as many blocks: the candidates binned into their cell's
+//                 fine histogram (shared-memory histogram per visit, non-empty bins added to the global row);
+//   k_sel_fin_a   one block per cell: exact `below` / candidate count from the visit records, proof of the bracket,
+//                 scan of the fine histogram -> ambiguous fine bins [f2, l2], their value bounds, count below them;
+//   k_sel_gather  every COMPACT block's region again (L2), by as many blocks: values inside the ambiguous fine bins go
+//                 to the cell's short list (a global cursor; a few hundred values per cell);
+//   k_sel_fin_b   one block per cell: the block search on that list, with the fine bins as its outer histogram.
+struct SelPar {
+    uint32_t *fine;            // [maxCells][kSelBins2] fine histograms (cleared by k_sel_resolve)
+    float *lo2, *sc2;          // [maxCells] fine bin function
+    int32_t *f2, *l2;          // [maxCells] ambiguous fine bins
+    uint32_t *base2, *k2;      // [maxCells] particles below fine bin f2; values in [f2, l2]
+    float *v2lo, *v2hi;        // [maxCells] value bounds of [f2, l2]
+    uint32_t *ambCnt;          // [maxCells] fill level of the cell's list
+    float *amb;                // [maxCells][kSelAmbCap]
+};
+
 // RESOLVE of every cell of a streaming level as a kernel of its own (single rank, between HIST and COMPACT): one block
 // per cell publishes the candidate bins and their value bounds.  COMPACT then enters a cell with four loads instead of
 // a 32 KB row, a scan and a bisection per block and cell, and needs no row buffer in shared memory.
 __global__ void __launch_bounds__(kThreads) k_sel_resolve(LevelState lv, SelState ss, uint32_t nCells, int nb1, uint32_t candCap,
-                                                           int sampleS, float sampleZ) {
+                                                           int sampleS, float sampleZ, SelPar pr /* fine == null: no parallel FINISH */) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     uint32_t *hbuf = reinterpret_cast<uint32_t *>(sel_smem);
     __shared__ SelResolveSmem rs;
@@ -769,6 +796,19 @@ __global__ void __launch_bounds__(kThreads) k_sel_resolve(LevelState lv, SelStat
             float vLo, vHi;
             sel_value_bounds_warp(bf, bl, L, sel_scale(L, lv.mR[c], nb1), nb1, vLo, vHi);
             if (threadIdx.x == 0) { ss.vlo[c] = vLo; ss.vhi[c] = vHi; }
+        }
+        if (pr.fine) {      // fine bin function over the candidate bins' interval (the range k_sel_finish refines over), cleared row
+            for (int i = threadIdx.x; i < kSelBins2; i += kThreads) pr.fine[(size_t)c * kSelBins2 + i] = 0u;
+            if (threadIdx.x == 0) {
+                const float L = lv.mL[c], s1 = sel_scale(L, lv.mR[c], nb1);
+                float a = 0.f, b = 0.f;
+                if (s1 > 0.f && bf <= bl) {
+                    a = __fadd_rn(L, __fdiv_rn((float)bf, s1));
+                    b = __fadd_rn(L, __fdiv_rn((float)(bl + 1u), s1));
+                }
+                pr.lo2[c] = a; pr.sc2[c] = sel_scale(a, b, kSelBins2);
+                pr.ambCnt[c] = 0u;
+            }
         }
     }
 }
@@ -1212,6 +1252,180 @@ __global__ void __launch_bounds__(1024) k_sel_finish(const float *__restrict__ c
         sel_block_search(vals, K, bs_, 1, L, sel_scale(L, R, nb1), nb1, (int)bf, (int)bl, hist2, amb, lv, ss, sc, c, hbmPasses, sm,
                          c == blockIdx.x ? bs : nullptr, K > cap);
         if (bs && threadIdx.x == 0 && c == blockIdx.x) bs[7] = gtimer();
+    }
+    sel_report_done(dn, ss.n_flagged);
+}
+
+// ---- parallel FINISH: fine histograms of the candidates, one block per COMPACT block ----
+__global__ void __launch_bounds__(kThreads) k_sel_fine(const float *__restrict__ cand, SelPriv sp, SelPar pr, uint32_t nBlocks) {
+    __shared__ uint32_t s_h[kSelBins2];
+    pdl_enter();
+    for (uint32_t b = blockIdx.x; b < nBlocks; b += gridDim.x) {
+        const SelVisitRec *r = sp.visits + b;
+        const uint32_t n = min(__ldcg(&r->n), (uint32_t)kSelMaxVisit);
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint32_t c = __ldcg(&r->v[j].cell), off = __ldcg(&r->v[j].off), cnt = __ldcg(&r->v[j].cnt);
+            if (!cnt) continue;         // block-uniform
+            const float lo2 = __ldcg(&pr.lo2[c]), sc2 = __ldcg(&pr.sc2[c]);
+            __syncthreads();
+            for (int i = threadIdx.x; i < kSelBins2; i += kThreads) s_h[i] = 0u;
+            __syncthreads();
+            uint32_t i = threadIdx.x;
+            for (; i + 3u * kThreads < cnt; i += 4u * kThreads) {      // four loads in flight per thread
+                float q[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) q[u] = __ldcg(cand + off + i + (uint32_t)u * kThreads);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) atomicAdd(&s_h[sel_bin(q[u], lo2, sc2, kSelBins2)], 1u);
+            }
+            for (; i < cnt; i += kThreads) atomicAdd(&s_h[sel_bin(__ldcg(cand + off + i), lo2, sc2, kSelBins2)], 1u);
+            __syncthreads();
+            for (int k = threadIdx.x; k < kSelBins2; k += kThreads) {
+                const uint32_t v = s_h[k];
+                if (v) atomicAdd(&pr.fine[(size_t)c * kSelBins2 + k], v);
+            }
+        }
+    }
+}
+
+// ---- parallel FINISH, step A ----
+__global__ void __launch_bounds__(kThreads) k_sel_fin_a(LevelState lv, SelState ss, SelPriv sp, SelPar pr, uint32_t nCells, int nb1) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_below, s_cnt, s_bad, s_base2, s_end2;
+    __shared__ int s_first, s_last;
+    pdl_enter();
+    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int per = kSelBins2 / kThreads;        // 8
+    for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
+        __syncthreads();
+        const uint32_t act = lv.active[c], b0 = lv.bnd[c], b1 = lv.bnd[c + 1];
+        const uint32_t flg = __ldcg(&ss.flag[c]);
+        const uint32_t bf = __ldcg(&ss.bfirst[c]), bl = __ldcg(&ss.blast[c]);
+        if (!act || flg || b1 == b0) continue;        // (empty cells: k_sel_fin_b searches on nothing)
+        const uint32_t k0 = b0 / sp.chunk, k1 = (b1 - 1u) / sp.chunk, nP = k1 - k0 + 1u;
+        if (tid == 0) { s_below = 0u; s_cnt = 0u; s_bad = 0u; s_first = kSelBins2; s_last = -1; s_base2 = 0u; s_end2 = 0u; }
+        __syncthreads();
+        uint32_t myBelow = 0, myCnt = 0;
+        for (uint32_t i = tid; i < nP; i += kThreads) {
+            const SelVisitRec *r = sp.visits + (k0 + i);
+            const uint32_t n = __ldcg(&r->n);
+            if (n > (uint32_t)kSelMaxVisit) s_bad = 1u;
+            for (uint32_t j = 0; j < min(n, (uint32_t)kSelMaxVisit); ++j)
+                if (__ldcg(&r->v[j].cell) == c) { myCnt += __ldcg(&r->v[j].cnt); myBelow += __ldcg(&r->v[j].below); }
+        }
+        myBelow = __reduce_add_sync(0xffffffffu, myBelow);
+        myCnt = __reduce_add_sync(0xffffffffu, myCnt);
+        if (lane == 0) { if (myBelow) atomicAdd(&s_below, myBelow); if (myCnt) atomicAdd(&s_cnt, myCnt); }
+        __syncthreads();
+        const uint32_t base = s_below, K = s_cnt;
+        SelTarget tg;
+        tg.init(lv.total[c], lv.nleaf[c]);
+        const bool proven = (bf == 0u || tg.diff(base) <= -3) && (bl + 1u >= (uint32_t)nb1 || tg.diff(base + K) >= 3);
+        // ---- scan of the fine histogram (it holds exactly the K candidates) ----
+        uint32_t h[per], sum = 0;
+#pragma unroll
+        for (int j = 0; j < per; ++j) { h[j] = __ldcg(&pr.fine[(size_t)c * kSelBins2 + tid * per + j]); sum += h[j]; }
+        uint32_t total;
+        const uint32_t excl = sel_block_scan(sum, s_w, total);
+        int myFirst = kSelBins2, myLast = -1;
+        {
+            uint32_t p = base + excl;
+#pragma unroll
+            for (int j = 0; j < per; ++j) {
+                const uint32_t pn = p + h[j];
+                const int b = tid * per + j;
+                if (tg.diff(pn) > -3) myFirst = min(myFirst, b);
+                if (tg.diff(p) < 3) myLast = max(myLast, b);
+                p = pn;
+            }
+        }
+        if (myFirst < kSelBins2) atomicMin(&s_first, myFirst);
+        if (myLast >= 0) atomicMax(&s_last, myLast);
+        __syncthreads();
+        const int f2 = s_first, l2 = s_last;
+        {
+            uint32_t p = base + excl;
+#pragma unroll
+            for (int j = 0; j < per; ++j) {
+                const int b = tid * per + j;
+                if (b == f2) s_base2 = p;
+                p += h[j];
+                if (b == l2) s_end2 = p;
+            }
+        }
+        __syncthreads();
+        const uint32_t base2 = s_base2, K2 = s_end2 - s_base2;
+        // not proven / a dropped visit record / fine histogram incomplete / massive ties: the iterative search takes the cell
+        const bool ok = proven && !s_bad && bf <= bl && total == K && f2 <= l2 && K2 <= (uint32_t)kSelAmbCap;
+        if (tid < 32) {
+            float a = 0.f, b = 0.f;
+            if (ok) sel_value_bounds_warp((uint32_t)f2, (uint32_t)l2, __ldcg(&pr.lo2[c]), __ldcg(&pr.sc2[c]), kSelBins2, a, b);
+            if (tid == 0) {
+                if (!ok) { ss.flag[c] = 1u; atomicAdd(ss.n_flagged, 1u); }
+                pr.f2[c] = f2; pr.l2[c] = l2; pr.base2[c] = base2; pr.k2[c] = K2;
+                pr.v2lo[c] = ok ? a : __int_as_float(0x7f800000);       // (flagged: empty range, k_sel_gather appends nothing)
+                pr.v2hi[c] = ok ? b : __int_as_float(0xff800000);
+            }
+        }
+    }
+}
+
+// ---- step B: every COMPACT block's pieces again; values inside the ambiguous fine bins of their cell go to its list ----
+__global__ void __launch_bounds__(kThreads) k_sel_gather(const float *__restrict__ cand, SelPriv sp, SelPar pr, uint32_t nBlocks) {
+    pdl_enter();
+    for (uint32_t b = blockIdx.x; b < nBlocks; b += gridDim.x) {
+        const SelVisitRec *r = sp.visits + b;
+        const uint32_t n = min(__ldcg(&r->n), (uint32_t)kSelMaxVisit);
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint32_t c = __ldcg(&r->v[j].cell), off = __ldcg(&r->v[j].off), cnt = __ldcg(&r->v[j].cnt);
+            const float vLo = __ldcg(&pr.v2lo[c]), vHi = __ldcg(&pr.v2hi[c]);
+            float *dst = pr.amb + (size_t)c * kSelAmbCap;
+            uint32_t i = threadIdx.x;
+            for (; i + 3u * kThreads < cnt; i += 4u * kThreads) {      // four loads in flight per thread
+                float q[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) q[u] = __ldcg(cand + off + i + (uint32_t)u * kThreads);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (sel_is_cand(q[u], vLo, vHi)) { const uint32_t p = atomicAdd(&pr.ambCnt[c], 1u); if (p < (uint32_t)kSelAmbCap) dst[p] = q[u]; }
+            }
+            for (; i < cnt; i += kThreads) {
+                const float q = __ldcg(cand + off + i);
+                if (sel_is_cand(q, vLo, vHi)) { const uint32_t p = atomicAdd(&pr.ambCnt[c], 1u); if (p < (uint32_t)kSelAmbCap) dst[p] = q; }
+            }
+        }
+    }
+}
+
+// ---- step C: the block search of every cell on its short list; the fine bins are the search's outer histogram ----
+__global__ void __launch_bounds__(kThreads) k_sel_fin_b(LevelState lv, SelState ss, SelCtl sc, SelPar pr, uint32_t nCells, int *__restrict__ err,
+                                                         int hbmPasses, SelDone dn) {
+    __shared__ float s_vals[kSelAmbCap + 4];
+    __shared__ uint32_t s_hist2[kSelBins2];
+    __shared__ float s_amb[kSelAmbCap];
+    __shared__ SelSearchSmem sm;
+    pdl_enter();
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(sc.passes_out, hbmPasses);
+    for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
+        __syncthreads();
+        const uint32_t act = lv.active[c], b0 = lv.bnd[c], b1 = lv.bnd[c + 1];
+        if (!act) continue;
+        if (b1 == b0) {     // empty cell: the search on nothing finds the cut at once
+            if (tid == 0) ss.flag[c] = 0u;
+            sel_block_search(s_vals, 0u, 0u, 0, 0.f, 0.f, 1, 0, 0, s_hist2, s_amb, lv, ss, sc, c, hbmPasses, sm);
+            continue;
+        }
+        if (__ldcg(&ss.flag[c])) continue;
+        const uint32_t K2 = __ldcg(&pr.k2[c]), got = __ldcg(&pr.ambCnt[c]);
+        if (got != K2 || K2 > (uint32_t)kSelAmbCap) {     // cannot happen: the fine histogram and the gather use one bin function
+            if (tid == 0) atomicExch(err, ORB_ERR_STATE);
+            continue;
+        }
+        for (uint32_t i = tid; i < K2; i += kThreads) s_vals[i] = __ldcg(pr.amb + (size_t)c * kSelAmbCap + i);
+        __syncthreads();
+        sel_block_search(s_vals, K2, __ldcg(&pr.base2[c]), 1, __ldcg(&pr.lo2[c]), __ldcg(&pr.sc2[c]), kSelBins2, __ldcg(&pr.f2[c]), __ldcg(&pr.l2[c]),
+                         s_hist2, s_amb, lv, ss, sc, c, hbmPasses, sm);
     }
     sel_report_done(dn, ss.n_flagged);
 }

@@ -178,18 +178,19 @@ def test_signed_zero_coordinates(orb, oracle):
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
-@pytest.mark.parametrize("stride,z", [("1", "6"), ("8", "6"), ("4", "5"), ("8", "0.25"), ("16", "0")])
+@pytest.mark.parametrize("stride,z,par", [("1", "6", "1"), ("8", "6", "1"), ("8", "5", "0"), ("4", "5", "1"), ("8", "0.25", "1"), ("8", "0.25", "0"), ("16", "0", "1")])
 @pytest.mark.parametrize("n,d,gen", [(1 << 22, 1 << 11, "uniform"), (1 << 21, 1 << 6, "uniform"), (1 << 22, 1 << 10, "gaussian"),
                                      (1 << 21, 1 << 9, "plummer"), (3_000_017, 1 << 7, "uniform"), (1 << 23, 1 << 8, "uniform")])
-def test_build_bit_exact_with_sampled_rows(orb, oracle, n, d, gen, stride, z, monkeypatch):
+def test_build_bit_exact_with_sampled_rows(orb, oracle, n, d, gen, stride, z, par, monkeypatch):
     """Sampled histogram rows (ORB_SAMPLE_STRIDE > 1, the default): HIST bins a sample, RESOLVE widens the candidate bins by
     z standard deviations, the gathering pass counts exactly and the bracket must be proven by the exact numbers.  The
     tree never depends on the sample: stride 1 (exact rows), the default, and margins far too small (z = 0.25, z = 0:
     brackets fail, k_sel_percell searches again with exact rows, k_sel_finish leaves the cell to the iterative search)
-    all give the oracle's tree, ranges and particle order - streaming levels (private candidate regions + gather) and
-    one-block-per-cell levels."""
+    all give the oracle's tree, ranges and particle order - streaming levels (private candidate regions, finished in
+    parallel or by one block per cell) and one-block-per-cell levels."""
     monkeypatch.setenv("ORB_SAMPLE_STRIDE", stride)
     monkeypatch.setenv("ORB_SAMPLE_Z", z)
+    monkeypatch.setenv("ORB_PAR_FINISH", par)                # 1: fine histogram + k_sel_fin_a / gather / fin_b, 0: k_sel_finish<true>
     monkeypatch.setenv("ORB_SAMPLE_MIN_LOCAL", "0")          # (by default only builds of >= 2^25 particles per GPU sample,
     monkeypatch.setenv("ORB_SAMPLE_MAX_AVG", str(1 << 30))   #  and only cells of <= 2^25 particles)
     x, y, z_ = orb.generate_uniform(n) if gen == "uniform" else orb.generate_clustered(n, gen)

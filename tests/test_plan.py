@@ -97,17 +97,18 @@ def test_automatic_prefuse_policy(orb):
 
 def test_sampled_rows_policy(orb):
     """Sampled histogram rows: one rank, builds of at least 2^25 particles per GPU; streaming levels
-    whose cells hold at most 2^25 particles, block-searched cells of at least 2^16; never with several ranks, never
+    (with the one-block FINISH, ORB_PAR_FINISH=0, only where cells hold at most 2^25 particles), block-searched cells of
+    at least 2^16; never with several ranks, never
     where the partition-built rows are forced."""
     c3 = [orb.plan_level(1 << 27, 1 << l, 1 << 16) for l in range(0, 15)]
-    assert [p.sample_stride for p in c3] == [1, 1] + [8] * 10 + [1, 1, 1]
+    assert [p.sample_stride for p in c3] == [8] * 12 + [1, 1, 1]
     assert [p.search for p in c3] == [1] * 7 + [2] * 8
     # the sampled streaming levels bin finely (the margin, not the bin width, sets the number of candidates)
-    assert all(p.hist_bins == 8192 for p in c3[2:5]) and all(p.hist_words == (1 << l) * p.hist_bins for l, p in enumerate(c3[:7]))
+    assert all(p.hist_bins == 8192 for p in c3[:5]) and all(p.hist_words == (1 << l) * p.hist_bins for l, p in enumerate(c3[:7]))
     assert all(p.cand_cap <= 49152 for p in c3)
     c2 = [orb.plan_level(1 << 24, 1 << l, 1 << 12) for l in range(0, 11)]
     assert all(p.sample_stride == 1 for p in c2)
     c4 = [orb.plan_level(1 << 26, 1 << l, 1 << 14) for l in range(0, 13)]
-    assert [p.sample_stride for p in c4] == [1] + [8] * 10 + [1, 1]
+    assert [p.sample_stride for p in c4] == [8] * 11 + [1, 1]
     assert all(orb.plan_level(1 << 27, 1 << l, 1 << 16, n_ranks=2).sample_stride <= 1 for l in range(0, 15))
     assert all(orb.plan_level(1 << 27, 1 << l, 1 << 16, prefuse=1).sample_stride <= 1 for l in range(0, 15))
