@@ -1,0 +1,130 @@
+"""Size-independent properties of the CPU oracle (oracle/orb_oracle.c) on random small inputs (hypothesis): what any
+ORB build of the reference's o=0 path guarantees whatever the input - the same properties the full-size GPU tests
+check where a bit-exact CPU answer would take too long (tests/test_gpu_parity.py::test_full_size_*).
+
+Reference semantics: orbit.cpp:146-250 (bisection, split), partition.cpp:30-60 (Hoare), count.cpp:8-30."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+SET = dict(max_examples=60, derandomize=True, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+
+
+def columns(seed: int, n: int, grid: int):
+    """three float32 columns in [-0.5, 0.5); grid > 0 snaps x (and partly y) to a lattice so that cuts meet ties"""
+    rng = np.random.default_rng(seed)
+    x = rng.random(n, dtype=np.float32) - np.float32(0.5)
+    y = rng.random(n, dtype=np.float32) - np.float32(0.5)
+    z = rng.random(n, dtype=np.float32) - np.float32(0.5)
+    if grid:
+        x = (np.floor(x * grid) / grid).astype(np.float32)
+        y[::3] = (np.floor(y[::3] * grid) / grid).astype(np.float32)
+    return x, y, z
+
+
+def children(c):
+    return 2 * (int(c["id"]) + 1) - 1, 2 * (int(c["id"]) + 1)           # cell.h:49-55
+
+
+@settings(**SET)
+@given(seed=st.integers(0, 2**31 - 1), n=st.integers(64, 6000), logd=st.integers(1, 6), grid=st.sampled_from([0, 0, 16, 64]),
+       full=st.booleans(), ties=st.sampled_from(["canonical", "hoare"]))
+def test_build_invariants(oracle, seed, n, logd, grid, full, ties):
+    d = 1 << logd
+    if ties == "hoare":
+        # The verbatim Hoare scan reads past a cell whose particles are ALL left of the cut and may then put the boundary
+        # one past the cell's end (partition.cpp:38: the coordinate is read before `i <= endInd` is tested) - a quirk
+        # the oracle keeps (tests/test_oracle_vs_reference.py) and that needs a cell of a few particles whose cut was
+        # never found.  Keep the cells populated here; the degenerate sizes run in canonical mode below.
+        n = max(n, 32 * d)
+    x, y, z = columns(seed, n, grid)
+    mode = oracle.TIES_CANONICAL if ties == "canonical" else oracle.TIES_HOARE
+    r = oracle.build(x, y, z, d, ties=mode, full_levels=full)
+    s = r["stats"]
+    levels = logd if full else logd - 1                                    # orbit.cpp:102: the reference stops one level early
+    assert s.n_levels == levels
+    assert all(1 <= s.iters[l] <= 32 for l in range(levels))               # orbit.cpp:149: at most 32 bisection steps
+    # the particles are only ever permuted
+    assert oracle.set_hash(r["x"], r["y"], r["z"]) == oracle.set_hash(x, y, z)
+    rng, heap, cols = r["ranges"][0], r["heap"], (r["x"], r["y"], r["z"])
+    assert tuple(rng[0]) == (0, n)
+    n_split = (1 << levels) - 1
+    for c in heap[:n_split]:
+        lid, rid = children(c)
+        b, e = (int(v) for v in rng[int(c["id"])])
+        (lb, le), (rb, re) = ((int(v) for v in rng[k]) for k in (lid, rid))
+        assert (lb, re) == (b, e) and le == rb and b <= le <= e           # partition.cpp:54-60: the children tile the parent
+        # split of the leaf budget (cell.h:78-100) and of the box along the cut axis
+        assert int(heap[lid]["nLeafCells"]) + int(heap[rid]["nLeafCells"]) == int(c["nLeafCells"])
+        assert int(heap[lid]["nLeafCells"]) == (int(c["nLeafCells"]) + 1) // 2
+        ax, cut = int(c["cutAxis"]), oracle.get_cut(c)
+        assert 0 <= ax <= 2 and c["lower"][ax] <= cut <= c["upper"][ax]
+        assert heap[lid]["upper"][ax] == cut and heap[rid]["lower"][ax] == cut
+        col = cols[ax]
+        if ties == "canonical":                                           # stable x < cut
+            assert (col[lb:le] < cut).all() and (col[rb:re] >= cut).all()
+        elif le < e:                                                      # Hoare: both scans stop on == cut (partition.cpp:38,43)
+            assert (col[lb:le] <= cut).all() and (col[rb:re] >= cut).all()
+        # a found cut balances the GLOBAL counts to |diff| < 3 (orbit.cpp:204-207); the canonical split IS the count
+        if ties == "canonical" and c["foundCut"]:
+            ratio = np.float32(np.ceil(int(c["nLeafCells"]) / 2.0) / int(c["nLeafCells"]))
+            diff = int(np.float32(le - lb) - np.float32(e - b) * ratio)
+            assert abs(diff) < 3
+    # the deepest ranges tile [0, n) in id order
+    first = (1 << levels) - 1
+    leaves = rng[first: first + (1 << levels)].astype(np.int64)
+    assert leaves[0, 0] == 0 and leaves[-1, 1] == n and (leaves[1:, 0] == leaves[:-1, 1]).all()
+
+
+@settings(**SET)
+@given(seed=st.integers(0, 2**31 - 1), n=st.integers(256, 6000), logd=st.integers(2, 6), shards=st.integers(2, 5))
+def test_tree_does_not_depend_on_the_sharding(oracle, seed, n, logd, shards):
+    """Counts are integer sums over shards (countLeft.cpp:44-53), so the cells are the same for any sharding, and each
+    leaf holds the same particles as a set, wherever the shard boundaries fall (canonical ties)."""
+    x, y, z = columns(seed, n, 32)
+    cutpts = np.sort(np.random.default_rng(seed ^ 0x5bd1e995).integers(0, n + 1, shards - 1))
+    off = np.concatenate([[0], cutpts, [n]]).astype(np.uint64)
+    one = oracle.build(x, y, z, 1 << logd, ties=oracle.TIES_CANONICAL)
+    many = oracle.build(x, y, z, 1 << logd, ties=oracle.TIES_CANONICAL, n_shards=shards, shard_off=off)
+    assert many["heap"].tobytes() == one["heap"].tobytes()
+    assert list(many["stats"].iters[:logd]) == list(one["stats"].iters[:logd])
+    sizes = (many["ranges"][:, :, 1].astype(np.int64) - many["ranges"][:, :, 0]).sum(axis=0)
+    assert np.array_equal(sizes, one["ranges"][0][:, 1].astype(np.int64) - one["ranges"][0][:, 0])
+    levels = logd - 1
+    first = (1 << levels) - 1
+    for leaf in range(first, first + (1 << levels)):
+        b, e = (int(v) for v in one["ranges"][0][leaf])
+        want = np.sort(oracle.particle_hash(one["x"][b:e], one["y"][b:e], one["z"][b:e]))
+        got = []
+        for s_ in range(shards):                      # a shard's ranges index its own slice (lcl->particles of that thread)
+            o = int(off[s_])
+            sb, se = (o + int(v) for v in many["ranges"][s_][leaf])
+            got.append(oracle.particle_hash(many["x"][sb:se], many["y"][sb:se], many["z"][sb:se]))
+        assert np.array_equal(np.sort(np.concatenate(got)), want)
+
+
+@settings(**SET)
+@given(seed=st.integers(0, 2**31 - 1), n=st.integers(64, 4000), logd=st.integers(1, 6))
+def test_tie_modes_agree_when_no_particle_sits_on_a_cut(oracle, seed, n, logd):
+    """SURVEY.md 8(c) tie contract (2): with zero tie particles the verbatim Hoare partition and the canonical one
+    produce the same cells and the same ranges (the particle ORDER inside a cell may differ)."""
+    n = max(n, 32 << logd)            # populated cells: see the note on the Hoare scan's overrun in test_build_invariants
+    x, y, z = columns(seed, n, 0)
+    h = oracle.build(x, y, z, 1 << logd, ties=oracle.TIES_HOARE)
+    c = oracle.build(x, y, z, 1 << logd, ties=oracle.TIES_CANONICAL)
+    if h["stats"].tie_particles == 0 and c["stats"].tie_particles == 0:
+        assert h["heap"].tobytes() == c["heap"].tobytes()
+        assert np.array_equal(h["ranges"], c["ranges"])
+    # the per-level iteration counts depend on counts only while the cells hold the same sets
+    assert h["stats"].iters[0] == c["stats"].iters[0]
+
+
+@pytest.mark.parametrize("n,d", [(1, 2), (2, 2), (3, 4), (5, 8), (64, 64)])
+def test_tiny_and_ragged_cells(oracle, n, d):
+    """fewer particles than leaf cells: empty children appear, nothing is lost, ranges still tile"""
+    x, y, z = columns(n * 7 + d, n, 0)
+    r = oracle.build(x, y, z, d, ties=oracle.TIES_CANONICAL, full_levels=True)
+    assert oracle.set_hash(r["x"], r["y"], r["z"]) == oracle.set_hash(x, y, z)
+    leaves = r["ranges"][0][d - 1: 2 * d - 1].astype(np.int64)
+    assert leaves[0, 0] == 0 and leaves[-1, 1] == n and (leaves[1:, 0] == leaves[:-1, 1]).all()
+    assert ((leaves[:, 1] - leaves[:, 0]) >= 0).all()
