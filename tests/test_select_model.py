@@ -459,3 +459,106 @@ def test_value_bounds_equal_the_bin_test():
         #  candidate - such a bin is empty and never becomes `first`, sel_resolve_cell only picks occupied prefixes)
         fin = np.isfinite(pts)
         assert np.array_equal((b < first)[fin], (pts < v_lo)[fin])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Parallel FINISH of the sampled streaming levels (csrc/orb_select.cuh: k_sel_resolve publishes the FINE bin function
+# over the candidate bins' interval, k_sel_fine bins the candidates, k_sel_fin_a proves the bracket and scans the fine
+# histogram, k_sel_gather collects the values of the ambiguous fine bins, k_sel_fin_b searches with the fine bins as
+# the only outer histogram).
+# ---------------------------------------------------------------------------------------------------------------
+def parallel_finish(v, L, R, nleaf, stride, z, nb1=1024, nb2=2048, amb_cap=2048, piece=128):
+    """Returns (result or None, why): None + "unproven" / "ties" is what the kernels flag for the iterative search."""
+    n = v.size
+    prod = make_prod(n, nleaf)
+    lo1, s1 = bin_params(L, R, nb1)
+    idx = np.arange(n)
+    smp = v[(idx // piece) % stride == 0]
+    ns = smp.size
+    ps = np.concatenate([[0], np.cumsum(np.bincount(sel_bin(smp, lo1, s1, nb1), minlength=nb1))])
+    pA = next(p for p in range(ns + 1) if diff_of(sample_bound(p, ns, n, z, True), prod) > -3)
+    pB = next(p for p in range(ns, -1, -1) if diff_of(sample_bound(p, ns, n, z, False), prod) < 3)
+    firsts = [b for b in range(nb1) if ps[b + 1] >= pA]
+    lasts = [b for b in range(nb1) if ps[b] <= pB]
+    if not firsts or not lasts or firsts[0] > lasts[-1]:
+        return None, "unproven"
+    f1, l1 = firsts[0], lasts[-1]
+    # k_sel_resolve: fine bin function over [L + f1 / s1, L + (l1 + 1) / s1) - NOT the exact value bounds of the candidate
+    # bins; candidates a rounding step outside it clamp to fine bin 0 / nb2 - 1, which keeps the function monotone
+    if s1 > 0:
+        a, bnd = f32(L + f32(f32(f1) / s1)), f32(L + f32(f32(l1 + 1) / s1))
+    else:
+        a, bnd = f32(0), f32(0)
+    lo2, s2 = bin_params(a, bnd, nb2)
+    # COMPACT: exact count below the candidate bins, the candidates themselves (membership by bin = by value bounds)
+    b1 = sel_bin(v, lo1, s1, nb1)
+    base = int(np.count_nonzero(b1 < f1))
+    cand = v[(b1 >= f1) & (b1 <= l1)]
+    K = cand.size
+    # k_sel_fin_a: proof with the exact numbers, scan of the fine histogram
+    if not ((f1 == 0 or diff_of(base, prod) <= -3) and (l1 == nb1 - 1 or diff_of(base + K, prod) >= 3)):
+        return None, "unproven"
+    b2 = sel_bin(cand, lo2, s2, nb2)
+    p2 = np.concatenate([[0], np.cumsum(np.bincount(b2, minlength=nb2))])
+    f2 = next((b for b in range(nb2) if diff_of(base + p2[b + 1], prod) > -3), nb2)
+    l2 = next((b for b in range(nb2 - 1, -1, -1) if diff_of(base + p2[b], prod) < 3), -1)
+    if f2 > l2 or p2[l2 + 1] - p2[f2] > amb_cap:
+        return None, "ties"
+    base2 = base + int(p2[f2])
+    amb = cand[(b2 >= f2) & (b2 <= l2)]          # k_sel_gather (by the value bounds of [f2, l2]; same set)
+    # k_sel_fin_b: replay; a cut is decided by its FINE bin alone unless that bin is ambiguous
+    Lc, Rc, it, found, nleft = L, R, 0, False, None
+    while it < MAX_ITER:
+        cut = mid_cut(Lc, Rc)
+        c2 = int(sel_bin(cut, lo2, s2, nb2))
+        dec = -1 if c2 < f2 else (1 if c2 > l2 else 0)
+        it += 1
+        if dec == 0:
+            cnt = base2 + int(np.count_nonzero(amb < cut))
+            d = diff_of(cnt, prod)
+            if abs(d) < 3:
+                found, nleft = True, cnt
+                break
+            dec = 1 if d > 0 else -1
+        if dec > 0:
+            Rc = cut
+        else:
+            Lc = cut
+    if not found:
+        cut = mid_cut(Lc, Rc)
+        c2 = int(sel_bin(cut, lo2, s2, nb2))
+        if c2 < f2 or c2 > l2:
+            return None, "final cut outside the ambiguous bins"
+        nleft = base2 + int(np.count_nonzero(amb < cut))
+    return (Lc, Rc, it, found, nleft), "ok"
+
+
+@pytest.mark.parametrize("stride,z", [(8, 5.0), (16, 6.0), (8, 0.5)])
+def test_parallel_finish_never_changes_the_result(stride, z):
+    """The fine bins alone decide every cut outside [f2, l2]: correct because the proof puts diff(base) <= -3 below the
+    candidate range and diff(base + K) >= 3 above it, so a cut that leaves the candidate range on either side has the
+    decision of the clamped fine bin.  Whatever the sample, a result that is returned equals the literal loop's."""
+    rng = np.random.default_rng(41)
+    returned = 0
+    for trial in range(14):
+        n = int(rng.integers(30_000, 250_000))
+        kind = trial % 4
+        if kind == 0:
+            v = rng.random(n, dtype=f32) - f32(0.5)
+        elif kind == 1:
+            v = rng.normal(-0.2, 0.02, n).clip(-0.5, 0.5).astype(f32)
+        elif kind == 2:
+            v = np.concatenate([rng.normal(0.3, 0.0005, n // 3), rng.random(n - n // 3) - 0.5]).astype(f32)
+            rng.shuffle(v)
+        else:                                   # a lattice: ties inside the ambiguous bins
+            v = (np.floor((rng.random(n) - 0.5) * 4096) / 4096).astype(f32)
+        nleaf = int(rng.choice([2, 3, 5, 64, 4097]))
+        L, R = f32(-0.5), f32(0.5)
+        if trial % 5 == 4:                      # margins narrower than the data (a cell deep in the tree)
+            L, R = f32(-0.25), f32(0.375)
+        want = literal_bisection(v, L, R, v.size, nleaf)
+        got, why = parallel_finish(v, L, R, nleaf, stride, z)
+        if got is not None:
+            returned += 1
+            assert same(got, want), (trial, why, got, want)
+    assert returned >= (8 if z >= 5.0 else 1)
