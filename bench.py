@@ -465,7 +465,8 @@ def run_leg(job: Job, name: str, args, primary: bool):
                 floor.append(time.perf_counter() - t0)
         floor_s = job.reduce(sum(floor) / len(floor), "max")
         e2e = {"value": passes_job / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "copy_floor_ms": floor_s * 1e3, "copy_floor_note": "pinned H2D + D2H of the particle columns alone, all ranks at once, max over ranks"}
+               "copy_floor_ms": floor_s * 1e3, "copy_floor_note": "pinned H2D + D2H of the particle columns alone, all ranks at once, max over ranks",
+               "bytes_note": f"per rank ({world} rank(s) copy at once: the job moves {world} x these bytes per step)"}
 
     # ---- the same build in the reference-exact tie mode (Hoare emulation)
     hoare = None
